@@ -1,0 +1,127 @@
+"""Pin oracle/spn_oracle.py (numpy restatement) against the fixtures produced by
+running the reference's own modules (tests/golden/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import spn_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PP = sorted(glob.glob(os.path.join(GOLDEN, "pp_*.npz")) + glob.glob(os.path.join(GOLDEN, "lrru_*.npz")))
+NL = sorted(glob.glob(os.path.join(GOLDEN, "nlspn_*.npz")))
+
+
+def _close(a, b, rtol, atol, what):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    assert (err <= tol).all(), f"{what}: max abs err {err.max():.3e}, max |ref| {np.abs(b).max():.3e}"
+
+
+def test_fixtures_present():
+    assert len(PP) == 10 and len(NL) == 5
+
+
+@pytest.mark.parametrize("path", PP, ids=[os.path.basename(p)[:-4] for p in PP])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_postprocessor_matches_reference(path, prec):
+    z = np.load(path)
+    dt = np.float64 if prec == "f64" else np.float32
+    # fp64: algebraic identity with the reference; fp32: rounding-order noise only
+    rtol, atol = (1e-12, 1e-12) if prec == "f64" else (1e-5, 2e-6)
+    init, weight, offset, gout = (z["in_" + k].astype(dt) for k in ("init", "weight", "offset", "grad_out"))
+    w9, b1 = z["in_w"].astype(dt).reshape(9), z["in_b"].astype(dt)[0]
+    mode, scale = int(z["norm_mode"]), float(z["scale"])
+    out = O.postprocessor_forward(init, weight, offset, w9, b1, mode, scale)
+    _close(out, z[prec + "_out"], rtol, atol, "out")
+    g = O.postprocessor_backward(gout, init, weight, offset, w9, mode, scale)
+    for k in ("grad_init", "grad_weight", "grad_offset", "grad_w", "grad_b"):
+        ref = z[f"{prec}_{k}"]
+        scale_k = max(1.0, float(np.abs(ref).max()))
+        _close(g[k], ref, rtol, atol * scale_k * (50 if k in ("grad_w", "grad_b") and prec == "f32" else 1), k)
+
+
+@pytest.mark.parametrize("path", NL, ids=[os.path.basename(p)[:-4] for p in NL])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_nlspn_forward_matches_reference(path, prec):
+    z = np.load(path)
+    dt = np.float64 if prec == "f64" else np.float32
+    rtol, atol = (1e-12, 1e-12) if prec == "f64" else (1e-5, 2e-6)
+    conv_out = z[prec + "_conv_out"].astype(dt)
+    conf = z["in_confidence"].astype(dt)
+    gamma = z["in_gamma"].astype(dt)[0]
+    offset, aff = O.nlspn_offset_affinity(conv_out, conf, gamma, affinity=str(z["cfg_affinity"]),
+                                          conf_prop=bool(z["cfg_conf_prop"]), legacy=bool(z["cfg_legacy"]))
+    _close(offset, z[prec + "_offset"], rtol, atol, "offset")
+    _close(aff, z[prec + "_aff"], rtol, atol, "aff")
+    feat, feats = O.nlspn_propagate(z["in_feat_init"].astype(dt), offset, aff, int(z["cfg_T"]),
+                                    feat_fix=z["in_feat_fix"].astype(dt),
+                                    preserve_input=bool(z["cfg_preserve_input"]))
+    _close(np.stack(feats), z[prec + "_list_feat"], rtol, atol, "list_feat")
+    _close(feat, z[prec + "_feat"], rtol, atol, "feat")
+
+
+def test_known_answers():
+    """Analytic cases from SURVEY.md §8c."""
+    rng = np.random.default_rng(0)
+    B, H, W = 2, 7, 9
+    init = rng.random((B, 1, H, W))
+    zero_off = np.zeros((B, 18, H, W))
+    ones9 = np.ones(9)
+    # (i) offsets 0, constant weight, residual => m == 0 => out = b + scale*init
+    wconst = np.full((B, 9, H, W), 0.3)
+    out = O.postprocessor_forward(init, wconst, zero_off, ones9, 0.25, O.NORM_RESIDUAL, 0.5)
+    np.testing.assert_allclose(out, 0.25 + 0.5 * init, atol=1e-14)
+    # (ii) offsets 0, sum mode, w == 1 => zero-padded 3x3 box mean
+    out = O.postprocessor_forward(init, wconst, zero_off, ones9, 0.0, O.NORM_SUM)
+    pad = np.pad(init[:, 0], ((0, 0), (1, 1), (1, 1)))
+    box = sum(pad[:, i:i + H, j:j + W] for i in range(3) for j in range(3)) / 9
+    np.testing.assert_allclose(out[:, 0], box, atol=1e-14)
+    # (iii) integer offsets => shifted copies: only tap 4 active, offset (+2,-1)
+    off = zero_off.copy()
+    off[:, 8], off[:, 9] = 2.0, -1.0
+    m = np.zeros((B, 9, H, W)); m[:, 4] = 1
+    out = O.deform_gather(init, off, m, ones9, 0.0)
+    exp = np.zeros((B, H, W)); exp[:, :H - 2, 1:] = init[:, 0, 2:, :W - 1]
+    np.testing.assert_allclose(out[:, 0], exp, atol=1e-14)
+    # (iv) sample at h in (H-1,H): only the top row of the pair is valid; h >= H => 0
+    off = zero_off.copy(); off[:, 8] = 0.25
+    out = O.deform_gather(init, off, m, ones9, 0.0)
+    np.testing.assert_allclose(out[:, 0, H - 1], 0.75 * init[:, 0, H - 1], atol=1e-14)
+    off[:, 8] = 1.0
+    out = O.deform_gather(init, off, m, ones9, 0.0)
+    np.testing.assert_allclose(out[:, 0, H - 1], 0.0, atol=0)
+    # (v) NLSPN with zero conv output => offsets 0, aff 0, centre 1 => identity for all T
+    conv_out = np.zeros((B, 24, H, W))
+    offset, aff = O.nlspn_offset_affinity(conv_out, rng.random((B, 1, H, W)), 4.0)
+    assert (offset == 0).all() and (aff[:, 4] == 1).all() and (np.delete(aff, 4, 1) == 0).all()
+    feat, feats = O.nlspn_propagate(init, offset, aff, 6)
+    for f in feats:
+        np.testing.assert_array_equal(f, init)
+
+
+def test_backward_is_gradient_of_forward():
+    """Central finite differences in fp64 on the restatement itself."""
+    rng = np.random.default_rng(1)
+    B, H, W = 1, 5, 6
+    init = rng.random((B, 1, H, W)); weight = rng.random((B, 9, H, W)) + 0.1
+    offset = rng.normal(0, 1.5, (B, 18, H, W)); gout = rng.normal(size=(B, 1, H, W))
+    w9 = 1 + 0.1 * rng.normal(size=9); b1 = 0.1
+    for mode in (O.NORM_NONE, O.NORM_RESIDUAL, O.NORM_SUM):
+        g = O.postprocessor_backward(gout, init, weight, offset, w9, mode, 0.7)
+        f = lambda i, wt, o, w_: (O.postprocessor_forward(i, wt, o, w_, b1, mode, 0.7) * gout).sum()
+        eps = 1e-6
+        for name, arr, grad in (("init", init, g["grad_init"]), ("weight", weight, g["grad_weight"]),
+                                ("offset", offset, g["grad_offset"])):
+            idx = [tuple(rng.integers(0, s) for s in arr.shape) for _ in range(12)]
+            for ix in idx:
+                ap, am = arr.copy(), arr.copy()
+                ap[ix] += eps; am[ix] -= eps
+                args_p = dict(init=init, weight=weight, offset=offset); args_m = dict(args_p)
+                args_p[name], args_m[name] = ap, am
+                num = (f(args_p["init"], args_p["weight"], args_p["offset"], w9)
+                       - f(args_m["init"], args_m["weight"], args_m["offset"], w9)) / (2 * eps)
+                assert abs(num - grad[ix]) < 1e-6 * max(1, abs(num)), (mode, name, ix, num, grad[ix])
