@@ -1,0 +1,70 @@
+"""ctypes binding of libjspsr_spn.so (the C ABI in include/jspsr_spn.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError
+is raised with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_float, c_int, c_size_t, c_uint, c_void_p
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libjspsr_spn.so")
+
+NORM_NONE, NORM_RESIDUAL, NORM_SUM = 0, 1, 2
+F32, BF16 = 0, 1
+AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
+BWD_ACCUMULATE = 1
+
+# name -> (restype, argtypes); mirrors include/jspsr_spn.h one to one
+_SIGNATURES = {
+    "jspsr_version": (c_int, []),
+    "jspsr_last_error": (ctypes.c_char_p, []),
+    "jspsr_spn_workspace_bytes": (c_size_t, []),
+    "jspsr_spn_forward": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "jspsr_spn_backward": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
+    "jspsr_spn_forward_strip": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_float, c_int, c_void_p, c_void_p]),
+    "jspsr_spn_offset_absmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "jspsr_spn_iterate": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "jspsr_nlspn_affinity_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "jspsr_nlspn_affinity_backward": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
+    "jspsr_spn_host_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "jspsr_spn_forward_host": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_int]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", _CSRC, "-j8"] + ([] if verbose else ["-s"])
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C jspsr_b200/csrc`). jspsr_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().jspsr_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")

@@ -1,0 +1,253 @@
+// C ABI of libjspsr_spn.so (see include/jspsr_spn.h): argument validation, TMA
+// descriptor encoding, launches.  No torch types, no allocation, no synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/jspsr_spn.h"
+#include "spn_kernels.cuh"
+
+using namespace jspsr;
+
+namespace jspsr {
+cudaError_t launch_offset_absmax(const void* offset, size_t n_pairs_block, size_t cs, int B, bool bf16, float* out2,
+                                 cudaStream_t stream);
+cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const float* mask_fix, void* dst, size_t n,
+                                  bool bf16, cudaStream_t stream);
+cudaError_t launch_nlspn_affinity_forward(const void* conv_out, const void* confidence, const float* gamma,
+                                          void* offset_out, void* aff_out, int B, int H, int W, int affinity, int legacy,
+                                          bool bf16, cudaStream_t stream);
+cudaError_t launch_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff, const void* conv_out,
+                                           const void* confidence, const float* gamma, void* grad_conv_out,
+                                           float* grad_confidence, float* grad_scale, void* workspace, int B, int H,
+                                           int W, int affinity, bool bf16, cudaStream_t stream);
+}  // namespace jspsr
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(JSPSR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------
+// TMA descriptor for the DEM buffer viewed as [B][rows][W]; box = the staged tile
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+static bool tma_disabled_by_env() {
+    // read on every call so tests can flip it; the manual tile loader is the same
+    // kernel with the TMA box copy replaced by bounds-checked loads
+    const char* e = getenv("JSPSR_SPN_DISABLE_TMA");
+    return e && e[0] == '1';
+}
+
+// Returns true when the TMA path can be used for this buffer (and fills *map).
+static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, int W, bool bf16) {
+    if (tma_disabled_by_env()) return false;
+    const size_t es = bf16 ? 2 : 4;
+    if (((uintptr_t)init & 15) != 0) return false;
+    if (((size_t)W * es) % 16 != 0) return false;  // TMA global strides are multiples of 16 bytes
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)W * es, (cuuint64_t)W * es * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)SW, (cuuint32_t)SH, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void*>(init), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static int check_common(int B, int H, int W, int norm_mode, int dtype) {
+    if (B <= 0 || H <= 0 || W <= 0) return fail(JSPSR_ERR_BAD_ARG, "non-positive dimension B=%d H=%d W=%d", B, H, W);
+    if (H > (1 << 24) || W > (1 << 24))
+        return fail(JSPSR_ERR_UNSUPPORTED, "H and W are limited to 2^24 (fp32 pixel coordinates must be exact)");
+    if (norm_mode < 0 || norm_mode > 2) return fail(JSPSR_ERR_BAD_ARG, "norm_mode %d is not 0/1/2", norm_mode);
+    if (dtype != JSPSR_F32 && dtype != JSPSR_BF16) return fail(JSPSR_ERR_BAD_ARG, "dtype %d is not 0 (f32) / 1 (bf16)", dtype);
+    return 0;
+}
+static int check_align(const void* p, size_t a, const char* name) {
+    if (p && ((uintptr_t)p % a) != 0) return fail(JSPSR_ERR_ALIGN, "%s is not aligned to %zu bytes", name, a);
+    return 0;
+}
+static int fill_geom(Geom* g, int B, int Hs, int W, int H_img, int row0, int init_row0, int init_rows) {
+    g->B = B; g->H = Hs; g->W = W; g->H_img = H_img; g->row0 = row0; g->init_row0 = init_row0; g->init_rows = init_rows;
+    g->tiles_x = (W + TILE_W - 1) / TILE_W;
+    g->tiles_y = (Hs + TILE_H - 1) / TILE_H;
+    const size_t tiles = (size_t)g->tiles_x * g->tiles_y * B;
+    if (tiles > 0x7fffffffull) return fail(JSPSR_ERR_UNSUPPORTED, "too many tiles (%zu) for one launch", tiles);
+    return 0;
+}
+
+extern "C" {
+
+int jspsr_version(void) { return JSPSR_SPN_VERSION; }
+const char* jspsr_last_error(void) { return g_err; }
+size_t jspsr_spn_workspace_bytes(void) { return sizeof(ReduceWs); }
+
+int jspsr_spn_forward_strip(const void* init, const void* weight, const void* offset, const float* w9, const float* b1,
+                            void* out, int B, int Hs, int W, int H_img, int row0, int init_row0, int init_rows,
+                            int norm_mode, float scale, int dtype, int* status, void* stream) {
+    if (int e = check_common(B, Hs, W, norm_mode, dtype)) return e;
+    if (!init || !weight || !offset || !out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    if (H_img < Hs || row0 < 0 || row0 + Hs > H_img || init_row0 < 0 || init_rows <= 0 || init_row0 + init_rows > H_img ||
+        H_img > (1 << 24))
+        return fail(JSPSR_ERR_BAD_ARG, "inconsistent strip geometry (Hs=%d H_img=%d row0=%d init_row0=%d init_rows=%d)", Hs,
+                    H_img, row0, init_row0, init_rows);
+    const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
+    if (int e = check_align(init, es, "init")) return e;
+    if (int e = check_align(weight, es, "weight")) return e;
+    if (int e = check_align(offset, es, "offset")) return e;
+    if (int e = check_align(out, es, "out")) return e;
+    if (int e = check_align(w9, 4, "w9")) return e;
+    if (int e = check_align(b1, 4, "b1")) return e;
+    LaunchArgs la;
+    if (int e = fill_geom(&la.g, B, Hs, W, H_img, row0, init_row0, init_rows)) return e;
+    la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9; la.b1 = b1; la.out = out;
+    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.status = status;
+    la.stream = (cudaStream_t)stream;
+    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, la.bf16);
+    cudaError_t ce = launch_spn_forward(la);
+    if (ce != cudaSuccess) return cuda_fail(ce, "spn_forward launch");
+    return JSPSR_OK;
+}
+
+int jspsr_spn_forward(const void* init, const void* weight, const void* offset, const float* w9, const float* b1,
+                      void* out, int B, int H, int W, int norm_mode, float scale, int dtype, void* stream) {
+    if (!w9 || !b1) return fail(JSPSR_ERR_BAD_ARG, "w9/b1 must be device pointers (use jspsr_spn_iterate for w=1,b=0)");
+    return jspsr_spn_forward_strip(init, weight, offset, w9, b1, out, B, H, W, H, 0, 0, H, norm_mode, scale, dtype,
+                                   nullptr, stream);
+}
+
+int jspsr_spn_backward(const void* grad_out, const void* init, const void* weight, const void* offset, const float* w9,
+                       float* grad_init, void* grad_weight, void* grad_offset, float* grad_w9, float* grad_b1,
+                       void* workspace, int B, int H, int W, int norm_mode, float scale, int dtype, unsigned flags,
+                       void* stream) {
+    if (int e = check_common(B, H, W, norm_mode, dtype)) return e;
+    if (!grad_out || !init || !weight || !offset || !grad_weight || !grad_offset)
+        return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    if (grad_w9 && !workspace) return fail(JSPSR_ERR_BAD_ARG, "workspace is required when grad_w9 is requested");
+    if (grad_b1 && !grad_w9) return fail(JSPSR_ERR_BAD_ARG, "grad_b1 without grad_w9 is not supported");
+    const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
+    if (int e = check_align(grad_out, es, "grad_out")) return e;
+    if (int e = check_align(init, es, "init")) return e;
+    if (int e = check_align(weight, es, "weight")) return e;
+    if (int e = check_align(offset, es, "offset")) return e;
+    if (int e = check_align(grad_weight, es, "grad_weight")) return e;
+    if (int e = check_align(grad_offset, es, "grad_offset")) return e;
+    if (int e = check_align(grad_init, 4, "grad_init")) return e;
+    if (int e = check_align(workspace, 16, "workspace")) return e;
+    LaunchArgs la;
+    if (int e = fill_geom(&la.g, B, H, W, H, 0, 0, H)) return e;
+    la.grad_out = grad_out; la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9;
+    la.grad_init = grad_init; la.grad_weight = grad_weight; la.grad_offset = grad_offset;
+    la.grad_w9 = grad_w9; la.grad_b1 = grad_b1; la.workspace = workspace;
+    la.accumulate = (flags & JSPSR_BWD_ACCUMULATE) != 0;
+    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.stream = (cudaStream_t)stream;
+    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, la.bf16);
+    if (grad_init) {
+        cudaError_t ce = cudaMemsetAsync(grad_init, 0, (size_t)B * H * W * sizeof(float), la.stream);
+        if (ce != cudaSuccess) return cuda_fail(ce, "grad_init memset");
+    }
+    cudaError_t ce = launch_spn_backward(la);
+    if (ce != cudaSuccess) return cuda_fail(ce, "spn_backward launch");
+    return JSPSR_OK;
+}
+
+int jspsr_spn_offset_absmax(const void* offset, int B, int H, int W, int dtype, float* out2, void* stream) {
+    if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (!offset || !out2) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
+    cudaError_t ce = launch_offset_absmax(offset, 0, (size_t)H * W, B, dtype == JSPSR_BF16, out2, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "offset_absmax launch");
+    return JSPSR_OK;
+}
+
+int jspsr_spn_iterate(const void* feat_init, const void* aff, const void* offset, const void* feat_fix,
+                      const void* mask_fix, void* list_out, void* scratch, int B, int H, int W, int T, int dtype,
+                      void* stream) {
+    if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (T <= 0) return fail(JSPSR_ERR_BAD_ARG, "T=%d must be positive", T);
+    if (!feat_init || !aff || !offset || !list_out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    if ((feat_fix == nullptr) != (mask_fix == nullptr))
+        return fail(JSPSR_ERR_BAD_ARG, "feat_fix and mask_fix must be given together");
+    if (feat_fix && !scratch) return fail(JSPSR_ERR_BAD_ARG, "preserve_input needs a [B,1,H,W] scratch buffer");
+    const bool bf16 = dtype == JSPSR_BF16;
+    const size_t es = bf16 ? 2 : 4, n = (size_t)B * H * W;
+    const char* src = (const char*)feat_init;
+    for (int t = 0; t < T; ++t) {
+        if (feat_fix) {  // nlspn.py:228-229
+            cudaError_t ce = launch_preserve_blend(src, feat_fix, (const float*)mask_fix, scratch, n, bf16, (cudaStream_t)stream);
+            if (ce != cudaSuccess) return cuda_fail(ce, "preserve_input blend launch");
+            src = (const char*)scratch;
+        }
+        char* dst = (char*)list_out + (size_t)t * n * es;
+        LaunchArgs la;
+        if (int e = fill_geom(&la.g, B, H, W, H, 0, 0, H)) return e;
+        la.init = src; la.weight = aff; la.offset = offset; la.w9 = nullptr; la.b1 = nullptr; la.out = dst;
+        la.mode = NORM_NONE; la.scale = 0.f; la.bf16 = bf16; la.stream = (cudaStream_t)stream;
+        la.use_tma = make_init_tmap(&la.tmap, src, B, H, W, bf16);
+        cudaError_t ce = launch_spn_forward(la);
+        if (ce != cudaSuccess) return cuda_fail(ce, "spn_iterate launch");
+        src = dst;
+    }
+    return JSPSR_OK;
+}
+
+int jspsr_nlspn_affinity_forward(const void* conv_out, const void* confidence, const float* aff_scale_const,
+                                 void* offset_out, void* aff_out, int B, int H, int W, int affinity, int legacy,
+                                 int dtype, void* stream) {
+    if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (!conv_out || !offset_out || !aff_out || !aff_scale_const) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
+    if (affinity < 0 || affinity > 3) return fail(JSPSR_ERR_BAD_ARG, "affinity %d is not AS/ASS/TC/TGASS", affinity);
+    if (legacy && !confidence) return fail(JSPSR_ERR_BAD_ARG, "legacy only has an effect with confidence propagation");
+    cudaError_t ce = launch_nlspn_affinity_forward(conv_out, confidence, aff_scale_const, offset_out, aff_out, B, H, W,
+                                                   affinity, legacy, dtype == JSPSR_BF16, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "nlspn_affinity_forward launch");
+    return JSPSR_OK;
+}
+
+int jspsr_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff, const void* conv_out,
+                                  const void* confidence, const float* aff_scale_const, void* grad_conv_out,
+                                  float* grad_confidence, float* grad_scale, void* workspace, int B, int H, int W,
+                                  int affinity, int dtype, void* stream) {
+    if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (!grad_offset || !grad_aff || !conv_out || !grad_conv_out || !aff_scale_const)
+        return fail(JSPSR_ERR_BAD_ARG, "null pointer");
+    if (affinity < 0 || affinity > 3) return fail(JSPSR_ERR_BAD_ARG, "affinity %d is not AS/ASS/TC/TGASS", affinity);
+    if (grad_scale && !workspace) return fail(JSPSR_ERR_BAD_ARG, "workspace is required when grad_scale is requested");
+    if (grad_confidence && !confidence) return fail(JSPSR_ERR_BAD_ARG, "grad_confidence without confidence");
+    if (grad_confidence) {
+        cudaError_t ce = cudaMemsetAsync(grad_confidence, 0, (size_t)B * H * W * sizeof(float), (cudaStream_t)stream);
+        if (ce != cudaSuccess) return cuda_fail(ce, "grad_confidence memset");
+    }
+    cudaError_t ce = launch_nlspn_affinity_backward(grad_offset, grad_aff, conv_out, confidence, aff_scale_const,
+                                                    grad_conv_out, grad_confidence, grad_scale, workspace, B, H, W,
+                                                    affinity, dtype == JSPSR_BF16, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "nlspn_affinity_backward launch");
+    return JSPSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Shared device helpers for the propagation kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jspsr {
+
+// ---------------------------------------------------------------------------
+// Tile geometry.  One CTA owns a TILE_H x TILE_W block of output pixels of one
+// sample and stages the DEM rows/cols its taps can reach in shared memory:
+// HALO_* pixels around the block (offsets up to +-5 px stay on chip; anything
+// further takes the bounds-checked global path).  The staged tile is a dense
+// [SH][SW] box so one 3-D TMA box copy (zero-filled outside the image, which is
+// exactly torchvision's zero-outside rule) can fill it.
+// ---------------------------------------------------------------------------
+constexpr int TILE_W = 128;
+constexpr int TILE_H = 16;
+constexpr int HALO_T = 6, HALO_B = 7;   // rows above / below  (bottom needs the +1 bilinear row)
+constexpr int HALO_L = 6, HALO_R = 10;  // cols left / right   (right padded so SW % 4 == 0)
+constexpr int SW = TILE_W + HALO_L + HALO_R;  // 144
+constexpr int SH = TILE_H + HALO_T + HALO_B;  // 29
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+static_assert(SW % 4 == 0, "TMA inner box extent must be a multiple of 16 bytes");
+static_assert(SW <= 256 && SH <= 256, "TMA box extents are limited to 256");
+
+enum { NORM_NONE = 0, NORM_RESIDUAL = 1, NORM_SUM = 2 };
+
+// Geometry of one call.  Rows are expressed in GLOBAL image coordinates so that
+// a row strip (multi-GPU sharding) computes bit-identical positions.
+struct Geom {
+    int B, H, W;          // rows/cols of weight/offset/out held by this call (the strip)
+    int H_img;            // rows of the whole image
+    int row0;             // global row of out row 0
+    int init_row0;        // global row of init buffer row 0
+    int init_rows;        // rows present in the init buffer
+    int tiles_x, tiles_y;
+};
+
+// ---------------------------------------------------------------------------
+// element access
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// streaming (read-once) loads: keep them out of L1 so the gather fallback and the
+// staged tile keep the cache
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) {
+    unsigned short u;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+    return __uint_as_float(((unsigned)u) << 16);
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, float v) {
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"(*reinterpret_cast<unsigned short*>(&b)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + TMA (cp.async.bulk.tensor) wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 3-D tiled box copy global -> shared, completion signalled on `bar`
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Stage the halo'd DEM tile.  TMA path: one elected thread issues a box copy with
+// hardware zero fill.  Manual path (W*sizeof(T) not a multiple of 16, or TMA
+// unavailable): bounds-checked cooperative loads.  Rows outside the init buffer are
+// zero either way; whether a zero row is *legitimate* (outside the image) or a
+// missing halo row is decided per tap through [r_lo, r_lo + r_span).
+// ---------------------------------------------------------------------------
+template <typename T, bool TMA>
+__device__ __forceinline__ void stage_tile_begin(T* tile, uint64_t* bar, const CUtensorMap* tmap, const T* init,
+                                                 const Geom& g, int b, int ox, int oy_buf) {
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(bar, SH * SW * sizeof(T));
+            tma_load_3d(tile, tmap, bar, ox, oy_buf, b);
+        }
+    } else {
+        const T* src = init + (size_t)b * g.init_rows * g.W;
+        for (int i = threadIdx.x; i < SH * SW; i += THREADS) {
+            int r = i / SW, c = i - r * SW;
+            int br = oy_buf + r, gx = ox + c;
+            T v = from_f32<T>(0.f);
+            if ((unsigned)br < (unsigned)g.init_rows && (unsigned)gx < (unsigned)g.W) v = src[(size_t)br * g.W + gx];
+            tile[i] = v;
+        }
+    }
+}
+template <bool TMA>
+__device__ __forceinline__ void stage_tile_wait(uint64_t* bar) {
+    __syncthreads();  // manual path: tile stores visible; TMA path: barrier init visible to all waiters
+    if constexpr (TMA) mbar_wait(bar, 0);
+}
+
+// Bounds-checked corner fetch from global memory (taps that leave the staged tile).
+// (hi, wi) are GLOBAL coordinates.  A row inside the image but missing from the init
+// buffer raises *status (row-strip calls with too small a halo).
+template <typename T>
+__device__ __forceinline__ float fetch_corner_global(const T* init_b, const Geom& g, int hi, int wi, int* status) {
+    if ((unsigned)hi >= (unsigned)g.H_img || (unsigned)wi >= (unsigned)g.W) return 0.f;
+    int br = hi - g.init_row0;
+    if ((unsigned)br >= (unsigned)g.init_rows) {
+        if (status) atomicOr(status, 1);
+        return 0.f;
+    }
+    return to_f32(init_b[(size_t)br * g.W + wi]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace jspsr

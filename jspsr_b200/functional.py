@@ -1,0 +1,329 @@
+"""Autograd-aware Python entry points over the C ABI (include/jspsr_spn.h).
+
+Everything here only validates shapes, hands raw device pointers + the current
+CUDA stream to libjspsr_spn.so and wires the results into autograd.  There is no
+PyTorch implementation of the arithmetic in this package: CPU tensors are
+rejected, a missing library raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BF16, BWD_ACCUMULATE, F32, NORM_NONE, NORM_RESIDUAL, NORM_SUM  # noqa: F401
+
+_workspaces = {}
+_launches = 0  # kernels of libjspsr_spn.so enqueued through this module (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"jspsr_b200: unsupported dtype {t.dtype} (float32 and bfloat16 only)")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("jspsr_b200 runs on CUDA tensors only (there is no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _workspace(t: torch.Tensor) -> torch.Tensor:
+    """Zero-initialised reduction scratch, one per (device, stream); the kernels leave it zeroed."""
+    key = (t.device.index, _stream_ptr(t))
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.lib().jspsr_spn_workspace_bytes(), dtype=torch.uint8, device=t.device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _check_shapes(init, weight, offset):
+    # mirrors the checks of torchvision.ops.deform_conv2d for this configuration
+    if init.dim() != 4 or init.shape[1] != 1:
+        raise RuntimeError(f"init must be [B,1,H,W], got {tuple(init.shape)}")
+    B, _, H, W = init.shape
+    if tuple(weight.shape) != (B, 9, H, W):
+        raise RuntimeError(f"mask/weight must be [B,9,H,W] = {(B, 9, H, W)}, got {tuple(weight.shape)}")
+    if offset.dim() != 4 or offset.shape[1] % 18 != 0 or tuple(offset.shape) != (B, 18, H, W):
+        raise RuntimeError(f"offset must be [B,2*3*3,H,W] = {(B, 18, H, W)}, got {tuple(offset.shape)}")
+    if not (init.dtype == weight.dtype == offset.dtype):
+        raise RuntimeError("init, weight and offset must share one dtype")
+    return B, H, W
+
+
+def _w9(w: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
+    if w is None:
+        return None
+    if w.numel() != 9:
+        raise RuntimeError(f"only kernel_size 3 is supported (w has {w.numel()} elements)")
+    return w.detach().to(device=like.device, dtype=torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# raw calls (no autograd)
+# ---------------------------------------------------------------------------
+def spn_forward(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) -> torch.Tensor:
+    _require_cuda(init, weight, offset, w, b)
+    B, H, W = _check_shapes(init, weight, offset)
+    init, weight, offset = init.contiguous(), weight.contiguous(), offset.contiguous()
+    w9 = _w9(w, init)
+    b1 = b.detach().to(device=init.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(init)
+    with torch.cuda.device(init.device):
+        rc = _lib.lib().jspsr_spn_forward(_ptr(init), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1), _ptr(out),
+                                          B, H, W, norm_mode, float(scale), _dtype_code(init), _stream_ptr(init))
+    _lib.check(rc, "jspsr_spn_forward")
+    _count()
+    return out
+
+
+def spn_backward(grad_out, init, weight, offset, w, norm_mode: int, scale: float = 1.0, need_grad_init=True,
+                 need_grad_w=True, accumulate_into=None):
+    """Returns (grad_init fp32 | None, grad_weight, grad_offset, grad_w [1,1,3,3] | None, grad_b [1] | None).
+    `accumulate_into=(grad_weight, grad_offset)` adds into existing buffers (fixed-affinity loops)."""
+    _require_cuda(grad_out, init, weight, offset, w)
+    B, H, W = _check_shapes(init, weight, offset)
+    grad_out = grad_out.to(init.dtype).contiguous()
+    init, weight, offset = init.contiguous(), weight.contiguous(), offset.contiguous()
+    w9 = _w9(w, init)
+    dev = init.device
+    grad_init = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev) if need_grad_init else None
+    flags = 0
+    if accumulate_into is not None:
+        grad_weight, grad_offset = accumulate_into
+        flags |= BWD_ACCUMULATE
+    else:
+        grad_weight, grad_offset = torch.empty_like(weight), torch.empty_like(offset)
+    grad_w = torch.empty(1, 1, 3, 3, dtype=torch.float32, device=dev) if need_grad_w else None
+    grad_b = torch.empty(1, dtype=torch.float32, device=dev) if need_grad_w else None
+    ws = _workspace(init) if need_grad_w else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().jspsr_spn_backward(_ptr(grad_out), _ptr(init), _ptr(weight), _ptr(offset), _ptr(w9),
+                                           _ptr(grad_init), _ptr(grad_weight), _ptr(grad_offset), _ptr(grad_w),
+                                           _ptr(grad_b), _ptr(ws), B, H, W, norm_mode, float(scale),
+                                           _dtype_code(init), flags, _stream_ptr(init))
+    _lib.check(rc, "jspsr_spn_backward")
+    _count()
+    return grad_init, grad_weight, grad_offset, grad_w, grad_b
+
+
+def spn_forward_strip(init_buf, weight, offset, w, b, norm_mode, scale, H_img, row0, init_row0, status=None):
+    """Row-strip forward: `init_buf` holds rows [init_row0, init_row0+init_buf.shape[2]) of the image."""
+    _require_cuda(init_buf, weight, offset)
+    B, _, Hs, W = weight.shape[0], None, weight.shape[2], weight.shape[3]
+    init_buf, weight, offset = init_buf.contiguous(), weight.contiguous(), offset.contiguous()
+    w9 = _w9(w, weight)
+    b1 = None if b is None else b.detach().to(device=weight.device, dtype=torch.float32).contiguous()
+    out = torch.empty(B, 1, Hs, W, dtype=weight.dtype, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = _lib.lib().jspsr_spn_forward_strip(_ptr(init_buf), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1),
+                                                _ptr(out), B, Hs, W, H_img, row0, init_row0, init_buf.shape[2],
+                                                norm_mode, float(scale), _dtype_code(weight), _ptr(status),
+                                                _stream_ptr(weight))
+    _lib.check(rc, "jspsr_spn_forward_strip")
+    _count()
+    return out
+
+
+def offset_absmax(offset: torch.Tensor) -> torch.Tensor:
+    """[max |row offset|, max |col offset|] as a 2-element fp32 device tensor."""
+    _require_cuda(offset)
+    B, C, H, W = offset.shape
+    if C != 18:
+        raise RuntimeError("offset must have 18 channels")
+    out = torch.zeros(2, dtype=torch.float32, device=offset.device)
+    offset = offset.contiguous()
+    with torch.cuda.device(offset.device):
+        rc = _lib.lib().jspsr_spn_offset_absmax(_ptr(offset), B, H, W, _dtype_code(offset), _ptr(out),
+                                                _stream_ptr(offset))
+    _lib.check(rc, "jspsr_spn_offset_absmax")
+    _count()
+    return out
+
+
+def spn_iterate(feat_init, aff, offset, T: int, feat_fix=None, mask_fix=None) -> torch.Tensor:
+    """T fixed-affinity applications; returns all intermediates [T,B,1,H,W]."""
+    _require_cuda(feat_init, aff, offset, feat_fix, mask_fix)
+    B, H, W = _check_shapes(feat_init, aff, offset)
+    feat_init, aff, offset = feat_init.contiguous(), aff.contiguous(), offset.contiguous()
+    out = torch.empty((T, B, 1, H, W), dtype=feat_init.dtype, device=feat_init.device)
+    scratch = None
+    if feat_fix is not None:
+        feat_fix = feat_fix.to(feat_init.dtype).contiguous()
+        mask_fix = mask_fix.to(torch.float32).contiguous()
+        scratch = torch.empty_like(feat_init)
+    with torch.cuda.device(feat_init.device):
+        rc = _lib.lib().jspsr_spn_iterate(_ptr(feat_init), _ptr(aff), _ptr(offset), _ptr(feat_fix), _ptr(mask_fix),
+                                          _ptr(out), _ptr(scratch), B, H, W, T, _dtype_code(feat_init),
+                                          _stream_ptr(feat_init))
+    _lib.check(rc, "jspsr_spn_iterate")
+    _count(T * (2 if feat_fix is not None else 1))
+    return out
+
+
+def nlspn_affinity_forward(conv_out, confidence, aff_scale_const, affinity: str, legacy: bool = False):
+    _require_cuda(conv_out, confidence, aff_scale_const)
+    B, C, H, W = conv_out.shape
+    if C != 24:
+        raise RuntimeError(f"conv_offset_aff output must have 24 channels (k_f = 3), got {C}")
+    conv_out = conv_out.contiguous()
+    if confidence is not None:
+        if tuple(confidence.shape) != (B, 1, H, W):
+            raise RuntimeError(f"confidence must be [B,1,H,W], got {tuple(confidence.shape)}")
+        confidence = confidence.to(conv_out.dtype).contiguous()
+    gamma = aff_scale_const.detach().to(device=conv_out.device, dtype=torch.float32).contiguous()
+    offset = torch.empty(B, 18, H, W, dtype=conv_out.dtype, device=conv_out.device)
+    aff = torch.empty(B, 9, H, W, dtype=conv_out.dtype, device=conv_out.device)
+    with torch.cuda.device(conv_out.device):
+        rc = _lib.lib().jspsr_nlspn_affinity_forward(_ptr(conv_out), _ptr(confidence), _ptr(gamma), _ptr(offset),
+                                                     _ptr(aff), B, H, W, _lib.AFFINITY[affinity], int(bool(legacy)),
+                                                     _dtype_code(conv_out), _stream_ptr(conv_out))
+    _lib.check(rc, "jspsr_nlspn_affinity_forward")
+    _count()
+    return offset, aff
+
+
+def nlspn_affinity_backward(grad_offset, grad_aff, conv_out, confidence, aff_scale_const, affinity: str,
+                            need_grad_conf=True, need_grad_scale=True):
+    _require_cuda(grad_offset, grad_aff, conv_out, confidence)
+    B, _, H, W = conv_out.shape
+    dev = conv_out.device
+    conv_out = conv_out.contiguous()
+    grad_offset = grad_offset.to(conv_out.dtype).contiguous()
+    grad_aff = grad_aff.to(conv_out.dtype).contiguous()
+    if confidence is not None:
+        confidence = confidence.to(conv_out.dtype).contiguous()
+    gamma = aff_scale_const.detach().to(device=dev, dtype=torch.float32).contiguous()
+    grad_conv = torch.empty_like(conv_out)
+    need_grad_conf = need_grad_conf and confidence is not None
+    grad_conf = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev) if need_grad_conf else None
+    need_grad_scale = need_grad_scale and affinity == "TGASS"
+    grad_scale = torch.empty(1, dtype=torch.float32, device=dev) if need_grad_scale else None
+    ws = _workspace(conv_out) if need_grad_scale else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().jspsr_nlspn_affinity_backward(_ptr(grad_offset), _ptr(grad_aff), _ptr(conv_out),
+                                                      _ptr(confidence), _ptr(gamma), _ptr(grad_conv), _ptr(grad_conf),
+                                                      _ptr(grad_scale), _ptr(ws), B, H, W, _lib.AFFINITY[affinity],
+                                                      _dtype_code(conv_out), _stream_ptr(conv_out))
+    _lib.check(rc, "jspsr_nlspn_affinity_backward")
+    _count()
+    return grad_conv, grad_conf, grad_scale
+
+
+# ---------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------
+class _Propagate(torch.autograd.Function):
+    """normalise -> deformable 3x3 gather -> (+ scale*init): one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, init, weight, offset, w, b, norm_mode, scale):
+        ctx.save_for_backward(init, weight, offset, w)
+        ctx.norm_mode, ctx.scale = norm_mode, scale
+        return spn_forward(init, weight, offset, w, b, norm_mode, scale)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        init, weight, offset, w = ctx.saved_tensors
+        need_init = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+        gi, gwt, goff, gw, gb = spn_backward(grad_out, init, weight, offset, w, ctx.norm_mode, ctx.scale,
+                                             need_grad_init=need_init, need_grad_w=need_w)
+        if gi is not None:
+            gi = gi.to(init.dtype)
+        if gw is not None:
+            gw, gb = gw.to(w.dtype).reshape(w.shape), gb.to(w.dtype)
+        return (gi, gwt if ctx.needs_input_grad[1] else None, goff if ctx.needs_input_grad[2] else None,
+                gw if ctx.needs_input_grad[3] else None, gb if ctx.needs_input_grad[4] else None, None, None)
+
+
+def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) -> torch.Tensor:
+    return _Propagate.apply(init, weight, offset, w, b, norm_mode, scale)
+
+
+class _Iterate(torch.autograd.Function):
+    """NLSPN loop (nlspn.py:222-235): T applications with fixed aff/offset, w=1, b=0."""
+
+    @staticmethod
+    def forward(ctx, feat_init, aff, offset, feat_fix, mask_fix, T):
+        out = spn_iterate(feat_init, aff, offset, T, feat_fix, mask_fix)
+        ctx.save_for_backward(feat_init, aff, offset, out, feat_fix, mask_fix)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_list):
+        feat_init, aff, offset, out, feat_fix, mask_fix = ctx.saved_tensors
+        T = ctx.T
+        grad_aff = grad_offset = None
+        carry = None  # gradient flowing into step t's output from step t+1
+        for t in range(T - 1, -1, -1):
+            g = grad_list[t] if carry is None else grad_list[t] + carry.to(grad_list.dtype)
+            src = feat_init if t == 0 else out[t - 1]
+            if feat_fix is not None:  # the step consumed the blended input (nlspn.py:229)
+                src = ((1.0 - mask_fix) * src + mask_fix * feat_fix).to(src.dtype)
+            acc = None if grad_aff is None else (grad_aff, grad_offset)
+            gi, grad_aff, grad_offset, _, _ = spn_backward(g, src, aff, offset, None, NORM_NONE, 0.0,
+                                                           need_grad_init=True, need_grad_w=False, accumulate_into=acc)
+            carry = gi if feat_fix is None else gi * (1.0 - mask_fix)
+        return (carry.to(feat_init.dtype) if ctx.needs_input_grad[0] else None,
+                grad_aff if ctx.needs_input_grad[1] else None,
+                grad_offset if ctx.needs_input_grad[2] else None, None, None, None)
+
+
+def iterate(feat_init, aff, offset, T: int, feat_fix=None, mask_fix=None) -> torch.Tensor:
+    return _Iterate.apply(feat_init, aff, offset, feat_fix, mask_fix, T)
+
+
+class _NlspnAffinity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, conv_out, confidence, aff_scale_const, affinity, legacy):
+        offset, aff = nlspn_affinity_forward(conv_out, confidence, aff_scale_const, affinity, legacy)
+        ctx.save_for_backward(conv_out, confidence, aff_scale_const)
+        ctx.affinity, ctx.legacy = affinity, legacy
+        return offset, aff
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_offset, grad_aff):
+        if ctx.legacy:
+            raise RuntimeError("NLSPN legacy mode is inference-only (the reference mutates its offsets in place, "
+                               "models/components/nlspn.py:118-128, which autograd rejects there too)")
+        conv_out, confidence, gamma = ctx.saved_tensors
+        gc, gconf, gscale = nlspn_affinity_backward(grad_offset, grad_aff, conv_out, confidence, gamma, ctx.affinity,
+                                                    need_grad_conf=ctx.needs_input_grad[1],
+                                                    need_grad_scale=ctx.needs_input_grad[2])
+        if gconf is not None:
+            gconf = gconf.to(confidence.dtype)
+        if gscale is not None:
+            gscale = gscale.to(gamma.dtype).reshape(gamma.shape)
+        return gc, gconf, gscale, None, None
+
+
+def nlspn_affinity(conv_out, confidence, aff_scale_const, affinity: str, legacy: bool = False):
+    return _NlspnAffinity.apply(conv_out, confidence, aff_scale_const, affinity, legacy)

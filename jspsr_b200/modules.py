@@ -1,0 +1,153 @@
+"""Drop-in nn.Modules for the reference's propagation layers.
+
+Same constructor arguments, attributes, forward signatures, return values and
+state_dict keys as
+  models/components/spn.py:79-118     PostProcessor
+  models/LRRU.py:250-298              Post_process_deconv
+  models/components/nlspn.py:8-235    NLSPN
+so `models/JSPSR.py:192-194,375`, `models/EDSR.py:107,134`,
+`models/LRRU.py:399,455-498` and `models/CompletionFormer.py:34-36,59-61` can use
+them unchanged and released checkpoints load (`utils/utils.py:360-364` filters by
+key name and shape: `w` [1,1,k,k], `b` [1]).  The arithmetic runs in
+libjspsr_spn.so; these classes hold parameters and call it.
+"""
+from __future__ import annotations
+
+from abc import ABC
+
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from ._lib import NORM_RESIDUAL, NORM_SUM
+
+
+def _require_k3(kernel_size: int):
+    if kernel_size != 3:
+        raise NotImplementedError(
+            f"jspsr_b200 implements the 3x3 propagation window the reference uses everywhere "
+            f"(got kernel_size={kernel_size})")
+
+
+class PostProcessor(nn.Module):
+    """models/components/spn.py:79-118."""
+
+    def __init__(self, kernel_size=3, residual=True, scale=1.0):
+        super().__init__()
+        _require_k3(kernel_size)
+        self.residual = residual
+        self.w = nn.Parameter(torch.ones((1, 1, kernel_size, kernel_size)))
+        self.b = nn.Parameter(torch.zeros(1))
+        self.stride = (1, 1)
+        self.padding = ((kernel_size - 1) // 2, (kernel_size - 1) // 2)
+        self.dilation = (1, 1)
+        self.scale = scale
+        if self.scale != 1:
+            print("Warning: The scale factor is not 1. This may lead to unexpected results.")
+
+    def forward(self, init_dem, weight, offset):
+        mode = NORM_RESIDUAL if self.residual else NORM_SUM
+        return F.propagate(init_dem, weight, offset, self.w, self.b, mode, float(self.scale))
+
+
+class Post_process_deconv(nn.Module, ABC):
+    """models/LRRU.py:250-298 (`args` needs .kernel_size and .dkn_residual)."""
+
+    def __init__(self, args):
+        super().__init__()
+        _require_k3(args.kernel_size)
+        self.dkn_residual = args.dkn_residual
+        self.w = nn.Parameter(torch.ones((1, 1, args.kernel_size, args.kernel_size)))
+        self.b = nn.Parameter(torch.zeros(1))
+        self.stride = (1, 1)
+        self.padding = ((args.kernel_size - 1) // 2, (args.kernel_size - 1) // 2)
+        self.dilation = (1, 1)
+        self.deformable_groups = 1
+        self.im2col_step = 64
+
+    def forward(self, depth, weight, offset):
+        mode = NORM_RESIDUAL if self.dkn_residual else NORM_SUM
+        return F.propagate(depth, weight, offset, self.w, self.b, mode, 1.0)
+
+
+class NLSPN(nn.Module):
+    """models/components/nlspn.py:8-235.  The 3x3 guidance conv stays a cuDNN conv (it
+    is the producer, like spn.Generator); everything after it - offset packing,
+    tanh/gamma scaling, confidence gating, abs-sum normalisation, centre weight and the
+    prop_time-step loop - runs in the CUDA library."""
+
+    def __init__(self, args, ch_g, ch_f, k_g, k_f):
+        super().__init__()
+        assert ch_f == 1, "only tested with ch_f == 1 but {}".format(ch_f)
+        assert (k_g % 2) == 1, "only odd kernel is supported but k_g = {}".format(k_g)
+        pad_g = int((k_g - 1) / 2)
+        assert (k_f % 2) == 1, "only odd kernel is supported but k_f = {}".format(k_f)
+        pad_f = int((k_f - 1) / 2)
+        _require_k3(k_f)
+
+        self.args = args
+        self.prop_time = self.args.prop_time
+        self.affinity = self.args.affinity
+        self.ch_g, self.ch_f, self.k_g, self.k_f = ch_g, ch_f, k_g, k_f
+        self.num = self.k_f * self.k_f - 1
+        self.idx_ref = self.num // 2
+
+        if self.affinity in ["AS", "ASS", "TC", "TGASS"]:
+            self.conv_offset_aff = nn.Conv2d(self.ch_g, 3 * self.num, kernel_size=self.k_g, stride=1,
+                                             padding=pad_g, bias=True)
+            self.conv_offset_aff.weight.data.zero_()
+            self.conv_offset_aff.bias.data.zero_()
+            if self.affinity == "TC":
+                self.aff_scale_const = nn.Parameter(self.num * torch.ones(1))
+                self.aff_scale_const.requires_grad = False
+            elif self.affinity == "TGASS":
+                self.aff_scale_const = nn.Parameter(self.args.affinity_gamma * self.num * torch.ones(1))
+            else:
+                self.aff_scale_const = nn.Parameter(torch.ones(1))
+                self.aff_scale_const.requires_grad = False
+        else:
+            raise NotImplementedError
+
+        # frozen gather parameters kept for state_dict compatibility (nlspn.py:61-68)
+        self.w = nn.Parameter(torch.ones((self.ch_f, 1, self.k_f, self.k_f)))
+        self.b = nn.Parameter(torch.zeros(self.ch_f))
+        self.w.requires_grad = False
+        self.b.requires_grad = False
+        self.w_conf = nn.Parameter(torch.ones((1, 1, 1, 1)))
+        self.w_conf.requires_grad = False
+
+        self.stride = 1
+        self.padding = pad_f
+        self.dilation = 1
+        self.groups = self.ch_f
+        self.deformable_groups = 1
+        self.im2col_step = 64
+
+    def _get_offset_affinity(self, guidance, confidence=None, rgb=None):
+        offset_aff = self.conv_offset_aff(guidance)
+        conf = confidence if self.args.conf_prop else None
+        return F.nlspn_affinity(offset_aff, conf, self.aff_scale_const, self.affinity,
+                                bool(getattr(self.args, "legacy", False)) and conf is not None)
+
+    def _propagate_once(self, feat, offset, aff):
+        return F.iterate(feat, aff, offset, 1)[0]
+
+    def forward(self, feat_init, guidance, confidence=None, feat_fix=None, rgb=None):
+        assert self.ch_g == guidance.shape[1]
+        assert self.ch_f == feat_init.shape[1]
+        if self.args.conf_prop:
+            assert confidence is not None
+        offset, aff = self._get_offset_affinity(guidance, confidence if self.args.conf_prop else None, rgb)
+
+        mask_fix = None
+        fix = None
+        if self.args.preserve_input:
+            assert feat_init.shape == feat_fix.shape
+            mask_fix = torch.sum(feat_fix > 0.0, dim=1, keepdim=True).detach()
+            mask_fix = (mask_fix > 0.0).type_as(feat_fix)
+            fix = feat_fix
+
+        feats = F.iterate(feat_init, aff, offset, self.prop_time, fix, mask_fix)
+        list_feat = list(feats.unbind(0))
+        feat_result = list_feat[-1]
+        return feat_result, list_feat, offset, aff, self.aff_scale_const.data

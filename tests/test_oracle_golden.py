@@ -125,3 +125,17 @@ def test_backward_is_gradient_of_forward():
                 num = (f(args_p["init"], args_p["weight"], args_p["offset"], w9)
                        - f(args_m["init"], args_m["weight"], args_m["offset"], w9)) / (2 * eps)
                 assert abs(num - grad[ix]) < 1e-6 * max(1, abs(num)), (mode, name, ix, num, grad[ix])
+
+
+@pytest.mark.parametrize("path", PP, ids=[os.path.basename(p)[:-4] for p in PP])
+def test_ref_port_matches_fixtures(path):
+    """oracle/ref_port.py (what bench.py times as the CPU baseline) against the real reference's outputs."""
+    import torch
+    from oracle import ref_port
+    z = np.load(path)
+    t = lambda k: torch.from_numpy(z["in_" + k])
+    mode, scale = int(z["norm_mode"]), float(z["scale"])
+    out, gw, go, gw9, gb = ref_port.postprocessor_step(t("init"), t("weight"), t("offset"), t("w"), t("b"),
+                                                       t("grad_out"), residual=(mode == 1), scale=scale)
+    for got, key in ((out, "out"), (gw, "grad_weight"), (go, "grad_offset"), (gw9, "grad_w"), (gb, "grad_b")):
+        np.testing.assert_allclose(got.numpy(), z["f32_" + key], rtol=1e-6, atol=1e-6, err_msg=key)
