@@ -18,12 +18,17 @@ namespace jspsr {
 constexpr int TILE_W = 128;
 constexpr int TILE_H = 16;
 constexpr int HALO_T = 6, HALO_B = 7;   // rows above / below  (bottom needs the +1 bilinear row)
-constexpr int HALO_L = 6, HALO_R = 10;  // cols left / right   (right padded so SW % 4 == 0)
+// cols left / right.  Measured on B200 (tools/tma_probe.cu): the innermost TMA box
+// coordinate must be 16-byte aligned (c0 * sizeof(T) % 16 == 0; negative is fine, an
+// unaligned c0 raises "illegal instruction"), rows are free.  x0 is a multiple of 128, so
+// a left halo of 8 keeps x0 - 8 aligned for fp32 and bf16; SW must be a multiple of 8
+// elements for the bf16 box (inner extent multiple of 16 bytes).
+constexpr int HALO_L = 8, HALO_R = 8;
 constexpr int SW = TILE_W + HALO_L + HALO_R;  // 144
 constexpr int SH = TILE_H + HALO_T + HALO_B;  // 29
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-static_assert(SW % 4 == 0, "TMA inner box extent must be a multiple of 16 bytes");
+static_assert(SW % 8 == 0 && HALO_L % 8 == 0 && TILE_W % 8 == 0, "TMA inner box extent / origin must be multiples of 16 bytes");
 static_assert(SW <= 256 && SH <= 256, "TMA box extents are limited to 256");
 
 enum { NORM_NONE = 0, NORM_RESIDUAL = 1, NORM_SUM = 2 };
