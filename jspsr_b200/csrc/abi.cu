@@ -64,7 +64,7 @@ static bool tma_disabled_by_env() {
 }
 
 // Returns true when the TMA path can be used for this buffer (and fills *map).
-static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, int W, bool bf16) {
+static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, int W, bool bf16, int tile_h) {
     if (tma_disabled_by_env()) return false;
     const size_t es = bf16 ? 2 : 4;
     if (((uintptr_t)init & 15) != 0) return false;
@@ -73,7 +73,7 @@ static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, 
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)W * es, (cuuint64_t)W * es * (cuuint64_t)rows};
-    cuuint32_t box[3] = {(cuuint32_t)SW, (cuuint32_t)SH, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)SW, (cuuint32_t)staged_rows(tile_h), 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                      const_cast<void*>(init), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -93,10 +93,29 @@ static int check_align(const void* p, size_t a, const char* name) {
     if (p && ((uintptr_t)p % a) != 0) return fail(JSPSR_ERR_ALIGN, "%s is not aligned to %zu bytes", name, a);
     return 0;
 }
-static int fill_geom(Geom* g, int B, int Hs, int W, int H_img, int row0, int init_row0, int init_rows) {
+// Rows per CTA: the largest of max_th/../2 that still gives the grid two CTAs per SM (small batches
+// are latency bound: more, shorter CTAs; large ones want the least halo overhead).  The forward is
+// fastest at 16 rows, the backward at 8 (measured, see spn_kernels.cuh).  JSPSR_SPN_TILE_H overrides.
+static int choose_tile_h(int B, int Hs, int W, int max_th) {
+    if (const char* e = getenv("JSPSR_SPN_TILE_H")) {
+        const int v = atoi(e);
+        if (v == 16 || v == 8 || v == 4 || v == 2) return v;
+    }
+    const size_t tx = (size_t)(W + TILE_W - 1) / TILE_W;
+    for (int th = max_th; th > 2; th >>= 1) {
+        const size_t tiles = tx * (size_t)((Hs + th - 1) / th) * (size_t)B;
+        if (tiles >= (size_t)148 * 2) return th;
+    }
+    return 2;
+}
+
+static int fill_geom(LaunchArgs* la, int B, int Hs, int W, int H_img, int row0, int init_row0, int init_rows,
+                     int max_th) {
+    Geom* g = &la->g;
+    la->tile_h = choose_tile_h(B, Hs, W, max_th);
     g->B = B; g->H = Hs; g->W = W; g->H_img = H_img; g->row0 = row0; g->init_row0 = init_row0; g->init_rows = init_rows;
     g->tiles_x = (W + TILE_W - 1) / TILE_W;
-    g->tiles_y = (Hs + TILE_H - 1) / TILE_H;
+    g->tiles_y = (Hs + la->tile_h - 1) / la->tile_h;
     const size_t tiles = (size_t)g->tiles_x * g->tiles_y * B;
     if (tiles > 0x7fffffffull) return fail(JSPSR_ERR_UNSUPPORTED, "too many tiles (%zu) for one launch", tiles);
     return 0;
@@ -125,11 +144,11 @@ int jspsr_spn_forward_strip(const void* init, const void* weight, const void* of
     if (int e = check_align(w9, 4, "w9")) return e;
     if (int e = check_align(b1, 4, "b1")) return e;
     LaunchArgs la;
-    if (int e = fill_geom(&la.g, B, Hs, W, H_img, row0, init_row0, init_rows)) return e;
+    if (int e = fill_geom(&la, B, Hs, W, H_img, row0, init_row0, init_rows, 16)) return e;
     la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9; la.b1 = b1; la.out = out;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.status = status;
     la.stream = (cudaStream_t)stream;
-    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, la.bf16);
+    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, la.bf16, la.tile_h);
     cudaError_t ce = launch_spn_forward(la);
     if (ce != cudaSuccess) return cuda_fail(ce, "spn_forward launch");
     return JSPSR_OK;
@@ -161,13 +180,13 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     if (int e = check_align(grad_init, 4, "grad_init")) return e;
     if (int e = check_align(workspace, 16, "workspace")) return e;
     LaunchArgs la;
-    if (int e = fill_geom(&la.g, B, H, W, H, 0, 0, H)) return e;
+    if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 8)) return e;
     la.grad_out = grad_out; la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9;
     la.grad_init = grad_init; la.grad_weight = grad_weight; la.grad_offset = grad_offset;
     la.grad_w9 = grad_w9; la.grad_b1 = grad_b1; la.workspace = workspace;
     la.accumulate = (flags & JSPSR_BWD_ACCUMULATE) != 0;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.stream = (cudaStream_t)stream;
-    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, la.bf16);
+    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, la.bf16, la.tile_h);
     if (grad_init) {
         cudaError_t ce = cudaMemsetAsync(grad_init, 0, (size_t)B * H * W * sizeof(float), la.stream);
         if (ce != cudaSuccess) return cuda_fail(ce, "grad_init memset");
@@ -205,10 +224,10 @@ int jspsr_spn_iterate(const void* feat_init, const void* aff, const void* offset
         }
         char* dst = (char*)list_out + (size_t)t * n * es;
         LaunchArgs la;
-        if (int e = fill_geom(&la.g, B, H, W, H, 0, 0, H)) return e;
+        if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 16)) return e;
         la.init = src; la.weight = aff; la.offset = offset; la.w9 = nullptr; la.b1 = nullptr; la.out = dst;
         la.mode = NORM_NONE; la.scale = 0.f; la.bf16 = bf16; la.stream = (cudaStream_t)stream;
-        la.use_tma = make_init_tmap(&la.tmap, src, B, H, W, bf16);
+        la.use_tma = make_init_tmap(&la.tmap, src, B, H, W, bf16, la.tile_h);
         cudaError_t ce = launch_spn_forward(la);
         if (ce != cudaSuccess) return cuda_fail(ce, "spn_iterate launch");
         src = dst;

@@ -20,13 +20,18 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
     atomicAdd(gi_b + (size_t)br * g.W + wi, v);
 }
 
-template <typename T, int MODE, bool TMA, bool GRAD_INIT>
+// ACC: grad_weight / grad_offset are added to (fixed-affinity T-step loop) instead of written.
+// CS : compile-time channel stride H*W (0 = runtime), see spn_forward.cu.
+// TH : rows per CTA.  `mode` is a runtime, warp-uniform switch.
+template <typename T, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH>
 __global__ void __launch_bounds__(THREADS, BWD_MIN_BLOCKS)
 spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, const T* __restrict__ weight,
                     const T* __restrict__ offset, const float* __restrict__ w9, float* __restrict__ grad_init,
                     T* __restrict__ grad_weight, T* __restrict__ grad_offset, float* __restrict__ grad_w9,
-                    float* __restrict__ grad_b1, ReduceWs* __restrict__ ws, const Geom g, const float scale,
-                    const bool accumulate, const __grid_constant__ CUtensorMap tmap) {
+                    float* __restrict__ grad_b1, ReduceWs* __restrict__ ws, const Geom g, const int mode,
+                    const float scale, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int SH = staged_rows(TH);
+    constexpr int PPT = pixels_per_thread(TH);
     __shared__ __align__(128) T tile[SH * SW];
     __shared__ __align__(16) float gtile[GRAD_INIT ? SH * SW : 1];
     __shared__ __align__(8) uint64_t bar;
@@ -34,15 +39,15 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     __shared__ float s_red[WARPS][10];
     __shared__ bool s_last;
 
-    TileCtx c = make_tile_ctx(g);
-    stage_tile_begin<T, TMA>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
+    const TileCtx c = make_tile_ctx<TH>(g);
+    stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
     if (GRAD_INIT) {
         for (int i = threadIdx.x; i < SH * SW; i += THREADS) gtile[i] = 0.f;
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t cs = (size_t)g.H * g.W;
+    const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
     const T* gout_b = gout + (size_t)c.b * cs;
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
@@ -50,23 +55,30 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     T* gwgt_b = grad_weight + (size_t)c.b * 9 * cs;
     T* goff_b = grad_offset + (size_t)c.b * 18 * cs;
     float* gi_b = GRAD_INIT ? grad_init + (size_t)c.b * g.init_rows * g.W : nullptr;
+    const T* tile_lo = tile + c.r_lo * SW;
+    float* gtile_lo = gtile + (GRAD_INIT ? c.r_lo * SW : 0);
 
     float a[9], oh[9], ow[9], go;
     auto load_inputs = [&](int it, bool& active, size_t& p) {
-        const int y = c.y0 + warp + WARPS * (it / (TILE_W / 32));
-        const int x = c.x0 + lane + 32 * (it % (TILE_W / 32));
+        const int y = c.y0 + pix_row<TH, true>(it), x = c.x0 + pix_col<TH, true>(it);
         active = (y < g.H) && (x < g.W);
         p = (size_t)y * g.W + x;
         if (active) {
+            const T* pw = wgt_b + p;
+            const T* po = off_b + p;
             go = ld_stream(gout_b + p);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a[k] = ld_stream(wgt_b + k * cs + p);
+            for (int k = 0; k < 9; ++k) a[k] = ld_stream(pw + k * cs);
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                oh[k] = ld_stream(off_b + (2 * k) * cs + p);
-                ow[k] = ld_stream(off_b + (2 * k + 1) * cs + p);
+                oh[k] = ld_stream(po + (2 * k) * cs);
+                ow[k] = ld_stream(po + (2 * k + 1) * cs);
             }
         }
+    };
+    auto store = [&](T* ptr, float v) {
+        if (ACC) v += to_f32(*ptr);
+        st_stream(ptr, v);
     };
 
     float acc_w[9], acc_b = 0.f;  // this thread's share of grad_w / grad_b
@@ -79,62 +91,77 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     stage_tile_wait<TMA>(&bar);
 
 #pragma unroll 1
-    for (int it = 0; it < PIX_PER_THREAD; ++it) {
+    for (int it = 0; it < PPT; ++it) {
         if (it > 0) load_inputs(it, active, p);
         if (!active) continue;
-        const int ry = warp + WARPS * (it / (TILE_W / 32));
-        const int cx = lane + 32 * (it % (TILE_W / 32));
+        const int ry = pix_row<TH, true>(it), cx = pix_col<TH, true>(it);
 
-        float s = 0.f;  // sum of raw affinities (NORM_SUM Jacobian)
-        if (MODE == NORM_SUM) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) s += a[k];
-        }
-        normalise9<MODE>(a);  // a[] now holds the modulation m_k
+        const float s = normalise9(a, mode);  // a[] now holds the modulation m_k; s = raw sum
 
         const float fy = (float)(g.row0 + c.y0 + ry), fx = (float)(c.x0 + cx);
+        const float hk[3] = {fy - 1.f, fy, fy + 1.f};
+        const float wk[3] = {fx - 1.f, fx, fx + 1.f};
+        T* po = goff_b + p;
         float gm[9];
+        unsigned slow = 0u;
         acc_b += go;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const float h = (fy + (float)(k / 3 - 1)) + oh[k];
-            const float w = (fx + (float)(k % 3 - 1)) + ow[k];
-            const Tap t = gather_tap<T>(tile, init_b, g, c, h, w, nullptr);
-            const float hh = 1.f - t.lh, hw = 1.f - t.lw;
-            const float val = hh * hw * t.v1 + hh * t.lw * t.v2 + t.lh * hw * t.v3 + t.lh * t.lw * t.v4;
-            // get_coordinate_weight
-            const float dh = t.lw * (t.v4 - t.v2) + hw * (t.v3 - t.v1);
-            const float dw = t.lh * (t.v4 - t.v3) + hh * (t.v2 - t.v1);
-            const float gk = go * s_w[k];   // dL/d(column_k)
-            const float gkm = gk * a[k];
-            acc_w[k] += go * (a[k] * val);
-            gm[k] = gk * val;
-            float goh = gkm * dh, gow = gkm * dw;
-            T* po = goff_b + (2 * k) * cs + p;
-            if (accumulate) {
-                goh += to_f32(po[0]);
-                gow += to_f32(po[cs]);
+            const FastTap t = fast_tap<T>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+            // value and both derivatives (torchvision get_coordinate_weight) share the two row differences
+            const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
+            const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
+            float dh = bot - top;
+            float val = fmaf(t.lh, dh, top);
+            float dw = fmaf(t.lh, d43 - d21, d21);
+            if (!t.ok) {
+                val = dh = dw = 0.f;
+                slow |= 1u << k;
             }
-            st_stream(po, goh);
-            st_stream(po + cs, gow);
+            const float ga = go * a[k];          // go * m_k
+            const float gkm = ga * s_w[k];       // dL/d(sample_k)
+            acc_w[k] = fmaf(ga, val, acc_w[k]);
+            gm[k] = (go * s_w[k]) * val;
+            store(po + (2 * k) * cs, gkm * dh);
+            store(po + (2 * k + 1) * cs, gkm * dw);
             if (GRAD_INIT) {
-                const float c1 = gkm * hh * hw, c2 = gkm * hh * t.lw, c3 = gkm * t.lh * hw, c4 = gkm * t.lh * t.lw;
-                if (t.in_tile) {
-                    float* gt = gtile + ((unsigned)t.h0 - (unsigned)c.oy) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
-                    atomicAdd(gt, c1);
+                if (t.ok) {
+                    const float ch = gkm * t.lh, cl = gkm - ch;  // rows h0+1 / h0
+                    const float c2 = cl * t.lw, c4 = ch * t.lw;
+                    float* gt = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
+                    atomicAdd(gt, cl - c2);
                     atomicAdd(gt + 1, c2);
-                    atomicAdd(gt + SW, c3);
+                    atomicAdd(gt + SW, ch - c4);
                     atomicAdd(gt + SW + 1, c4);
-                } else if (fabsf(h) < 1.0e9f && fabsf(w) < 1.0e9f) {
-                    scatter_corner_global<T>(gi_b, g, t.h0, t.w0, c1);
-                    scatter_corner_global<T>(gi_b, g, t.h0, t.w0 + 1, c2);
-                    scatter_corner_global<T>(gi_b, g, t.h0 + 1, t.w0, c3);
-                    scatter_corner_global<T>(gi_b, g, t.h0 + 1, t.w0 + 1, c4);
+                }
+            }
+        }
+        if (slow) {  // rare: flagged taps through the bounds-checked global path
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (slow & (1u << k)) {
+                    const float h = hk[k / 3] + oh[k], w = wk[k % 3] + ow[k];
+                    const SlowTap t = slow_tap<T>(init_b, g, h, w, nullptr);
+                    const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
+                    const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
+                    const float dh = bot - top, val = fmaf(t.lh, dh, top), dw = fmaf(t.lh, d43 - d21, d21);
+                    const float ga = go * a[k], gkm = ga * s_w[k];
+                    acc_w[k] = fmaf(ga, val, acc_w[k]);
+                    gm[k] += (go * s_w[k]) * val;
+                    store(po + (2 * k) * cs, gkm * dh);      // the fast pass stored 0 here (ACC: added 0)
+                    store(po + (2 * k + 1) * cs, gkm * dw);
+                    if (GRAD_INIT && t.finite) {
+                        const float ch = gkm * t.lh, cl = gkm - ch, c2 = cl * t.lw, c4 = ch * t.lw;
+                        scatter_corner_global<T>(gi_b, g, t.h0, t.w0, cl - c2);
+                        scatter_corner_global<T>(gi_b, g, t.h0, t.w0 + 1, c2);
+                        scatter_corner_global<T>(gi_b, g, t.h0 + 1, t.w0, ch - c4);
+                        scatter_corner_global<T>(gi_b, g, t.h0 + 1, t.w0 + 1, c4);
+                    }
                 }
             }
         }
         // Jacobian of the normalisation
-        if (MODE == NORM_RESIDUAL) {
+        if (mode == NORM_RESIDUAL) {
             float sg = gm[0];
 #pragma unroll
             for (int k = 1; k < 9; ++k) sg += gm[k];
@@ -142,20 +169,17 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
 #pragma unroll
             for (int k = 0; k < 9; ++k) gm[k] -= mean;
             if (GRAD_INIT) atomicAdd(gtile + (ry + HALO_T) * SW + (cx + HALO_L), scale * go);
-        } else if (MODE == NORM_SUM) {
+        } else if (mode == NORM_SUM) {
             float dot = 0.f;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) dot += gm[k] * a[k];
+            for (int k = 0; k < 9; ++k) dot = fmaf(gm[k], a[k], dot);
+            const float inv = __fdiv_rn(1.f, s);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) gm[k] = __fdiv_rn(gm[k] - dot, s);
+            for (int k = 0; k < 9; ++k) gm[k] = (gm[k] - dot) * inv;
         }
+        T* pw = gwgt_b + p;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            T* pw = gwgt_b + k * cs + p;
-            float v = gm[k];
-            if (accumulate) v += to_f32(pw[0]);
-            st_stream(pw, v);
-        }
+        for (int k = 0; k < 9; ++k) store(pw + k * cs, gm[k]);
     }
 
     // ---- grad_init: flush the shared accumulation tile ----
@@ -207,34 +231,47 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     }
 }
 
-template <typename T, int MODE, bool TMA, bool GI>
-static void launch_one(const LaunchArgs& la, dim3 grid) {
-    spn_backward_kernel<T, MODE, TMA, GI><<<grid, THREADS, 0, la.stream>>>(
+template <typename T, bool TMA, bool GI, bool ACC, int CS, int TH>
+static void launch_one(const LaunchArgs& la) {
+    dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
+    spn_backward_kernel<T, TMA, GI, ACC, CS, TH><<<grid, THREADS, 0, la.stream>>>(
         (const T*)la.grad_out, (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.grad_init,
-        (T*)la.grad_weight, (T*)la.grad_offset, la.grad_w9, la.grad_b1, (ReduceWs*)la.workspace, la.g, la.scale,
-        la.accumulate, la.tmap);
+        (T*)la.grad_weight, (T*)la.grad_offset, la.grad_w9, la.grad_b1, (ReduceWs*)la.workspace, la.g, la.mode,
+        la.scale, la.tmap);
 }
 
-template <typename T, int MODE>
-static cudaError_t launch_bwd_mode(const LaunchArgs& la) {
-    dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
+// (TMA, CS) variants: the compile-time stride only exists for 128x128-pixel planes, which always qualify for TMA
+template <typename T, bool GI, bool ACC, int TH>
+static void launch_variant(const LaunchArgs& la) {
+    const size_t cs = (size_t)la.g.H * la.g.W;
+    if (la.use_tma && cs == 16384) launch_one<T, true, GI, ACC, 16384, TH>(la);
+    else if (la.use_tma) launch_one<T, true, GI, ACC, 0, TH>(la);
+    else launch_one<T, false, GI, ACC, 0, TH>(la);
+}
+
+template <typename T, int TH>
+static cudaError_t launch_bwd_th(const LaunchArgs& la) {
     const bool gi = la.grad_init != nullptr;
-    if (la.use_tma) {
-        if (gi) launch_one<T, MODE, true, true>(la, grid);
-        else launch_one<T, MODE, true, false>(la, grid);
+    if (la.accumulate) {
+        // only the fixed-affinity loop accumulates (NLSPN backward: grad_init always needed)
+        if (!gi) return cudaErrorNotSupported;
+        launch_variant<T, true, true, TH>(la);
+    } else if (gi) {
+        launch_variant<T, true, false, TH>(la);
     } else {
-        if (gi) launch_one<T, MODE, false, true>(la, grid);
-        else launch_one<T, MODE, false, false>(la, grid);
+        launch_variant<T, false, false, TH>(la);
     }
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_bwd_dtype(const LaunchArgs& la) {
-    switch (la.mode) {
-        case NORM_NONE: return launch_bwd_mode<T, NORM_NONE>(la);
-        case NORM_RESIDUAL: return launch_bwd_mode<T, NORM_RESIDUAL>(la);
-        default: return launch_bwd_mode<T, NORM_SUM>(la);
+    switch (la.tile_h) {
+        case 16: return launch_bwd_th<T, 16>(la);
+        case 8: return launch_bwd_th<T, 8>(la);
+        case 4: return launch_bwd_th<T, 4>(la);
+        case 2: return launch_bwd_th<T, 2>(la);
+        default: return cudaErrorInvalidValue;
     }
 }
 

@@ -16,7 +16,10 @@ namespace jspsr {
 // exactly torchvision's zero-outside rule) can fill it.
 // ---------------------------------------------------------------------------
 constexpr int TILE_W = 128;
-constexpr int TILE_H = 16;
+// Rows per CTA are a template parameter TH in {16, 8, 4, 2}: 16 for large problems (least
+// halo overhead, 8 pixels per thread), smaller for small batches so that the grid still
+// covers all 148 SMs a few times over and a thread's serial chain of pixels stays short
+// (the reference's own batch of 70 tiles is only 560 CTAs at TH = 16).
 constexpr int HALO_T = 6, HALO_B = 7;   // rows above / below  (bottom needs the +1 bilinear row)
 // cols left / right.  Measured on B200 (tools/tma_probe.cu): the innermost TMA box
 // coordinate must be 16-byte aligned (c0 * sizeof(T) % 16 == 0; negative is fine, an
@@ -25,11 +28,11 @@ constexpr int HALO_T = 6, HALO_B = 7;   // rows above / below  (bottom needs the
 // elements for the bf16 box (inner extent multiple of 16 bytes).
 constexpr int HALO_L = 8, HALO_R = 8;
 constexpr int SW = TILE_W + HALO_L + HALO_R;  // 144
-constexpr int SH = TILE_H + HALO_T + HALO_B;  // 29
+constexpr int staged_rows(int th) { return th + HALO_T + HALO_B; }  // 29 for TH = 16
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 static_assert(SW % 8 == 0 && HALO_L % 8 == 0 && TILE_W % 8 == 0, "TMA inner box extent / origin must be multiples of 16 bytes");
-static_assert(SW <= 256 && SH <= 256, "TMA box extents are limited to 256");
+static_assert(SW <= 256 && staged_rows(16) <= 256, "TMA box extents are limited to 256");
 
 enum { NORM_NONE = 0, NORM_RESIDUAL = 1, NORM_SUM = 2 };
 
@@ -123,9 +126,10 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // zero either way; whether a zero row is *legitimate* (outside the image) or a
 // missing halo row is decided per tap through [r_lo, r_lo + r_span).
 // ---------------------------------------------------------------------------
-template <typename T, bool TMA>
+template <typename T, bool TMA, int TH>
 __device__ __forceinline__ void stage_tile_begin(T* tile, uint64_t* bar, const CUtensorMap* tmap, const T* init,
                                                  const Geom& g, int b, int ox, int oy_buf) {
+    constexpr int SH = staged_rows(TH);
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);

@@ -10,42 +10,50 @@
 
 namespace jspsr {
 
-template <typename T, int MODE, bool TMA>
+// CS: compile-time channel stride H*W (0 = runtime).  With CS known (the reference's
+// 128x128 tiles: 16384) the 27 channel loads of a pixel share one address register with
+// immediate offsets instead of a 64-bit add per channel.
+// TH: rows per CTA (see spn_common.cuh).  `mode` (normalisation) is a runtime, warp-uniform switch.
+template <typename T, bool TMA, int CS, int TH>
 __global__ void __launch_bounds__(THREADS, FWD_MIN_BLOCKS)
 spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, const T* __restrict__ offset,
                    const float* __restrict__ w9, const float* __restrict__ b1, T* __restrict__ out, const Geom g,
-                   const float scale, int* __restrict__ status, const __grid_constant__ CUtensorMap tmap) {
+                   const int mode, const float scale, int* __restrict__ status,
+                   const __grid_constant__ CUtensorMap tmap) {
+    constexpr int SH = staged_rows(TH);
+    constexpr int PPT = pixels_per_thread(TH);
     __shared__ __align__(128) T tile[SH * SW];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_w[10];
 
-    TileCtx c = make_tile_ctx(g);
-    stage_tile_begin<T, TMA>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
+    const TileCtx c = make_tile_ctx<TH>(g);
+    stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     // w9 == nullptr: frozen unit weight / zero bias (NLSPN, nlspn.py:61-65)
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
     if (threadIdx.x == 9) s_w[9] = b1 ? b1[0] : 0.f;
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t cs = (size_t)g.H * g.W;  // channel stride
+    const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;  // channel stride
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
     const T* init_b = init + (size_t)c.b * g.init_rows * g.W;
     T* out_b = out + (size_t)c.b * cs;
+    const T* tile_lo = tile + c.r_lo * SW;
 
-    // pixel `it` of this thread: row warp + WARPS*(it / 4) of the tile, column lane + 32*(it % 4)
+    // pixel `it` of this thread: linear index it*256 + tid in the TH x 128 block (a warp = 32 consecutive x)
     float a[9], oh[9], ow[9];
     auto load_inputs = [&](int it, bool& active, size_t& p) {
-        const int y = c.y0 + warp + WARPS * (it / (TILE_W / 32));
-        const int x = c.x0 + lane + 32 * (it % (TILE_W / 32));
+        const int y = c.y0 + pix_row<TH, false>(it), x = c.x0 + pix_col<TH, false>(it);
         active = (y < g.H) && (x < g.W);
         p = (size_t)y * g.W + x;
         if (active) {
+            const T* pw = wgt_b + p;
+            const T* po = off_b + p;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a[k] = ld_stream(wgt_b + k * cs + p);
+            for (int k = 0; k < 9; ++k) a[k] = ld_stream(pw + k * cs);
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                oh[k] = ld_stream(off_b + (2 * k) * cs + p);
-                ow[k] = ld_stream(off_b + (2 * k + 1) * cs + p);
+                oh[k] = ld_stream(po + (2 * k) * cs);
+                ow[k] = ld_stream(po + (2 * k + 1) * cs);
             }
         }
     };
@@ -57,52 +65,72 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     stage_tile_wait<TMA>(&bar);
 
 #pragma unroll 1
-    for (int it = 0; it < PIX_PER_THREAD; ++it) {
+    for (int it = 0; it < PPT; ++it) {
         if (it > 0) load_inputs(it, active, p);
         if (!active) continue;
-        const int ry = warp + WARPS * (it / (TILE_W / 32));
-        const int cx = lane + 32 * (it % (TILE_W / 32));
-        normalise9<MODE>(a);
+        const int ry = pix_row<TH, false>(it), cx = pix_col<TH, false>(it);
+        normalise9(a, mode);
 
+        // torchvision: (out_y - pad + i*dil) formed as an integer, converted, + offset
         const float fy = (float)(g.row0 + c.y0 + ry), fx = (float)(c.x0 + cx);
-        float acc = 0.f;
+        const float hk[3] = {fy - 1.f, fy, fy + 1.f};
+        const float wk[3] = {fx - 1.f, fx, fx + 1.f};
+        // Each tap's contribution replaces its (normalised) affinity in a[]; a flagged tap keeps the
+        // affinity until the slow pass has its value.  The final sum runs in tap order whatever the
+        // mix of fast and slow taps, so the result does not depend on tiling or strip layout.
+        unsigned slow = 0u;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            // torchvision: (out_y - pad + i*dil) formed as an integer, converted, + offset
-            const float h = (fy + (float)(k / 3 - 1)) + oh[k];
-            const float w = (fx + (float)(k % 3 - 1)) + ow[k];
-            const Tap t = gather_tap<T>(tile, init_b, g, c, h, w, status);
-            const float hh = 1.f - t.lh, hw = 1.f - t.lw;
-            const float val = hh * hw * t.v1 + hh * t.lw * t.v2 + t.lh * hw * t.v3 + t.lh * t.lw * t.v4;
-            acc += s_w[k] * (a[k] * val);
+            const FastTap t = fast_tap<T>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+            const float val = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+            a[k] = t.ok ? (s_w[k] * a[k]) * val : a[k];
+            slow |= t.ok ? 0u : (1u << k);
         }
+        if (slow) {  // rare: redo the flagged taps through the bounds-checked global path
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (slow & (1u << k)) {
+                    const SlowTap t = slow_tap<T>(init_b, g, hk[k / 3] + oh[k], wk[k % 3] + ow[k], status);
+                    a[k] = (s_w[k] * a[k]) * bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+                }
+            }
+        }
+        float acc = a[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) acc += a[k];
         acc += s_w[9];
-        if (MODE == NORM_RESIDUAL) acc += scale * to_f32(tile[(ry + HALO_T) * SW + (cx + HALO_L)]);
+        if (mode == NORM_RESIDUAL) acc = fmaf(scale, to_f32(tile[(ry + HALO_T) * SW + (cx + HALO_L)]), acc);
         st_stream(out_b + p, acc);
     }
 }
 
-template <typename T, int MODE>
-static cudaError_t launch_fwd_mode(const LaunchArgs& la) {
+template <typename T, bool TMA, int CS, int TH>
+static void launch_fwd_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    if (la.use_tma)
-        spn_forward_kernel<T, MODE, true><<<grid, THREADS, 0, la.stream>>>(
-            (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (T*)la.out, la.g, la.scale,
-            la.status, la.tmap);
-    else
-        spn_forward_kernel<T, MODE, false><<<grid, THREADS, 0, la.stream>>>(
-            (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (T*)la.out, la.g, la.scale,
-            la.status, la.tmap);
-    return cudaGetLastError();
+    spn_forward_kernel<T, TMA, CS, TH><<<grid, THREADS, 0, la.stream>>>(
+        (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (T*)la.out, la.g, la.mode, la.scale,
+        la.status, la.tmap);
+}
+
+// (TMA, CS) variants: the compile-time stride only exists for 128x128-pixel planes, which always qualify for TMA
+template <typename T, int TH>
+static void launch_fwd_th(const LaunchArgs& la) {
+    const size_t cs = (size_t)la.g.H * la.g.W;
+    if (la.use_tma && cs == 16384) launch_fwd_one<T, true, 16384, TH>(la);
+    else if (la.use_tma) launch_fwd_one<T, true, 0, TH>(la);
+    else launch_fwd_one<T, false, 0, TH>(la);
 }
 
 template <typename T>
 static cudaError_t launch_fwd_dtype(const LaunchArgs& la) {
-    switch (la.mode) {
-        case NORM_NONE: return launch_fwd_mode<T, NORM_NONE>(la);
-        case NORM_RESIDUAL: return launch_fwd_mode<T, NORM_RESIDUAL>(la);
-        default: return launch_fwd_mode<T, NORM_SUM>(la);
+    switch (la.tile_h) {
+        case 16: launch_fwd_th<T, 16>(la); break;
+        case 8: launch_fwd_th<T, 8>(la); break;
+        case 4: launch_fwd_th<T, 4>(la); break;
+        case 2: launch_fwd_th<T, 2>(la); break;
+        default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_spn_forward(const LaunchArgs& la) {

@@ -7,7 +7,25 @@ namespace jspsr {
 
 constexpr int FWD_MIN_BLOCKS = 4;  // 1024 threads/SM, <= 64 registers/thread
 constexpr int BWD_MIN_BLOCKS = 3;
-constexpr int PIX_PER_THREAD = (TILE_H / WARPS) * (TILE_W / 32);  // 8
+constexpr int pixels_per_thread(int th) { return th * TILE_W / THREADS; }  // 8 for TH = 16
+
+// Pixel `it` of a thread inside the TH x 128 block.  A warp always covers 32 consecutive x of
+// one row (coalesced 128-byte lines).  Two mappings, chosen per kernel from measurements
+// (B200, 4096 tiles of 128x128, fp32):
+//   LINEAR = false: warp w owns rows w, w+8, ... and walks the four 32-column segments of a row
+//                   (forward: 1.27 ms vs 1.37 ms linear)
+//   LINEAR = true : pixel index it*256 + tid, two full rows per pass
+//                   (backward at TH = 8: 2.47 ms vs 2.57 ms for rows/TH = 16)
+template <int TH, bool LINEAR>
+__device__ __forceinline__ int pix_row(int it) {
+    if (!LINEAR && TH >= 2 * WARPS) return (int)(threadIdx.x >> 5) + WARPS * (it / (TILE_W / 32));
+    return (it * THREADS + (int)threadIdx.x) >> 7;
+}
+template <int TH, bool LINEAR>
+__device__ __forceinline__ int pix_col(int it) {
+    if (!LINEAR && TH >= 2 * WARPS) return (int)(threadIdx.x & 31) + 32 * (it % (TILE_W / 32));
+    return (it * THREADS + (int)threadIdx.x) & (TILE_W - 1);
+}
 
 struct TileCtx {
     int b;        // sample
@@ -15,9 +33,12 @@ struct TileCtx {
     int ox, oy;   // GLOBAL column / row of staged-tile element [0][0]
     int r_lo;     // staged rows [r_lo, r_lo + r_span] hold correct data for a (r, r+1) pair
     unsigned r_span;
+    unsigned oy_lo;  // (unsigned)(oy + r_lo): global row of the first trusted staged row
 };
 
+template <int TH>
 __device__ __forceinline__ TileCtx make_tile_ctx(const Geom& g) {
+    constexpr int SH = staged_rows(TH);
     TileCtx c;
     unsigned t = blockIdx.x;
     const int tx = t % g.tiles_x;
@@ -25,7 +46,7 @@ __device__ __forceinline__ TileCtx make_tile_ctx(const Geom& g) {
     const int ty = t % g.tiles_y;
     c.b = t / g.tiles_y;
     c.x0 = tx * TILE_W;
-    c.y0 = ty * TILE_H;
+    c.y0 = ty * TH;
     c.ox = c.x0 - HALO_L;
     c.oy = g.row0 + c.y0 - HALO_T;
     // A staged row is trustworthy when it lies outside the image (zero is the right
@@ -35,69 +56,93 @@ __device__ __forceinline__ TileCtx make_tile_ctx(const Geom& g) {
     if (g.init_row0 + g.init_rows < g.H_img) hi = min(SH, g.init_row0 + g.init_rows - c.oy);
     c.r_lo = lo;
     c.r_span = (hi - 1 > lo) ? (unsigned)(hi - 1 - lo) : 0u;
+    c.oy_lo = (unsigned)(c.oy + lo);
     return c;
 }
 
-template <int MODE>
-__device__ __forceinline__ void normalise9(float (&a)[9]) {
-    if (MODE == NORM_NONE) return;
+// a2 of SURVEY section 8: residual -> subtract the tap mean; sum -> divide by the tap sum.
+// `mode` is warp-uniform (a kernel argument).  Returns the raw sum (needed by the
+// sum-mode Jacobian).  Sum mode multiplies by one correctly rounded reciprocal instead of
+// nine divisions (<= 1 ulp from torch's a / s).
+__device__ __forceinline__ float normalise9(float (&a)[9], int mode) {
+    if (mode == NORM_NONE) return 0.f;
     float s = a[0];
 #pragma unroll
     for (int k = 1; k < 9; ++k) s += a[k];
-    if (MODE == NORM_RESIDUAL) {
+    if (mode == NORM_RESIDUAL) {
         const float mean = __fdiv_rn(s, 9.f);  // torch.mean: sum / n
 #pragma unroll
         for (int k = 0; k < 9; ++k) a[k] -= mean;
     } else {
+        const float inv = __fdiv_rn(1.f, s);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) a[k] = __fdiv_rn(a[k], s);
+        for (int k = 0; k < 9; ++k) a[k] *= inv;
     }
+    return s;
 }
 
-struct Tap {
-    float v1, v2, v3, v4;  // (h0,w0) (h0,w1) (h1,w0) (h1,w1), zero outside the image
-    float lh, lw;          // fractional parts
-    int h0, w0;            // GLOBAL integer corner
-    bool in_tile;
+// ---------------------------------------------------------------------------
+// Branch-free tap (the hot loop).  Every tap loads its four neighbours from the
+// staged tile through ONE address; a tap whose footprint is not wholly inside the
+// trusted part of the tile reads element 0 instead and is flagged, and the flagged
+// taps of a pixel (rare: offsets beyond the halo, non-finite offsets, strip edges)
+// are redone afterwards through slow_tap().  Keeping branches out of the 9-tap body
+// lets the 36 shared loads of a pixel overlap instead of serialising per tap.
+// ---------------------------------------------------------------------------
+struct FastTap {
+    float v1, v2, v3, v4, lh, lw;
+    int h0, w0;
+    bool ok;
 };
 
-// The four bilinear neighbours of a sample at GLOBAL position (h, w).
-// Fast path: both rows and both columns are inside the staged tile -> 4 shared loads
-// off one address (the tile is zero outside the image, so no bounds logic).
-// Slow path: per-corner bounds-checked global loads.
 template <typename T>
-__device__ __forceinline__ Tap gather_tap(const T* __restrict__ tile, const T* __restrict__ init_b, const Geom& g,
-                                          const TileCtx& c, float h, float w, int* status) {
-    Tap t;
-    const float hf = floorf(h), wf = floorf(w);
-    t.lh = h - hf;
-    t.lw = w - wf;
+__device__ __forceinline__ FastTap fast_tap(const T* __restrict__ tile_lo, const TileCtx& c, float h, float w) {
+    FastTap t;
     t.h0 = __float2int_rd(h);  // saturating; NaN -> 0
     t.w0 = __float2int_rd(w);
-    const unsigned r = (unsigned)t.h0 - (unsigned)c.oy;
+    t.lh = h - floorf(h);
+    t.lw = w - floorf(w);
+    const unsigned r = (unsigned)t.h0 - c.oy_lo;
     const unsigned q = (unsigned)t.w0 - (unsigned)c.ox;
-    t.in_tile = (r - (unsigned)c.r_lo < c.r_span) && (q < (unsigned)(SW - 1));
-    if (t.in_tile) {
-        const T* s = tile + r * SW + q;
-        t.v1 = to_f32(s[0]);
-        t.v2 = to_f32(s[1]);
-        t.v3 = to_f32(s[SW]);
-        t.v4 = to_f32(s[SW + 1]);
-    } else {
-        t.v1 = t.v2 = t.v3 = t.v4 = 0.f;
-        if (fabsf(h) < 1.0e9f && fabsf(w) < 1.0e9f) {
-            // finite position: per-corner validity only.  This equals torchvision's
-            // forward (its whole-sample test changes nothing when corners are checked)
-            // and is exactly its backward (get_coordinate_weight has no such test).
-            t.v1 = fetch_corner_global(init_b, g, t.h0, t.w0, status);
-            t.v2 = fetch_corner_global(init_b, g, t.h0, t.w0 + 1, status);
-            t.v3 = fetch_corner_global(init_b, g, t.h0 + 1, t.w0, status);
-            t.v4 = fetch_corner_global(init_b, g, t.h0 + 1, t.w0 + 1, status);
-        } else if (h == h && w == w) {
-            // +-inf / absurdly far: torchvision returns 0; keep inf - inf = NaN out of it.
-            t.lh = t.lw = 0.f;
-        }  // NaN positions keep lh/lw = NaN so the result is NaN like the reference's
-    }
+    t.ok = (r < c.r_span) && (q < (unsigned)(SW - 1));
+    const T* s = tile_lo + (t.ok ? r * SW + q : 0u);
+    t.v1 = to_f32(s[0]);
+    t.v2 = to_f32(s[1]);
+    t.v3 = to_f32(s[SW]);
+    t.v4 = to_f32(s[SW + 1]);
+    return t;
+}
+
+// bilinear value in lerp form (6 flops; within 1 ulp-ish of torchvision's 4-product form)
+__device__ __forceinline__ float bilerp(float v1, float v2, float v3, float v4, float lh, float lw) {
+    const float top = fmaf(lw, v2 - v1, v1);
+    const float bot = fmaf(lw, v4 - v3, v3);
+    return fmaf(lh, bot - top, top);
+}
+
+// Slow tap: per-corner bounds-checked global loads (exactly torchvision's corner rule).
+struct SlowTap {
+    float v1, v2, v3, v4, lh, lw;
+    int h0, w0;
+    bool finite;
+};
+template <typename T>
+__device__ __noinline__ SlowTap slow_tap(const T* __restrict__ init_b, const Geom g, float h, float w, int* status) {
+    SlowTap t;
+    t.h0 = __float2int_rd(h);
+    t.w0 = __float2int_rd(w);
+    t.lh = h - floorf(h);
+    t.lw = w - floorf(w);
+    t.v1 = t.v2 = t.v3 = t.v4 = 0.f;
+    t.finite = fabsf(h) < 1.0e9f && fabsf(w) < 1.0e9f;
+    if (t.finite) {
+        t.v1 = fetch_corner_global(init_b, g, t.h0, t.w0, status);
+        t.v2 = fetch_corner_global(init_b, g, t.h0, t.w0 + 1, status);
+        t.v3 = fetch_corner_global(init_b, g, t.h0 + 1, t.w0, status);
+        t.v4 = fetch_corner_global(init_b, g, t.h0 + 1, t.w0 + 1, status);
+    } else if (h == h && w == w) {
+        t.lh = t.lw = 0.f;  // +-inf / absurdly far: torchvision returns 0; keep inf - inf = NaN out of it
+    }                       // NaN positions keep lh/lw = NaN so the result is NaN like the reference's
     return t;
 }
 
@@ -124,6 +169,8 @@ struct LaunchArgs {
     bool bf16 = false;
     bool use_tma = false;
     int* status = nullptr;
+    int tile_h = 16;  // rows per CTA (16 / 8 / 4 / 2), chosen by abi.cu; the TMA box is encoded to match
+    int tiles_y_of(int th) const { return (g.H + th - 1) / th; }
     cudaStream_t stream = nullptr;
     CUtensorMap tmap{};
 };
