@@ -214,23 +214,43 @@ int jspsr_spn_iterate(const void* feat_init, const void* aff, const void* offset
         return fail(JSPSR_ERR_BAD_ARG, "feat_fix and mask_fix must be given together");
     if (feat_fix && !scratch) return fail(JSPSR_ERR_BAD_ARG, "preserve_input needs a [B,1,H,W] scratch buffer");
     const bool bf16 = dtype == JSPSR_BF16;
-    const size_t es = bf16 ? 2 : 4, n = (size_t)B * H * W;
-    const char* src = (const char*)feat_init;
-    for (int t = 0; t < T; ++t) {
-        if (feat_fix) {  // nlspn.py:228-229
-            cudaError_t ce = launch_preserve_blend(src, feat_fix, (const float*)mask_fix, scratch, n, bf16, (cudaStream_t)stream);
-            if (ce != cudaSuccess) return cuda_fail(ce, "preserve_input blend launch");
-            src = (const char*)scratch;
+    const size_t es = bf16 ? 2 : 4, px = (size_t)H * W, n = (size_t)B * px;
+    // Optional L2 blocking (JSPSR_SPN_ITER_CHUNK_MB > 0): run all T steps on one chunk of samples whose
+    // affinities/offsets fit the L2 before moving on.  OFF by default: measured on B200 (tools/iter_bench.py,
+    // 4096 tiles, T = 6) the dependent, sub-wave launches it creates are 1.6-2.8x SLOWER than T full-batch
+    // launches (12.4-21.3 ms vs 7.7 ms); real T-fusion needs a persistent cluster-per-sample kernel.
+    size_t budget = 0;
+    if (const char* e = getenv("JSPSR_SPN_ITER_CHUNK_MB")) budget = (size_t)atol(e) << 20;
+    size_t chunk = (size_t)B;
+    if (budget > 0 && T > 1) {
+        chunk = budget / (px * 27 * es);
+        if (chunk < 1) chunk = 1;
+        if (chunk > (size_t)B) chunk = (size_t)B;
+    }
+    for (size_t b0 = 0; b0 < (size_t)B; b0 += chunk) {
+        const int nb = (int)(((size_t)B - b0 < chunk) ? ((size_t)B - b0) : chunk);
+        const char* src = (const char*)feat_init + b0 * px * es;
+        const char* aff_c = (const char*)aff + b0 * px * 9 * es;
+        const char* off_c = (const char*)offset + b0 * px * 18 * es;
+        for (int t = 0; t < T; ++t) {
+            if (feat_fix) {  // nlspn.py:228-229
+                char* blend = (char*)scratch + b0 * px * es;
+                cudaError_t ce = launch_preserve_blend(src, (const char*)feat_fix + b0 * px * es,
+                                                       (const float*)mask_fix + b0 * px, blend, (size_t)nb * px, bf16,
+                                                       (cudaStream_t)stream);
+                if (ce != cudaSuccess) return cuda_fail(ce, "preserve_input blend launch");
+                src = blend;
+            }
+            char* dst = (char*)list_out + ((size_t)t * n + b0 * px) * es;
+            LaunchArgs la;
+            if (int e = fill_geom(&la, nb, H, W, H, 0, 0, H, 16)) return e;
+            la.init = src; la.weight = aff_c; la.offset = off_c; la.w9 = nullptr; la.b1 = nullptr; la.out = dst;
+            la.mode = NORM_NONE; la.scale = 0.f; la.bf16 = bf16; la.stream = (cudaStream_t)stream;
+            la.use_tma = make_init_tmap(&la.tmap, src, nb, H, W, bf16, la.tile_h);
+            cudaError_t ce = launch_spn_forward(la);
+            if (ce != cudaSuccess) return cuda_fail(ce, "spn_iterate launch");
+            src = dst;
         }
-        char* dst = (char*)list_out + (size_t)t * n * es;
-        LaunchArgs la;
-        if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 16)) return e;
-        la.init = src; la.weight = aff; la.offset = offset; la.w9 = nullptr; la.b1 = nullptr; la.out = dst;
-        la.mode = NORM_NONE; la.scale = 0.f; la.bf16 = bf16; la.stream = (cudaStream_t)stream;
-        la.use_tma = make_init_tmap(&la.tmap, src, B, H, W, bf16, la.tile_h);
-        cudaError_t ce = launch_spn_forward(la);
-        if (ce != cudaSuccess) return cuda_fail(ce, "spn_iterate launch");
-        src = dst;
     }
     return JSPSR_OK;
 }
