@@ -130,9 +130,9 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
                     const float c2 = cl * t.lw, c4 = ch * t.lw;
                     float* gt = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
                     atomicAdd(gt, cl - c2);
-                    atomicAdd(gt + 1, c2);
-                    atomicAdd(gt + SW, ch - c4);
-                    atomicAdd(gt + SW + 1, c4);
+                    if (c2 != 0.f) atomicAdd(gt + 1, c2);            // zero for integer columns (centre tap)
+                    if (ch != c4) atomicAdd(gt + SW, ch - c4);       // zero for integer rows
+                    if (c4 != 0.f) atomicAdd(gt + SW + 1, c4);
                 }
             }
         }
@@ -182,14 +182,27 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
         for (int k = 0; k < 9; ++k) store(pw + k * cs, gm[k]);
     }
 
-    // ---- grad_init: flush the shared accumulation tile ----
+    // ---- grad_init: flush the shared accumulation tile (one 16-byte vector RED per 4 columns) ----
     if (GRAD_INIT) {
         __syncthreads();
-        for (int i = threadIdx.x; i < SH * SW; i += THREADS) {
-            const float v = gtile[i];
-            if (v != 0.f) {
-                const int r = i / SW, q = i - r * SW;
-                scatter_corner_global<T>(gi_b, g, c.oy + r, c.ox + q, v);
+        const bool vec_ok = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad_init) & 15) == 0);
+        for (int i = threadIdx.x; i < SH * (SW / 4); i += THREADS) {
+            const int r = i / (SW / 4), q = (i - r * (SW / 4)) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(gtile + r * SW + q);
+            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            const int gy = c.oy + r, gx = c.ox + q;
+            const int br = gy - g.init_row0;
+            if ((unsigned)gy >= (unsigned)g.H_img || (unsigned)br >= (unsigned)g.init_rows) continue;
+            if (vec_ok && gx >= 0 && gx + 3 < g.W) {
+                float* dst = gi_b + (size_t)br * g.W + gx;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                             "f"(v.w)
+                             : "memory");
+            } else {
+                scatter_corner_global<T>(gi_b, g, gy, gx, v.x);
+                scatter_corner_global<T>(gi_b, g, gy, gx + 1, v.y);
+                scatter_corner_global<T>(gi_b, g, gy, gx + 2, v.z);
+                scatter_corner_global<T>(gi_b, g, gy, gx + 3, v.w);
             }
         }
     }
