@@ -48,6 +48,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
+    const size_t csb = cs * sizeof(T);  // channel stride in bytes
     const T* gout_b = gout + (size_t)c.b * cs;
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
@@ -67,12 +68,37 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
             const T* pw = wgt_b + p;
             const T* po = off_b + p;
             go = ld_stream(gout_b + p);
+            if (CS) {  // compile-time stride: immediate offsets off one address register
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a[k] = ld_stream(pw + k * cs);
+                for (int k = 0; k < 9; ++k) a[k] = ld_stream(pw + k * cs);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                oh[k] = ld_stream(po + (2 * k) * cs);
-                ow[k] = ld_stream(po + (2 * k + 1) * cs);
+                for (int k = 0; k < 9; ++k) {
+                    oh[k] = ld_stream(po + (2 * k) * cs);
+                    ow[k] = ld_stream(po + (2 * k + 1) * cs);
+                }
+            } else {   // runtime stride: one opaque 64-bit add per channel off a few bases (short chains,
+                       // so all 27 loads still issue back to back)
+                const T* pw3 = step_ptr(pw, 3 * csb);
+                const T* pw6 = step_ptr(pw, 6 * csb);
+                a[0] = ld_stream(pw);
+                a[1] = ld_stream(step_ptr(pw, csb));
+                a[2] = ld_stream(step_ptr(pw, 2 * csb));
+                a[3] = ld_stream(pw3);
+                a[4] = ld_stream(step_ptr(pw3, csb));
+                a[5] = ld_stream(step_ptr(pw3, 2 * csb));
+                a[6] = ld_stream(pw6);
+                a[7] = ld_stream(step_ptr(pw6, csb));
+                a[8] = ld_stream(step_ptr(pw6, 2 * csb));
+#pragma unroll
+                for (int k3 = 0; k3 < 3; ++k3) {  // 6 offset channels per base
+                    const T* pb = k3 == 0 ? po : step_ptr(po, (size_t)(6 * k3) * csb);
+                    oh[3 * k3] = ld_stream(pb);
+                    ow[3 * k3] = ld_stream(step_ptr(pb, csb));
+                    oh[3 * k3 + 1] = ld_stream(step_ptr(pb, 2 * csb));
+                    ow[3 * k3 + 1] = ld_stream(step_ptr(pb, 3 * csb));
+                    oh[3 * k3 + 2] = ld_stream(step_ptr(pb, 4 * csb));
+                    ow[3 * k3 + 2] = ld_stream(step_ptr(pb, 5 * csb));
+                }
             }
         }
     };
@@ -101,7 +127,8 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
         const float fy = (float)(g.row0 + c.y0 + ry), fx = (float)(c.x0 + cx);
         const float hk[3] = {fy - 1.f, fy, fy + 1.f};
         const float wk[3] = {fx - 1.f, fx, fx + 1.f};
-        T* po = goff_b + p;
+        T* po = goff_b + p;   // slow-pass stores index from here
+        T* pos = po;          // running pointer of the fast pass when the stride is a runtime value
         float gm[9];
         unsigned slow = 0u;
         acc_b += go;
@@ -122,8 +149,15 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
             const float gkm = ga * s_w[k];       // dL/d(sample_k)
             acc_w[k] = fmaf(ga, val, acc_w[k]);
             gm[k] = (go * s_w[k]) * val;
-            store(po + (2 * k) * cs, gkm * dh);
-            store(po + (2 * k + 1) * cs, gkm * dw);
+            if (CS) {
+                store(po + (2 * k) * cs, gkm * dh);
+                store(po + (2 * k + 1) * cs, gkm * dw);
+            } else {
+                store(pos, gkm * dh);
+                pos = step_ptr(pos, csb);
+                store(pos, gkm * dw);
+                pos = step_ptr(pos, csb);
+            }
             if (GRAD_INIT) {
                 if (t.ok) {
                     const float ch = gkm * t.lh, cl = gkm - ch;  // rows h0+1 / h0
@@ -179,7 +213,14 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
         }
         T* pw = gwgt_b + p;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) store(pw + k * cs, gm[k]);
+        for (int k = 0; k < 9; ++k) {
+            if (CS) {
+                store(pw + k * cs, gm[k]);
+            } else {
+                store(pw, gm[k]);
+                pw = step_ptr(pw, csb);
+            }
+        }
     }
 
     // ---- grad_init: flush the shared accumulation tile (one 16-byte vector RED per 4 columns) ----

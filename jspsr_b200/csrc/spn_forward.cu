@@ -14,7 +14,11 @@ namespace jspsr {
 // 128x128 tiles: 16384) the 27 channel loads of a pixel share one address register with
 // immediate offsets instead of a 64-bit add per channel.
 // TH: rows per CTA (see spn_common.cuh).  `mode` (normalisation) is a runtime, warp-uniform switch.
-template <typename T, bool TMA, int CS, int TH>
+// LINEAR: pixel-to-thread mapping (spn_kernels.cuh).  The row mapping is fastest when image rows are
+// 128-byte aligned; when they are not (W*sizeof(T) % 128 != 0) a warp's 128-byte request straddles
+// DRAM granules and only the linear mapping, where the four warps of a row issue together, lets L2
+// merge them (measured at W = 2004: 11.1 GB read from DRAM for 7.5 GB of data with the row mapping).
+template <typename T, bool TMA, int CS, int TH, bool LINEAR>
 __global__ void __launch_bounds__(THREADS, FWD_MIN_BLOCKS)
 spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, const T* __restrict__ offset,
                    const float* __restrict__ w9, const float* __restrict__ b1, T* __restrict__ out, const Geom g,
@@ -32,7 +36,8 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
     if (threadIdx.x == 9) s_w[9] = b1 ? b1[0] : 0.f;
 
-    const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;  // channel stride
+    const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
+    const size_t csb = cs * sizeof(T);  // channel stride in bytes  // channel stride
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
     const T* init_b = init + (size_t)c.b * g.init_rows * g.W;
@@ -42,18 +47,43 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     // pixel `it` of this thread: linear index it*256 + tid in the TH x 128 block (a warp = 32 consecutive x)
     float a[9], oh[9], ow[9];
     auto load_inputs = [&](int it, bool& active, size_t& p) {
-        const int y = c.y0 + pix_row<TH, false>(it), x = c.x0 + pix_col<TH, false>(it);
+        const int y = c.y0 + pix_row<TH, LINEAR>(it), x = c.x0 + pix_col<TH, LINEAR>(it);
         active = (y < g.H) && (x < g.W);
         p = (size_t)y * g.W + x;
         if (active) {
             const T* pw = wgt_b + p;
             const T* po = off_b + p;
+            if (CS) {  // compile-time stride: immediate offsets off one address register
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a[k] = ld_stream(pw + k * cs);
+                for (int k = 0; k < 9; ++k) a[k] = ld_stream(pw + k * cs);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                oh[k] = ld_stream(po + (2 * k) * cs);
-                ow[k] = ld_stream(po + (2 * k + 1) * cs);
+                for (int k = 0; k < 9; ++k) {
+                    oh[k] = ld_stream(po + (2 * k) * cs);
+                    ow[k] = ld_stream(po + (2 * k + 1) * cs);
+                }
+            } else {   // runtime stride: one opaque 64-bit add per channel off a few bases (short chains,
+                       // so all 27 loads still issue back to back)
+                const T* pw3 = step_ptr(pw, 3 * csb);
+                const T* pw6 = step_ptr(pw, 6 * csb);
+                a[0] = ld_stream(pw);
+                a[1] = ld_stream(step_ptr(pw, csb));
+                a[2] = ld_stream(step_ptr(pw, 2 * csb));
+                a[3] = ld_stream(pw3);
+                a[4] = ld_stream(step_ptr(pw3, csb));
+                a[5] = ld_stream(step_ptr(pw3, 2 * csb));
+                a[6] = ld_stream(pw6);
+                a[7] = ld_stream(step_ptr(pw6, csb));
+                a[8] = ld_stream(step_ptr(pw6, 2 * csb));
+#pragma unroll
+                for (int k3 = 0; k3 < 3; ++k3) {  // 6 offset channels per base
+                    const T* pb = k3 == 0 ? po : step_ptr(po, (size_t)(6 * k3) * csb);
+                    oh[3 * k3] = ld_stream(pb);
+                    ow[3 * k3] = ld_stream(step_ptr(pb, csb));
+                    oh[3 * k3 + 1] = ld_stream(step_ptr(pb, 2 * csb));
+                    ow[3 * k3 + 1] = ld_stream(step_ptr(pb, 3 * csb));
+                    oh[3 * k3 + 2] = ld_stream(step_ptr(pb, 4 * csb));
+                    ow[3 * k3 + 2] = ld_stream(step_ptr(pb, 5 * csb));
+                }
             }
         }
     };
@@ -68,7 +98,7 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     for (int it = 0; it < PPT; ++it) {
         if (it > 0) load_inputs(it, active, p);
         if (!active) continue;
-        const int ry = pix_row<TH, false>(it), cx = pix_col<TH, false>(it);
+        const int ry = pix_row<TH, LINEAR>(it), cx = pix_col<TH, LINEAR>(it);
         normalise9(a, mode);
 
         // torchvision: (out_y - pad + i*dil) formed as an integer, converted, + offset
@@ -104,21 +134,24 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     }
 }
 
-template <typename T, bool TMA, int CS, int TH>
+template <typename T, bool TMA, int CS, int TH, bool LINEAR>
 static void launch_fwd_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_forward_kernel<T, TMA, CS, TH><<<grid, THREADS, 0, la.stream>>>(
+    spn_forward_kernel<T, TMA, CS, TH, LINEAR><<<grid, THREADS, 0, la.stream>>>(
         (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (T*)la.out, la.g, la.mode, la.scale,
         la.status, la.tmap);
 }
 
-// (TMA, CS) variants: the compile-time stride only exists for 128x128-pixel planes, which always qualify for TMA
+// (TMA, CS, LINEAR) variants: the compile-time stride only exists for 128x128-pixel planes (always
+// TMA-able and row-aligned); rows that are not 128-byte aligned use the linear mapping
 template <typename T, int TH>
 static void launch_fwd_th(const LaunchArgs& la) {
     const size_t cs = (size_t)la.g.H * la.g.W;
-    if (la.use_tma && cs == 16384) launch_fwd_one<T, true, 16384, TH>(la);
-    else if (la.use_tma) launch_fwd_one<T, true, 0, TH>(la);
-    else launch_fwd_one<T, false, 0, TH>(la);
+    const bool aligned = ((size_t)la.g.W * sizeof(T)) % 128 == 0;
+    if (la.use_tma && cs == 16384 && aligned) launch_fwd_one<T, true, 16384, TH, false>(la);
+    else if (la.use_tma && aligned) launch_fwd_one<T, true, 0, TH, false>(la);
+    else if (la.use_tma) launch_fwd_one<T, true, 0, TH, true>(la);
+    else launch_fwd_one<T, false, 0, TH, true>(la);
 }
 
 template <typename T>
