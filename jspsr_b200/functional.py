@@ -130,14 +130,18 @@ def spn_backward(grad_out, init, weight, offset, w, norm_mode: int, scale: float
     return grad_init, grad_weight, grad_offset, grad_w, grad_b
 
 
-def spn_forward_strip(init_buf, weight, offset, w, b, norm_mode, scale, H_img, row0, init_row0, status=None):
-    """Row-strip forward: `init_buf` holds rows [init_row0, init_row0+init_buf.shape[2]) of the image."""
+def spn_forward_strip(init_buf, weight, offset, w, b, norm_mode, scale, H_img, row0, init_row0, status=None, out=None):
+    """Row-strip forward: `init_buf` holds rows [init_row0, init_row0+init_buf.shape[2]) of the image.
+    `out` (optional, contiguous [B,1,Hs,W], e.g. the interior of the next halo buffer) receives the result."""
     _require_cuda(init_buf, weight, offset)
     B, _, Hs, W = weight.shape[0], None, weight.shape[2], weight.shape[3]
     init_buf, weight, offset = init_buf.contiguous(), weight.contiguous(), offset.contiguous()
     w9 = _w9(w, weight)
     b1 = None if b is None else b.detach().to(device=weight.device, dtype=torch.float32).contiguous()
-    out = torch.empty(B, 1, Hs, W, dtype=weight.dtype, device=weight.device)
+    if out is None:
+        out = torch.empty(B, 1, Hs, W, dtype=weight.dtype, device=weight.device)
+    elif tuple(out.shape) != (B, 1, Hs, W) or not out.is_contiguous() or out.dtype != weight.dtype:
+        raise RuntimeError("out must be a contiguous [B,1,Hs,W] tensor of the input dtype")
     with torch.cuda.device(weight.device):
         rc = _lib.lib().jspsr_spn_forward_strip(_ptr(init_buf), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1),
                                                 _ptr(out), B, Hs, W, H_img, row0, init_row0, init_buf.shape[2],

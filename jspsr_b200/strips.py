@@ -62,6 +62,40 @@ def global_halo(offset_band: torch.Tensor, group=None, absmax_fn=None) -> int:
     return int(math.ceil(float(m.item()))) + 2
 
 
+class HaloBuffer:
+    """One band of a single raster (B = 1) stored inside a buffer that already has room for the halo rows:
+    neighbours' rows are received straight into it and the kernel writes the next iteration's band straight
+    into the interior of the other buffer - no concatenation, no copy of the band."""
+
+    def __init__(self, band_rows: int, W: int, halo: int, rank: int, world: int, dtype, device):
+        self.top = halo if rank > 0 else 0
+        self.bot = halo if rank < world - 1 else 0
+        self.halo, self.rank, self.world, self.rows = halo, rank, world, band_rows
+        self.buf = torch.empty(1, 1, self.top + band_rows + self.bot, W, dtype=dtype, device=device)
+
+    @property
+    def interior(self) -> torch.Tensor:
+        return self.buf[:, :, self.top:self.top + self.rows]
+
+    def exchange(self, group=None) -> None:
+        """Send this band's first/last `halo` rows to the neighbours, receive theirs into the halo rows."""
+        if self.world == 1 or self.halo == 0:
+            return
+        if self.rows < self.halo:
+            raise RuntimeError(f"halo {self.halo} exceeds the band height {self.rows}: use fewer ranks")
+        h, t = self.halo, self.top
+        ops = []
+        if self.rank > 0:
+            ops += [dist.P2POp(dist.isend, self.buf[:, :, t:t + h], self.rank - 1, group),
+                    dist.P2POp(dist.irecv, self.buf[:, :, :t], self.rank - 1, group)]
+        if self.rank < self.world - 1:
+            e = t + self.rows
+            ops += [dist.P2POp(dist.isend, self.buf[:, :, e - h:e], self.rank + 1, group),
+                    dist.P2POp(dist.irecv, self.buf[:, :, e:e + h], self.rank + 1, group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 class StripPropagator:
     """Propagation of one rank's band.  `H_img` is the height of the whole raster."""
 
@@ -77,28 +111,56 @@ class StripPropagator:
         init_row0 = self.row0 - (halo if self.rank > 0 else 0)
         return buf, init_row0
 
+    def halo_buffer(self, band: torch.Tensor, halo: int) -> HaloBuffer:
+        """Place a [1,1,rows,W] band into a buffer with halo room (one copy, outside any hot loop)."""
+        hb = HaloBuffer(band.shape[2], band.shape[3], halo, self.rank, self.world, band.dtype, band.device)
+        hb.interior.copy_(band)
+        return hb
+
     def forward(self, init_band, weight_band, offset_band, w, b, norm_mode, scale=1.0, halo: Optional[int] = None):
-        """One application (JSPSR, T = 1): one halo exchange of the DEM, then the strip kernel."""
+        """One application (JSPSR, T = 1): one halo exchange of the DEM, then the strip kernel.
+        `init_band` is a tensor (exchange + concatenate) or a HaloBuffer already holding the band (zero-copy)."""
         from . import functional as F
+        status = torch.zeros(1, dtype=torch.int32, device=weight_band.device)
+        if isinstance(init_band, HaloBuffer):
+            init_band.exchange(self.group)
+            out = F.spn_forward_strip(init_band.buf, weight_band, offset_band, w, b, norm_mode, scale, self.H_img,
+                                      self.row0, self.row0 - init_band.top, status)
+            return out, status
         if halo is None:
             halo = global_halo(offset_band, self.group)
         buf, init_row0 = self._buffer(init_band, halo)
-        status = torch.zeros(1, dtype=torch.int32, device=init_band.device)
         out = F.spn_forward_strip(buf, weight_band, offset_band, w, b, norm_mode, scale, self.H_img, self.row0,
                                   init_row0, status)
         return out, status
 
-    def iterate(self, feat_band, aff_band, offset_band, T: int, halo: Optional[int] = None):
-        """T fixed-affinity applications (NLSPN loop): halo exchange of the feature every iteration."""
+    def iterate(self, feat_band, aff_band, offset_band, T: int, halo: Optional[int] = None, keep_all: bool = True):
+        """T fixed-affinity applications (NLSPN loop): halo exchange of the feature every iteration.
+        Single rasters (B = 1) ping-pong between two halo buffers (zero-copy); batches fall back to
+        exchange + concatenate.  Returns (list of bands [all T, or just the last], status)."""
         from . import functional as F
         if halo is None:
             halo = global_halo(offset_band, self.group)
         status = torch.zeros(1, dtype=torch.int32, device=feat_band.device)
         feats = []
+        if feat_band.shape[0] == 1:
+            rows, W = feat_band.shape[2], feat_band.shape[3]
+            bufs = [HaloBuffer(rows, W, halo, self.rank, self.world, feat_band.dtype, feat_band.device) for _ in range(2)]
+            bufs[0].interior.copy_(feat_band)
+            init_row0 = self.row0 - bufs[0].top
+            for t in range(T):
+                src, dst = bufs[t & 1], bufs[(t + 1) & 1]
+                src.exchange(self.group)
+                F.spn_forward_strip(src.buf, aff_band, offset_band, None, None, F.NORM_NONE, 0.0, self.H_img,
+                                    self.row0, init_row0, status, out=dst.interior)
+                if keep_all or t == T - 1:
+                    feats.append(dst.interior.clone() if (keep_all and t < T - 1) else dst.interior)
+            return feats, status
         cur = feat_band
-        for _ in range(T):
+        for t in range(T):
             buf, init_row0 = self._buffer(cur, halo)
             cur = F.spn_forward_strip(buf, aff_band, offset_band, None, None, F.NORM_NONE, 0.0, self.H_img,
                                       self.row0, init_row0, status)
-            feats.append(cur)
+            if keep_all or t == T - 1:
+                feats.append(cur)
         return feats, status

@@ -1,0 +1,76 @@
+"""CPU checks of the synthetic DFC30-shaped generator and, when the reference tree is present (build container
+only), of the interface-level drop-in: the replacement module can be installed into the reference's own
+models.JSPSR.Model and keeps its state_dict / optimizer-group contract.  No kernel runs here."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from jspsr_b200 import synth
+
+REF = "/root/reference"
+
+
+def test_dfc30_batch_shapes_and_ranges():
+    b = synth.dfc30_batch(4, 128, resolution=8, with_mask=True, seed=3)
+    assert tuple(b["lr_dem"].shape) == (4, 1, 128, 128) and tuple(b["hr_dem"].shape) == (4, 1, 128, 128)
+    assert tuple(b["image"].shape) == (4, 3, 128, 128) and tuple(b["mask"].shape) == (4, 15, 128, 128)
+    for k in ("lr_dem", "hr_dem", "image", "mask"):
+        assert b[k].dtype == torch.float32 and float(b[k].min()) >= 0.0 and float(b[k].max()) <= 1.0
+    for i in range(15):  # channel i takes the values {0, (i+1)/16}  (data_utils.py:262-265)
+        vals = torch.unique(b["mask"][:, i])
+        assert set(np.round(vals.numpy(), 6)) <= {0.0, round((i + 1) / 16, 6)}
+    assert len(b["meta"]) == 4 and {"id", "subset", "base", "shape", "bbox", "augmentation"} <= set(b["meta"][0])
+    # the low-resolution input is a smoothed copy of the target, not noise
+    err = (synth.descale_elevation(b["lr_dem"]) - synth.descale_elevation(b["hr_dem"])).abs().mean()
+    assert 0.05 < float(err) < 20.0
+    again = synth.dfc30_batch(4, 128, resolution=8, with_mask=True, seed=3)
+    assert torch.equal(again["hr_dem"], b["hr_dem"])
+    assert "mask" not in synth.dfc30_batch(2, 64, resolution=3, seed=1)
+
+
+def test_scale_descale_round_trip_matches_oracle_arithmetic():
+    from oracle import spn_oracle as O
+    x = torch.rand(2, 1, 16, 16) * 0.9 + 0.05
+    m = synth.descale_elevation(x, 8).numpy()
+    np.testing.assert_allclose(m, O.descale(x.numpy(), synth.ELEV_MIN, synth.ELEV_MAX[8], elev_log=True), rtol=1e-4)
+    back = synth.scale_elevation(torch.from_numpy(m), 8)
+    np.testing.assert_allclose(back.numpy(), x.numpy(), atol=1e-5)
+
+
+def test_propagation_inputs_statistics():
+    init, weight, offset, gout = synth.propagation_inputs(8, 64, 64, device="cpu")
+    assert tuple(offset.shape) == (8, 18, 64, 64) and torch.all(offset[:, 8:10] == 0)
+    assert 0.35 < float(weight.mean()) < 0.65 and float(offset.abs().max()) <= 8.0
+    assert 1.3 < float(offset[:, :8].std()) < 1.7
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree only exists in the build container")
+def test_installs_into_the_reference_model():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import contextlib
+    import io
+    from models.JSPSR import Model
+    import jspsr_b200 as jb
+    in_channels = {"lr_dem": 1, "COP30": 1, "image": 3}   # utils/config.py:50-52
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Model(in_channels=in_channels, num_feature=32, layers=(2, 2, 2, 2), spn=True)
+    ref_pp = model.postprocessor
+    ref_keys = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.postprocessor = jb.PostProcessor(kernel_size=3, residual=ref_pp.residual, scale=ref_pp.scale)
+    new_keys = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert new_keys == ref_keys, "state_dict keys/shapes changed: released checkpoints would not load"
+    assert (model.postprocessor.stride, model.postprocessor.padding, model.postprocessor.dilation) == \
+           (ref_pp.stride, ref_pp.padding, ref_pp.dilation)
+    # a checkpoint written by the reference module loads into the replacement
+    sd = {"w": torch.full((1, 1, 3, 3), 0.7), "b": torch.full((1,), -0.2)}
+    ref_pp.load_state_dict(sd)
+    model.postprocessor.load_state_dict(ref_pp.state_dict())
+    assert torch.equal(model.postprocessor.w, ref_pp.w) and torch.equal(model.postprocessor.b, ref_pp.b)
+    # the diff_lr optimizer groups pick the layer up by name (utils/common_config.py:250-253)
+    names = [n for n, _ in model.named_parameters() if "postprocessor" in n]
+    assert names == ["postprocessor.w", "postprocessor.b"]

@@ -60,9 +60,10 @@ def main():
     band = [t[:, :, r0:r1].contiguous() for t in full]
     sp = StripPropagator(Hs)
     out, status = sp.forward(band[0], band[1], band[2], w, b, 1, 1.0)
+    out_hb, status_hb = sp.forward(sp.halo_buffer(band[0], 8), band[1], band[2], w, b, 1, 1.0)
     feats, status2 = sp.iterate(band[0], band[1] * 0.1, band[2], 3)
     ok = torch.equal(out, ref1[:, :, r0:r1]) and all(torch.equal(f, reff[t][:, :, r0:r1]) for t, f in enumerate(feats))
-    ok = ok and int(status.item()) == 0 and int(status2.item()) == 0
+    ok = ok and torch.equal(out_hb, out) and int(status.item()) == 0 and int(status2.item()) == 0 and int(status_hb.item()) == 0
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -75,11 +76,12 @@ def main():
     init, aff, off = make_rows(r0, r1, W, 11)
     sp = StripPropagator(H)
     halo = 8  # offsets are clipped to +-6: ceil(6) + 2
+    hb = sp.halo_buffer(init, halo)   # the band lives in a buffer with halo room: no copies in the loop
 
     def step():
         if T == 1:
-            return sp.forward(init, aff, off, w, b, 1, 1.0, halo=halo)[0]
-        return sp.iterate(init, aff, off, T, halo=halo)[0][-1]
+            return sp.forward(hb, aff, off, w, b, 1, 1.0)[0]
+        return sp.iterate(init, aff, off, T, halo=halo, keep_all=False)[0][-1]
 
     for _ in range(3):
         step()
