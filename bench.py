@@ -362,6 +362,11 @@ def run_ours(args, rank, world, local_rank):
     extras = {}
     if not args.no_extras and rank == 0:
         extras = config_batch_latency(torch, jspsr_b200, F, device, dtype)
+        if world == 1:
+            del init, gout
+            weight.grad = offset.grad = None
+            torch.cuda.empty_cache()
+            extras["variants"] = side_numbers(torch, F, device, min(B, 2048))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -375,6 +380,47 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def side_numbers(torch, F, device, B):
+    """Kernel-level numbers for the other variants of the path, same tile batch: bf16 I/O, the fixed-affinity
+    T = 6 loop (NLSPN), and the backward that also returns grad_init.  Each with its algorithmic bytes."""
+    peak, _ = peak_hbm()
+    out = {}
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    npix = B * TILE * TILE
+    init, weight, offset, gout, w, b = make_inputs(torch, B, device, torch.bfloat16, 4321)
+    f = timed(lambda: F.spn_forward(init, weight, offset, w, b, 1, 1.0))
+    g = timed(lambda: F.spn_backward(gout, init, weight, offset, w, 1, 1.0, need_grad_init=False))
+    out["bf16_io"] = {"fwd_ms": f, "bwd_ms": g, "gpix_iter_per_s_fwd_bwd": npix / ((f + g) * 1e-3) / 1e9,
+                      "fwd_frac_of_hbm_peak": FWD_BYTES["bf16"] * npix / (f * 1e-3) / 1e9 / peak,
+                      "bwd_frac_of_hbm_peak": BWD_BYTES["bf16"] * npix / (g * 1e-3) / 1e9 / peak,
+                      "note": "bf16 I/O, fp32 arithmetic; issue-bound (see profiles/r01_summary.md), not HBM-bound"}
+    del init, weight, offset, gout
+    init, weight, offset, gout, w, b = make_inputs(torch, B, device, torch.float32, 4322)
+    g = timed(lambda: F.spn_backward(gout, init, weight, offset, w, 1, 1.0, need_grad_init=True))
+    out["backward_with_grad_init"] = {"ms": g, "frac_of_hbm_peak": 228 * npix / (g * 1e-3) / 1e9 / peak,
+                                      "note": "scatter through shared-memory atomics (CAS loops); used by NLSPN only"}
+    T = 6
+    aff = weight * 0.1
+    it = timed(lambda: F.spn_iterate(init, aff, offset, T), n=3)
+    out["nlspn_loop_T6"] = {"ms": it, "gpix_iter_per_s": npix * T / (it * 1e-3) / 1e9,
+                            "frac_of_hbm_peak_compulsory": (4 + 108 + 4 * T) * npix / (it * 1e-3) / 1e9 / peak,
+                            "frac_of_hbm_peak_as_run": 116 * T * npix / (it * 1e-3) / 1e9 / peak,
+                            "note": "T launches of the forward kernel, all T outputs kept"}
+    return out
 
 
 def config_batch_latency(torch, jspsr_b200, F, device, dtype):
