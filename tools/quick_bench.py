@@ -59,6 +59,19 @@ if __name__ == "__main__":
     run(64, 334, 334, f32, tag="334 manual")
     for B in (70, 50, 2):
         run(B, 128, 128, f32, tag="config batch")
+    # NLSPN affinity front-end (one launch each way)
+    B, H, W = 2048, 128, 128
+    g = torch.Generator(device="cuda").manual_seed(2)
+    conv_out = torch.randn(B, 24, H, W, device="cuda", generator=g)
+    conv_out[:, 16:] *= 60
+    conf = torch.rand(B, 1, H, W, device="cuda", generator=g)
+    gamma = torch.full((1,), 4.0, device="cuda")
+    go_ = torch.randn(B, 18, H, W, device="cuda", generator=g); ga_ = torch.randn(B, 9, H, W, device="cuda", generator=g)
+    fm, _ = timeit(lambda: F.nlspn_affinity_forward(conv_out, conf, gamma, "TGASS"))
+    bm, _ = timeit(lambda: F.nlspn_affinity_backward(go_, ga_, conv_out, conf, gamma, "TGASS"))
+    npx = B * H * W
+    print(f"nlspn affinity B={B}: fwd {fm*1e3:.1f} us {npx*4*(24+1+27)/fm/1e6:.0f} GB/s ({npx*4*(24+1+27)/fm/1e6/PEAK:.3f}) | "
+          f"bwd {bm*1e3:.1f} us {npx*4*(27+24+1+24+1)/bm/1e6:.0f} GB/s ({npx*4*(27+24+1+24+1)/bm/1e6/PEAK:.3f})", flush=True)
     # launch-latency view: both kernels in one CUDA graph (what bench.py reports as config_batch)
     for B in (70, 50, 2):
         g = torch.Generator(device="cuda").manual_seed(1)
