@@ -15,13 +15,11 @@ cudaError_t launch_offset_absmax(const void* offset, size_t n_pairs_block, size_
                                  cudaStream_t stream);
 cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const float* mask_fix, void* dst, size_t n,
                                   bool bf16, cudaStream_t stream);
-cudaError_t launch_nlspn_affinity_forward(const void* conv_out, const void* confidence, const float* gamma,
-                                          void* offset_out, void* aff_out, int B, int H, int W, int affinity, int legacy,
-                                          bool bf16, cudaStream_t stream);
-cudaError_t launch_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff, const void* conv_out,
-                                           const void* confidence, const float* gamma, void* grad_conv_out,
-                                           float* grad_confidence, float* grad_scale, void* workspace, int B, int H,
-                                           int W, int affinity, bool bf16, cudaStream_t stream);
+cudaError_t launch_nlspn_affinity(const void* conv_out, const void* confidence, const float* gamma, void* offset_out,
+                                  void* aff_out, const void* grad_offset, const void* grad_aff, void* grad_conv_out,
+                                  float* grad_confidence, float* grad_scale, void* workspace, const Geom& g, int tile_h,
+                                  bool use_tma, const CUtensorMap& tmap, int affinity, int legacy, bool bf16,
+                                  bool forward, cudaStream_t stream);
 }  // namespace jspsr
 
 static thread_local char g_err[512] = "";
@@ -262,8 +260,17 @@ int jspsr_nlspn_affinity_forward(const void* conv_out, const void* confidence, c
     if (!conv_out || !offset_out || !aff_out || !aff_scale_const) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
     if (affinity < 0 || affinity > 3) return fail(JSPSR_ERR_BAD_ARG, "affinity %d is not AS/ASS/TC/TGASS", affinity);
     if (legacy && !confidence) return fail(JSPSR_ERR_BAD_ARG, "legacy only has an effect with confidence propagation");
-    cudaError_t ce = launch_nlspn_affinity_forward(conv_out, confidence, aff_scale_const, offset_out, aff_out, B, H, W,
-                                                   affinity, legacy, dtype == JSPSR_BF16, (cudaStream_t)stream);
+    LaunchArgs la;  // geometry + TMA descriptor of the confidence map (the staged tensor of this kernel)
+    if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 8)) return e;
+    if (la.tile_h == 4) {  // the affinity kernels are instantiated for 8 and 2 rows per CTA
+        la.tile_h = 2;
+        la.g.tiles_y = (H + 1) / 2;
+    }
+    const bool bf16 = dtype == JSPSR_BF16;
+    la.use_tma = confidence && make_init_tmap(&la.tmap, confidence, B, H, W, bf16, la.tile_h);
+    cudaError_t ce = launch_nlspn_affinity(conv_out, confidence, aff_scale_const, offset_out, aff_out, nullptr, nullptr,
+                                           nullptr, nullptr, nullptr, nullptr, la.g, la.tile_h, la.use_tma, la.tmap,
+                                           affinity, legacy, bf16, true, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "nlspn_affinity_forward launch");
     return JSPSR_OK;
 }
@@ -282,9 +289,17 @@ int jspsr_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff,
         cudaError_t ce = cudaMemsetAsync(grad_confidence, 0, (size_t)B * H * W * sizeof(float), (cudaStream_t)stream);
         if (ce != cudaSuccess) return cuda_fail(ce, "grad_confidence memset");
     }
-    cudaError_t ce = launch_nlspn_affinity_backward(grad_offset, grad_aff, conv_out, confidence, aff_scale_const,
-                                                    grad_conv_out, grad_confidence, grad_scale, workspace, B, H, W,
-                                                    affinity, dtype == JSPSR_BF16, (cudaStream_t)stream);
+    LaunchArgs la;
+    if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 8)) return e;
+    if (la.tile_h == 4) {
+        la.tile_h = 2;
+        la.g.tiles_y = (H + 1) / 2;
+    }
+    const bool bf16 = dtype == JSPSR_BF16;
+    la.use_tma = confidence && make_init_tmap(&la.tmap, confidence, B, H, W, bf16, la.tile_h);
+    cudaError_t ce = launch_nlspn_affinity(conv_out, confidence, aff_scale_const, nullptr, nullptr, grad_offset, grad_aff,
+                                           grad_conv_out, grad_confidence, grad_scale, workspace, la.g, la.tile_h,
+                                           la.use_tma, la.tmap, affinity, 0, bf16, false, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "nlspn_affinity_backward launch");
     return JSPSR_OK;
 }

@@ -3,197 +3,312 @@
 // offsets, tanh/gamma scaling, eight separate 1x1 deform_conv2d confidence gathers,
 // the multiply, abs-sum normalisation with its floor at 1, and the centre weight
 // (about 30 launches in the reference).  Backward is its autograd.
+//
+// Same machinery as the propagation kernels: one CTA per TH x 128 pixel block, the
+// confidence map staged in shared memory by TMA (zero fill = torchvision's zero-outside rule),
+// branch-free taps with a deferred bounds-checked slow pass, 24 streamed channels in and
+// 27 out per pixel; the backward scatters grad_confidence into a shared accumulation tile
+// that is flushed with vector REDs.
 #include "spn_kernels.cuh"
 
 namespace jspsr {
 
 enum { AFF_AS = 0, AFF_ASS = 1, AFF_TC = 2, AFF_TGASS = 3 };
 
-struct Bil {
-    float v1, v2, v3, v4, lh, lw;
-    int h0, w0;
-    bool inside;
-};
+constexpr int AFF_MIN_BLOCKS = 3;
 
-// torchvision bilinear_interpolate on a [H,W] plane (1x1 deformable gather, pad 0)
-template <typename T>
-__device__ __forceinline__ Bil bilinear_at(const T* __restrict__ img, int H, int W, float h, float w) {
-    Bil r;
-    r.v1 = r.v2 = r.v3 = r.v4 = 0.f;
-    r.lh = r.lw = 0.f;
-    r.h0 = r.w0 = 0;
-    r.inside = !((h <= -1.f) || (h >= (float)H) || (w <= -1.f) || (w >= (float)W)) && (h == h) && (w == w);
-    if (h != h || w != w) { r.lh = h - h; r.lw = w - w; return r; }  // NaN stays NaN
-    if (!r.inside) return r;
-    r.h0 = __float2int_rd(h);
-    r.w0 = __float2int_rd(w);
-    r.lh = h - floorf(h);
-    r.lw = w - floorf(w);
-    const int h1 = r.h0 + 1, w1 = r.w0 + 1;
-    if (r.h0 >= 0 && r.w0 >= 0) r.v1 = to_f32(img[(size_t)r.h0 * W + r.w0]);
-    if (r.h0 >= 0 && w1 <= W - 1) r.v2 = to_f32(img[(size_t)r.h0 * W + w1]);
-    if (h1 <= H - 1 && r.w0 >= 0) r.v3 = to_f32(img[(size_t)h1 * W + r.w0]);
-    if (h1 <= H - 1 && w1 <= W - 1) r.v4 = to_f32(img[(size_t)h1 * W + w1]);
-    return r;
-}
-__device__ __forceinline__ float bil_value(const Bil& r) {
-    const float hh = 1.f - r.lh, hw = 1.f - r.lw;
-    return hh * hw * r.v1 + hh * r.lw * r.v2 + r.lh * hw * r.v3 + r.lh * r.lw * r.v4;
-}
+// tanh(x/100) / gamma' with the reference's operation order; the two divisions become multiplications
+// by correctly rounded reciprocals (<= 1 ulp each)
+__device__ __forceinline__ float aff_tanh(float af) { return tanhf(af * 0.01f); }
 
-template <int AFF>
-__device__ __forceinline__ float scale_aff(float af, float gamma, float& th) {
-    if (AFF == AFF_TC) {
-        th = tanhf(__fdiv_rn(af, 100.f));
-        return __fdiv_rn(th, gamma);
-    } else if (AFF == AFF_TGASS) {
-        th = tanhf(__fdiv_rn(af, 100.f));
-        return __fdiv_rn(th, gamma + 1e-8f);
-    }
-    th = 0.f;
-    return af;
-}
+// position of the confidence sample of neighbour n (1x1 deformable gather, pad 0): pixel + offset
+// (nlspn.py:130-139); tap index idx = n with the centre skipped
+__device__ __forceinline__ int tap_index(int n) { return n < 4 ? n : n + 1; }
 
-template <typename T, int AFF, bool CONF>
-__global__ void __launch_bounds__(256)
+template <typename T, bool CONF, bool TMA, int TH>
+__global__ void __launch_bounds__(THREADS, AFF_MIN_BLOCKS)
 nlspn_affinity_fwd_kernel(const T* __restrict__ conv_out, const T* __restrict__ conf, const float* __restrict__ gamma_p,
-                          T* __restrict__ offset_out, T* __restrict__ aff_out, int B, int H, int W, int legacy) {
-    const size_t cs = (size_t)H * W, total = (size_t)B * cs;
+                          T* __restrict__ offset_out, T* __restrict__ aff_out, const Geom g, const int affinity,
+                          const int legacy, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int SH = staged_rows(TH);
+    constexpr int PPT = pixels_per_thread(TH);
+    __shared__ __align__(128) T tile[CONF ? SH * SW : 8];
+    __shared__ __align__(8) uint64_t bar;
+
+    const TileCtx c = make_tile_ctx<TH>(g);
+    if (CONF) stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, conf, g, c.b, c.ox, c.oy - g.init_row0);
+
+    const size_t cs = (size_t)g.H * g.W;
+    const T* cv_b = conv_out + (size_t)c.b * 24 * cs;
+    T* oo_b = offset_out + (size_t)c.b * 18 * cs;
+    T* ao_b = aff_out + (size_t)c.b * 9 * cs;
+    const T* conf_b = CONF ? conf + (size_t)c.b * cs : nullptr;
+    const T* tile_lo = tile + (CONF ? c.r_lo * SW : 0);
+    const bool tanh_type = affinity == AFF_TC || affinity == AFF_TGASS;
     const float gamma = gamma_p[0];
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = p / cs, yx = p - b * cs;
-        const int y = (int)(yx / W), x = (int)(yx - (size_t)y * W);
-        const T* cv = conv_out + b * 24 * cs + yx;
-        T* oo = offset_out + b * 18 * cs + yx;
-        T* ao = aff_out + b * 9 * cs + yx;
-        const T* cf = CONF ? conf + b * cs : nullptr;
-        float u[8], sabs = 0.f;
+    const float rgam = __fdiv_rn(1.f, affinity == AFF_TGASS ? gamma + 1e-8f : gamma);
+
+    float oh[8], ow[8], u[8];
+    auto load_inputs = [&](int it, bool& active, size_t& p) {
+        const int y = c.y0 + pix_row<TH, true>(it), x = c.x0 + pix_col<TH, true>(it);
+        active = (y < g.H) && (x < g.W);
+        p = (size_t)y * g.W + x;
+        if (active) {
+            const T* cv = cv_b + p;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const int idx = n < 4 ? n : n + 1;  // tap index with the centre skipped
-            // cat(o1,o2).view(B,8,2,H,W): pair n = channels (2n, 2n+1)  (nlspn.py:85)
-            float oh = ld_stream(cv + (2 * n) * cs), ow = ld_stream(cv + (2 * n + 1) * cs);
-            if (legacy) {  // nlspn.py:122-128 shifts the shared storage in place
-                oh += (float)(idx / 3 - 1);
-                ow += (float)(idx % 3 - 1);
+            for (int n = 0; n < 8; ++n) {
+                // cat(o1,o2).view(B,8,2,H,W): pair n = channels (2n, 2n+1)  (nlspn.py:85)
+                oh[n] = ld_stream(cv + (2 * n) * cs);
+                ow[n] = ld_stream(cv + (2 * n + 1) * cs);
+                u[n] = ld_stream(cv + (16 + n) * cs);
             }
-            st_stream(oo + (2 * idx) * cs, oh);
-            st_stream(oo + (2 * idx + 1) * cs, ow);
-            float th;
-            float t = scale_aff<AFF>(ld_stream(cv + (16 + n) * cs), gamma, th);
-            if (CONF) {
-                const Bil r = bilinear_at<T>(cf, H, W, (float)y + oh, (float)x + ow);
-                t *= bil_value(r);
-            }
-            u[n] = t;
-            sabs += fabsf(t);
         }
-        st_stream(oo + 8 * cs, 0.f);
-        st_stream(oo + 9 * cs, 0.f);
-        sabs += 1e-4f;
-        if (AFF == AFF_ASS || AFF == AFF_TGASS) sabs = sabs < 1.f ? 1.f : sabs;
-        float sum = 0.f;
+    };
+
+    bool active;
+    size_t p;
+    load_inputs(0, active, p);
+    if (CONF) stage_tile_wait<TMA>(&bar);
+
+#pragma unroll 1
+    for (int it = 0; it < PPT; ++it) {
+        if (it > 0) load_inputs(it, active, p);
+        if (!active) continue;
+        const float fy = (float)(c.y0 + pix_row<TH, true>(it)), fx = (float)(c.x0 + pix_col<TH, true>(it));
+        T* oo = oo_b + p;
+        unsigned slow = 0u;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            if (AFF != AFF_TC) u[n] = __fdiv_rn(u[n], sabs);
-            sum += u[n];
-            st_stream(ao + (n < 4 ? n : n + 1) * cs, u[n]);
+            const int idx = tap_index(n);
+            if (legacy) {  // nlspn.py:122-128 shifts the shared storage in place
+                oh[n] += (float)(idx / 3 - 1);
+                ow[n] += (float)(idx % 3 - 1);
+            }
+            st_stream(oo + (2 * idx) * cs, oh[n]);
+            st_stream(oo + (2 * idx + 1) * cs, ow[n]);
+            if (tanh_type) u[n] = aff_tanh(u[n]) * rgam;
+            if (CONF) {
+                const FastTap t = fast_tap<T>(tile_lo, c, fy + oh[n], fx + ow[n]);
+                const float val = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+                u[n] = t.ok ? u[n] * val : u[n];
+                slow |= t.ok ? 0u : (1u << n);
+            }
+        }
+        st_stream(oo + 8 * cs, 0.f);  // zero reference offset at idx_ref = 4 (nlspn.py:86-90)
+        st_stream(oo + 9 * cs, 0.f);
+        if (CONF && slow) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (slow & (1u << n)) {
+                    const SlowTap t = slow_tap<T>(conf_b, g, fy + oh[n], fx + ow[n], nullptr);
+                    u[n] *= bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+                }
+            }
+        }
+        // abs-sum normalisation with its floor, centre weight (nlspn.py:159-173)
+        float sabs = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) sabs += fabsf(u[n]);
+        sabs += 1e-4f;
+        if (affinity == AFF_ASS || affinity == AFF_TGASS) sabs = sabs < 1.f ? 1.f : sabs;
+        const float inv = affinity == AFF_TC ? 1.f : __fdiv_rn(1.f, sabs);
+        float sum = 0.f;
+        T* ao = ao_b + p;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float v = u[n] * inv;
+            sum += v;
+            st_stream(ao + tap_index(n) * cs, v);
         }
         st_stream(ao + 4 * cs, 1.f - sum);
     }
 }
 
-template <typename T, int AFF, bool CONF>
-__global__ void __launch_bounds__(256)
+template <typename T, bool CONF, bool TMA, int TH>
+__global__ void __launch_bounds__(THREADS, AFF_MIN_BLOCKS)
 nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict__ grad_aff,
                           const T* __restrict__ conv_out, const T* __restrict__ conf, const float* __restrict__ gamma_p,
                           T* __restrict__ grad_conv, float* __restrict__ grad_conf, float* __restrict__ grad_scale,
-                          ReduceWs* __restrict__ ws, int B, int H, int W) {
-    __shared__ float s_red[8];
+                          ReduceWs* __restrict__ ws, const Geom g, const int affinity,
+                          const __grid_constant__ CUtensorMap tmap) {
+    constexpr int SH = staged_rows(TH);
+    constexpr int PPT = pixels_per_thread(TH);
+    __shared__ __align__(128) T tile[CONF ? SH * SW : 8];
+    __shared__ __align__(16) float gtile[CONF ? SH * SW : 4];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_red[WARPS];
     __shared__ bool s_last;
-    const size_t cs = (size_t)H * W, total = (size_t)B * cs;
-    const float gamma = gamma_p[0];
-    const float geff = AFF == AFF_TGASS ? gamma + 1e-8f : gamma;
-    float acc_gamma = 0.f;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = p / cs, yx = p - b * cs;
-        const int y = (int)(yx / W), x = (int)(yx - (size_t)y * W);
-        const T* cv = conv_out + b * 24 * cs + yx;
-        const T* go = grad_offset + b * 18 * cs + yx;
-        const T* ga = grad_aff + b * 9 * cs + yx;
-        T* gc = grad_conv + b * 24 * cs + yx;
-        const T* cf = CONF ? conf + b * cs : nullptr;
-        float* gcf = (CONF && grad_conf) ? grad_conf + b * cs : nullptr;
 
-        float t[8], th[8], cval[8], u[8], sabs = 0.f;
-        Bil bil[CONF ? 8 : 1];
+    const TileCtx c = make_tile_ctx<TH>(g);
+    if (CONF) {
+        stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, conf, g, c.b, c.ox, c.oy - g.init_row0);
+        for (int i = threadIdx.x; i < SH * SW; i += THREADS) gtile[i] = 0.f;
+    }
+    const bool scatter = CONF && grad_conf != nullptr;
+
+    const size_t cs = (size_t)g.H * g.W;
+    const T* cv_b = conv_out + (size_t)c.b * 24 * cs;
+    const T* go_b = grad_offset + (size_t)c.b * 18 * cs;
+    const T* ga_b = grad_aff + (size_t)c.b * 9 * cs;
+    T* gc_b = grad_conv + (size_t)c.b * 24 * cs;
+    const T* conf_b = CONF ? conf + (size_t)c.b * cs : nullptr;
+    float* gcf_b = scatter ? grad_conf + (size_t)c.b * cs : nullptr;
+    const T* tile_lo = tile + (CONF ? c.r_lo * SW : 0);
+    float* gtile_lo = gtile + (CONF ? c.r_lo * SW : 0);
+    const bool tanh_type = affinity == AFF_TC || affinity == AFF_TGASS;
+    const bool normalised = affinity != AFF_TC;
+    const float gamma = gamma_p[0];
+    const float rgam = __fdiv_rn(1.f, affinity == AFF_TGASS ? gamma + 1e-8f : gamma);
+    float acc_gamma = 0.f;
+
+    float oh[8], ow[8], af[8], gn[8];
+    auto load_inputs = [&](int it, bool& active, size_t& p) {
+        const int y = c.y0 + pix_row<TH, true>(it), x = c.x0 + pix_col<TH, true>(it);
+        active = (y < g.H) && (x < g.W);
+        p = (size_t)y * g.W + x;
+        if (active) {
+            const T* cv = cv_b + p;
+            const T* ga = ga_b + p;
+            const float gcen = ld_stream(ga + 4 * cs);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                oh[n] = ld_stream(cv + (2 * n) * cs);
+                ow[n] = ld_stream(cv + (2 * n + 1) * cs);
+                af[n] = ld_stream(cv + (16 + n) * cs);
+                gn[n] = ld_stream(ga + tap_index(n) * cs) - gcen;  // centre = 1 - sum
+            }
+        }
+    };
+
+    bool active;
+    size_t p;
+    load_inputs(0, active, p);
+    if (CONF) stage_tile_wait<TMA>(&bar);
+    else __syncthreads();
+
+#pragma unroll 1
+    for (int it = 0; it < PPT; ++it) {
+        if (it > 0) load_inputs(it, active, p);
+        if (!active) continue;
+        const float fy = (float)(c.y0 + pix_row<TH, true>(it)), fx = (float)(c.x0 + pix_col<TH, true>(it));
+        const T* go = go_b + p;
+        T* gc = gc_b + p;
+        // offsets feed the propagation directly; the confidence gather detaches them (nlspn.py:118)
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const int idx = n < 4 ? n : n + 1;
-            // offsets feed the propagation directly; the confidence gather detaches them
+            const int idx = tap_index(n);
             st_stream(gc + (2 * n) * cs, ld_stream(go + (2 * idx) * cs));
             st_stream(gc + (2 * n + 1) * cs, ld_stream(go + (2 * idx + 1) * cs));
-            t[n] = scale_aff<AFF>(ld_stream(cv + (16 + n) * cs), gamma, th[n]);
+        }
+        // recompute t_n = scaled affinity, cval_n = gathered confidence
+        float th[8], cval[8];
+        unsigned slow = 0u;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            th[n] = tanh_type ? aff_tanh(af[n]) : 0.f;
+            af[n] = tanh_type ? th[n] * rgam : af[n];  // af[] now holds t_n
             cval[n] = 1.f;
             if (CONF) {
-                const float oh = ld_stream(cv + (2 * n) * cs), ow = ld_stream(cv + (2 * n + 1) * cs);
-                bil[n] = bilinear_at<T>(cf, H, W, (float)y + oh, (float)x + ow);
-                cval[n] = bil_value(bil[n]);
+                const FastTap t = fast_tap<T>(tile_lo, c, fy + oh[n], fx + ow[n]);
+                cval[n] = t.ok ? bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw) : 0.f;
+                slow |= t.ok ? 0u : (1u << n);
             }
-            u[n] = t[n] * cval[n];
-            sabs += fabsf(u[n]);
+        }
+        if (CONF && slow) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (slow & (1u << n)) {
+                    const SlowTap t = slow_tap<T>(conf_b, g, fy + oh[n], fx + ow[n], nullptr);
+                    cval[n] = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+                }
+            }
+        }
+        float sabs = 0.f, dot = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float u = af[n] * cval[n];
+            sabs += fabsf(u);
+            dot = fmaf(gn[n], u, dot);
         }
         sabs += 1e-4f;
         bool clamped = false;
-        if (AFF == AFF_ASS || AFF == AFF_TGASS) {
+        if (affinity == AFF_ASS || affinity == AFF_TGASS) {
             clamped = sabs < 1.f;
             if (clamped) sabs = 1.f;
         }
-        const float gcen = ld_stream(ga + 4 * cs);
-        float gn[8], dot = 0.f;
+        const float inv = normalised ? __fdiv_rn(1.f, sabs) : 1.f;
+        const float corr = (normalised && !clamped) ? dot * inv * inv : 0.f;  // d(sum|u|)/du term
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            gn[n] = ld_stream(ga + (n < 4 ? n : n + 1) * cs) - gcen;  // centre = 1 - sum
-            dot += gn[n] * u[n];
-        }
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            float gu = gn[n];
-            if (AFF != AFF_TC) {
-                gu = __fdiv_rn(gn[n], sabs);
-                if (!clamped) {
-                    const float sgn = u[n] > 0.f ? 1.f : (u[n] < 0.f ? -1.f : 0.f);
-                    gu -= sgn * __fdiv_rn(dot, sabs * sabs);
-                }
-            }
-            float gt = gu * cval[n];
-            if (CONF && gcf) {
-                const float gv = gu * t[n];  // dL/d conf_sample
-                const Bil& r = bil[n];
-                if (r.inside && gv != 0.f) {
-                    const float hh = 1.f - r.lh, hw = 1.f - r.lw;
-                    const int h1 = r.h0 + 1, w1 = r.w0 + 1;
-                    if (r.h0 >= 0 && r.w0 >= 0) atomicAdd(gcf + (size_t)r.h0 * W + r.w0, gv * hh * hw);
-                    if (r.h0 >= 0 && w1 <= W - 1) atomicAdd(gcf + (size_t)r.h0 * W + w1, gv * hh * r.lw);
-                    if (h1 <= H - 1 && r.w0 >= 0) atomicAdd(gcf + (size_t)h1 * W + r.w0, gv * r.lh * hw);
-                    if (h1 <= H - 1 && w1 <= W - 1) atomicAdd(gcf + (size_t)h1 * W + w1, gv * r.lh * r.lw);
+            const float u = af[n] * cval[n];
+            const float sgn = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+            const float gu = gn[n] * inv - sgn * corr;   // dL/du_n
+            const float gt = gu * cval[n];               // dL/dt_n
+            if (scatter) {
+                const float gv = gu * af[n];             // dL/d(confidence sample)
+                const float h = fy + oh[n], w = fx + ow[n];
+                if (slow & (1u << n)) {
+                    const SlowTap t = slow_tap<T>(conf_b, g, h, w, nullptr);
+                    // torchvision's forward returns 0 for a sample wholly outside (-1,H)x(-1,W): no gradient there
+                    const bool inside = t.finite && h > -1.f && h < (float)g.H_img && w > -1.f && w < (float)g.W;
+                    if (inside && gv != 0.f) {
+                        const float ch = gv * t.lh, cl = gv - ch, c2 = cl * t.lw, c4 = ch * t.lw;
+                        const int r0 = t.h0, q0 = t.w0;
+                        if ((unsigned)r0 < (unsigned)g.H_img && (unsigned)q0 < (unsigned)g.W) atomicAdd(gcf_b + (size_t)r0 * g.W + q0, cl - c2);
+                        if ((unsigned)r0 < (unsigned)g.H_img && (unsigned)(q0 + 1) < (unsigned)g.W) atomicAdd(gcf_b + (size_t)r0 * g.W + q0 + 1, c2);
+                        if ((unsigned)(r0 + 1) < (unsigned)g.H_img && (unsigned)q0 < (unsigned)g.W) atomicAdd(gcf_b + (size_t)(r0 + 1) * g.W + q0, ch - c4);
+                        if ((unsigned)(r0 + 1) < (unsigned)g.H_img && (unsigned)(q0 + 1) < (unsigned)g.W) atomicAdd(gcf_b + (size_t)(r0 + 1) * g.W + q0 + 1, c4);
+                    }
+                } else {
+                    const FastTap t = fast_tap<T>(tile_lo, c, h, w);  // geometry only (values unused)
+                    const float ch = gv * t.lh, cl = gv - ch, c2 = cl * t.lw, c4 = ch * t.lw;
+                    float* gtp = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
+                    atomicAdd(gtp, cl - c2);
+                    atomicAdd(gtp + 1, c2);
+                    atomicAdd(gtp + SW, ch - c4);
+                    atomicAdd(gtp + SW + 1, c4);
                 }
             }
             float gaf = gt;
-            if (AFF == AFF_TC || AFF == AFF_TGASS) {
-                gaf = __fdiv_rn(__fdiv_rn(gt, geff) * (1.f - th[n] * th[n]), 100.f);
-                if (AFF == AFF_TGASS) acc_gamma -= gt * __fdiv_rn(th[n], geff * geff);
+            if (tanh_type) {
+                gaf = gt * rgam * (1.f - th[n] * th[n]) * 0.01f;
+                if (affinity == AFF_TGASS) acc_gamma -= gt * th[n] * rgam * rgam;
             }
             st_stream(gc + (16 + n) * cs, gaf);
         }
     }
-    if (AFF == AFF_TGASS && grad_scale != nullptr) {
+
+    if (scatter) {  // flush the accumulation tile: contributions to cells outside the image are dropped
+        __syncthreads();
+        const bool vec_ok = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad_conf) & 15) == 0);
+        for (int i = threadIdx.x; i < SH * (SW / 4); i += THREADS) {
+            const int r = i / (SW / 4), q = (i - r * (SW / 4)) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(gtile + r * SW + q);
+            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            const int gy = c.oy + r, gx = c.ox + q;
+            if ((unsigned)gy >= (unsigned)g.H_img) continue;
+            float* dst = gcf_b + (size_t)gy * g.W + gx;
+            if (vec_ok && gx >= 0 && gx + 3 < g.W) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                             "f"(v.w)
+                             : "memory");
+            } else {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((unsigned)(gx + j) < (unsigned)g.W && vv[j] != 0.f) atomicAdd(dst + j, vv[j]);
+            }
+        }
+    }
+
+    if (affinity == AFF_TGASS && grad_scale != nullptr) {
         acc_gamma = warp_sum(acc_gamma);
         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc_gamma;
         __syncthreads();
         if (threadIdx.x == 0) {
             float v = 0.f;
-            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += s_red[i];
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) v += s_red[i];
             atomicAdd(&ws->sums[0], (double)v);
             __threadfence();
             const unsigned tk = atomicAdd(&ws->ticket, 1u);
@@ -208,74 +323,62 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
     }
 }
 
-static int grid_for(size_t total) { return (int)min((size_t)148 * 8, (total + 255) / 256); }
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+struct AffArgs {
+    const void* conv_out; const void* conf; const float* gamma;
+    void* offset_out; void* aff_out;
+    const void* grad_offset; const void* grad_aff; void* grad_conv; float* grad_conf; float* grad_scale; void* ws;
+    Geom g; int affinity; int legacy; bool use_tma; int tile_h; CUtensorMap tmap; cudaStream_t stream;
+};
 
-template <typename T, int AFF>
-static void fwd_aff(const void* conv_out, const void* conf, const float* gamma, void* off, void* aff, int B, int H,
-                    int W, int legacy, cudaStream_t st) {
-    const int grid = grid_for((size_t)B * H * W);
-    if (conf)
-        nlspn_affinity_fwd_kernel<T, AFF, true><<<grid, 256, 0, st>>>((const T*)conv_out, (const T*)conf, gamma, (T*)off,
-                                                                      (T*)aff, B, H, W, legacy);
-    else
-        nlspn_affinity_fwd_kernel<T, AFF, false><<<grid, 256, 0, st>>>((const T*)conv_out, nullptr, gamma, (T*)off,
-                                                                       (T*)aff, B, H, W, 0);
+template <typename T, bool CONF, bool TMA, int TH>
+static void aff_fwd_launch(const AffArgs& a) {
+    dim3 grid((unsigned)((size_t)a.g.tiles_x * a.g.tiles_y * a.g.B));
+    nlspn_affinity_fwd_kernel<T, CONF, TMA, TH><<<grid, THREADS, 0, a.stream>>>(
+        (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.offset_out, (T*)a.aff_out, a.g, a.affinity, a.legacy, a.tmap);
 }
-template <typename T>
-static void fwd_dtype(const void* conv_out, const void* conf, const float* gamma, void* off, void* aff, int B, int H,
-                      int W, int affinity, int legacy, cudaStream_t st) {
-    switch (affinity) {
-        case AFF_AS: fwd_aff<T, AFF_AS>(conv_out, conf, gamma, off, aff, B, H, W, legacy, st); break;
-        case AFF_ASS: fwd_aff<T, AFF_ASS>(conv_out, conf, gamma, off, aff, B, H, W, legacy, st); break;
-        case AFF_TC: fwd_aff<T, AFF_TC>(conv_out, conf, gamma, off, aff, B, H, W, legacy, st); break;
-        default: fwd_aff<T, AFF_TGASS>(conv_out, conf, gamma, off, aff, B, H, W, legacy, st); break;
-    }
+template <typename T, bool CONF, bool TMA, int TH>
+static void aff_bwd_launch(const AffArgs& a) {
+    dim3 grid((unsigned)((size_t)a.g.tiles_x * a.g.tiles_y * a.g.B));
+    nlspn_affinity_bwd_kernel<T, CONF, TMA, TH><<<grid, THREADS, 0, a.stream>>>(
+        (const T*)a.grad_offset, (const T*)a.grad_aff, (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.grad_conv,
+        a.grad_conf, a.grad_scale, (ReduceWs*)a.ws, a.g, a.affinity, a.tmap);
 }
 
-cudaError_t launch_nlspn_affinity_forward(const void* conv_out, const void* confidence, const float* gamma,
-                                          void* offset_out, void* aff_out, int B, int H, int W, int affinity, int legacy,
-                                          bool bf16, cudaStream_t stream) {
-    if (bf16) fwd_dtype<__nv_bfloat16>(conv_out, confidence, gamma, offset_out, aff_out, B, H, W, affinity, legacy, stream);
-    else fwd_dtype<float>(conv_out, confidence, gamma, offset_out, aff_out, B, H, W, affinity, legacy, stream);
+template <typename T, bool FWD, bool CONF, bool TMA, int TH>
+static void aff_launch(const AffArgs& a) {
+    if (FWD) aff_fwd_launch<T, CONF, TMA, TH>(a);
+    else aff_bwd_launch<T, CONF, TMA, TH>(a);
+}
+
+template <typename T, bool FWD, int TH>
+static void aff_dispatch_th(const AffArgs& a) {
+    if (a.conf == nullptr) aff_launch<T, FWD, false, false, TH>(a);
+    else if (a.use_tma) aff_launch<T, FWD, true, true, TH>(a);
+    else aff_launch<T, FWD, true, false, TH>(a);
+}
+
+template <typename T, bool FWD>
+static cudaError_t aff_dispatch(const AffArgs& a) {
+    if (a.tile_h == 8) aff_dispatch_th<T, FWD, 8>(a);
+    else aff_dispatch_th<T, FWD, 2>(a);
     return cudaGetLastError();
 }
 
-template <typename T, int AFF>
-static void bwd_aff(const void* go, const void* ga, const void* conv_out, const void* conf, const float* gamma, void* gc,
-                    float* gconf, float* gscale, void* ws, int B, int H, int W, cudaStream_t st) {
-    const int grid = grid_for((size_t)B * H * W);
-    if (conf)
-        nlspn_affinity_bwd_kernel<T, AFF, true><<<grid, 256, 0, st>>>((const T*)go, (const T*)ga, (const T*)conv_out,
-                                                                      (const T*)conf, gamma, (T*)gc, gconf, gscale,
-                                                                      (ReduceWs*)ws, B, H, W);
-    else
-        nlspn_affinity_bwd_kernel<T, AFF, false><<<grid, 256, 0, st>>>((const T*)go, (const T*)ga, (const T*)conv_out,
-                                                                       nullptr, gamma, (T*)gc, nullptr, gscale,
-                                                                       (ReduceWs*)ws, B, H, W);
-}
-template <typename T>
-static void bwd_dtype(const void* go, const void* ga, const void* conv_out, const void* conf, const float* gamma,
-                      void* gc, float* gconf, float* gscale, void* ws, int B, int H, int W, int affinity,
-                      cudaStream_t st) {
-    switch (affinity) {
-        case AFF_AS: bwd_aff<T, AFF_AS>(go, ga, conv_out, conf, gamma, gc, gconf, gscale, ws, B, H, W, st); break;
-        case AFF_ASS: bwd_aff<T, AFF_ASS>(go, ga, conv_out, conf, gamma, gc, gconf, gscale, ws, B, H, W, st); break;
-        case AFF_TC: bwd_aff<T, AFF_TC>(go, ga, conv_out, conf, gamma, gc, gconf, gscale, ws, B, H, W, st); break;
-        default: bwd_aff<T, AFF_TGASS>(go, ga, conv_out, conf, gamma, gc, gconf, gscale, ws, B, H, W, st); break;
-    }
-}
-
-cudaError_t launch_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff, const void* conv_out,
-                                           const void* confidence, const float* gamma, void* grad_conv_out,
-                                           float* grad_confidence, float* grad_scale, void* workspace, int B, int H,
-                                           int W, int affinity, bool bf16, cudaStream_t stream) {
-    if (bf16)
-        bwd_dtype<__nv_bfloat16>(grad_offset, grad_aff, conv_out, confidence, gamma, grad_conv_out, grad_confidence,
-                                 grad_scale, workspace, B, H, W, affinity, stream);
-    else
-        bwd_dtype<float>(grad_offset, grad_aff, conv_out, confidence, gamma, grad_conv_out, grad_confidence, grad_scale,
-                         workspace, B, H, W, affinity, stream);
-    return cudaGetLastError();
+cudaError_t launch_nlspn_affinity(const void* conv_out, const void* confidence, const float* gamma, void* offset_out,
+                                  void* aff_out, const void* grad_offset, const void* grad_aff, void* grad_conv_out,
+                                  float* grad_confidence, float* grad_scale, void* workspace, const Geom& g, int tile_h,
+                                  bool use_tma, const CUtensorMap& tmap, int affinity, int legacy, bool bf16,
+                                  bool forward, cudaStream_t stream) {
+    AffArgs a;
+    a.conv_out = conv_out; a.conf = confidence; a.gamma = gamma; a.offset_out = offset_out; a.aff_out = aff_out;
+    a.grad_offset = grad_offset; a.grad_aff = grad_aff; a.grad_conv = grad_conv_out; a.grad_conf = grad_confidence;
+    a.grad_scale = grad_scale; a.ws = workspace; a.g = g; a.affinity = affinity; a.legacy = legacy;
+    a.use_tma = use_tma; a.tile_h = tile_h; a.tmap = tmap; a.stream = stream;
+    if (forward) return bf16 ? aff_dispatch<__nv_bfloat16, true>(a) : aff_dispatch<float, true>(a);
+    return bf16 ? aff_dispatch<__nv_bfloat16, false>(a) : aff_dispatch<float, false>(a);
 }
 
 }  // namespace jspsr
