@@ -6,7 +6,7 @@
 #include <cstring>
 
 #include "../../include/jspsr_spn.h"
-#include "spn_kernels.cuh"
+#include "spn_types.cuh"
 
 using namespace jspsr;
 
@@ -15,11 +15,23 @@ cudaError_t launch_offset_absmax(const void* offset, size_t n_pairs_block, size_
                                  cudaStream_t stream);
 cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const float* mask_fix, void* dst, size_t n,
                                   bool bf16, cudaStream_t stream);
-cudaError_t launch_nlspn_affinity(const void* conv_out, const void* confidence, const float* gamma, void* offset_out,
-                                  void* aff_out, const void* grad_offset, const void* grad_aff, void* grad_conv_out,
-                                  float* grad_confidence, float* grad_scale, void* workspace, const Geom& g, int tile_h,
-                                  bool use_tma, const CUtensorMap& tmap, int affinity, int legacy, bool bf16,
-                                  bool forward, cudaStream_t stream);
+// The tile kernels exist twice (spn_common.cuh): `wide` stages a 14/15-row, 16-column halo, `narrow` 6/7 rows and
+// 8 columns.  Wide wins on tile batches, narrow on whole rasters; the launcher picks by image width.
+#define JSPSR_DECLARE_VARIANT(NS)                                                                                       \
+    namespace NS {                                                                                                      \
+    cudaError_t launch_spn_forward(const LaunchArgs& la);                                                               \
+    cudaError_t launch_spn_backward(const LaunchArgs& la);                                                              \
+    int stage_box_cols();                                                                                               \
+    int stage_box_rows(int th);                                                                                         \
+    cudaError_t launch_nlspn_affinity(const void* conv_out, const void* confidence, const float* gamma,                 \
+                                      void* offset_out, void* aff_out, const void* grad_offset, const void* grad_aff,   \
+                                      void* grad_conv_out, float* grad_confidence, float* grad_scale, void* workspace,  \
+                                      const Geom& g, int tile_h, bool use_tma, const CUtensorMap& tmap, int affinity,   \
+                                      int legacy, bool bf16, bool forward, cudaStream_t stream);                        \
+    }
+JSPSR_DECLARE_VARIANT(narrow)
+JSPSR_DECLARE_VARIANT(wide)
+#undef JSPSR_DECLARE_VARIANT
 }  // namespace jspsr
 
 static thread_local char g_err[512] = "";
@@ -54,6 +66,15 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// wide halo for tile-like inputs, narrow for rasters (JSPSR_SPN_HALO=narrow|wide overrides)
+static bool choose_wide(int W) {
+    if (const char* e = getenv("JSPSR_SPN_HALO")) {
+        if (e[0] == 'w') return true;
+        if (e[0] == 'n') return false;
+    }
+    return W <= 1024;
+}
+
 static bool tma_disabled_by_env() {
     // read on every call so tests can flip it; the manual tile loader is the same
     // kernel with the TMA box copy replaced by bounds-checked loads
@@ -62,7 +83,8 @@ static bool tma_disabled_by_env() {
 }
 
 // Returns true when the TMA path can be used for this buffer (and fills *map).
-static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, int W, bool bf16, int tile_h) {
+static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, int W, bool bf16, int tile_h,
+                           bool wide) {
     if (tma_disabled_by_env()) return false;
     const size_t es = bf16 ? 2 : 4;
     if (((uintptr_t)init & 15) != 0) return false;
@@ -71,7 +93,8 @@ static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, 
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)W * es, (cuuint64_t)W * es * (cuuint64_t)rows};
-    cuuint32_t box[3] = {(cuuint32_t)SW, (cuuint32_t)staged_rows(tile_h), 1u};
+    cuuint32_t box[3] = {(cuuint32_t)(wide ? wide::stage_box_cols() : narrow::stage_box_cols()),
+                         (cuuint32_t)(wide ? wide::stage_box_rows(tile_h) : narrow::stage_box_rows(tile_h)), 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                      const_cast<void*>(init), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -97,7 +120,7 @@ static int check_align(const void* p, size_t a, const char* name) {
 static int choose_tile_h(int B, int Hs, int W, int max_th) {
     if (const char* e = getenv("JSPSR_SPN_TILE_H")) {
         const int v = atoi(e);
-        if (v == 16 || v == 8 || v == 4 || v == 2) return v;
+        if ((v == 16 || v == 8 || v == 4 || v == 2) && v <= max_th) return v;
     }
     const size_t tx = (size_t)(W + TILE_W - 1) / TILE_W;
     for (int th = max_th; th > 2; th >>= 1) {
@@ -146,8 +169,9 @@ int jspsr_spn_forward_strip(const void* init, const void* weight, const void* of
     la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9; la.b1 = b1; la.out = out;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.status = status;
     la.stream = (cudaStream_t)stream;
-    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, la.bf16, la.tile_h);
-    cudaError_t ce = launch_spn_forward(la);
+    const bool wide = choose_wide(W);
+    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, la.bf16, la.tile_h, wide);
+    cudaError_t ce = wide ? wide::launch_spn_forward(la) : narrow::launch_spn_forward(la);
     if (ce != cudaSuccess) return cuda_fail(ce, "spn_forward launch");
     return JSPSR_OK;
 }
@@ -184,12 +208,13 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     la.grad_w9 = grad_w9; la.grad_b1 = grad_b1; la.workspace = workspace;
     la.accumulate = (flags & JSPSR_BWD_ACCUMULATE) != 0;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.stream = (cudaStream_t)stream;
-    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, la.bf16, la.tile_h);
+    const bool wide = choose_wide(W);
+    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, la.bf16, la.tile_h, wide);
     if (grad_init) {
         cudaError_t ce = cudaMemsetAsync(grad_init, 0, (size_t)B * H * W * sizeof(float), la.stream);
         if (ce != cudaSuccess) return cuda_fail(ce, "grad_init memset");
     }
-    cudaError_t ce = launch_spn_backward(la);
+    cudaError_t ce = wide ? wide::launch_spn_backward(la) : narrow::launch_spn_backward(la);
     if (ce != cudaSuccess) return cuda_fail(ce, "spn_backward launch");
     return JSPSR_OK;
 }
@@ -244,8 +269,9 @@ int jspsr_spn_iterate(const void* feat_init, const void* aff, const void* offset
             if (int e = fill_geom(&la, nb, H, W, H, 0, 0, H, 16)) return e;
             la.init = src; la.weight = aff_c; la.offset = off_c; la.w9 = nullptr; la.b1 = nullptr; la.out = dst;
             la.mode = NORM_NONE; la.scale = 0.f; la.bf16 = bf16; la.stream = (cudaStream_t)stream;
-            la.use_tma = make_init_tmap(&la.tmap, src, nb, H, W, bf16, la.tile_h);
-            cudaError_t ce = launch_spn_forward(la);
+            const bool wide = choose_wide(W);
+            la.use_tma = make_init_tmap(&la.tmap, src, nb, H, W, bf16, la.tile_h, wide);
+            cudaError_t ce = wide ? wide::launch_spn_forward(la) : narrow::launch_spn_forward(la);
             if (ce != cudaSuccess) return cuda_fail(ce, "spn_iterate launch");
             src = dst;
         }
@@ -267,8 +293,9 @@ int jspsr_nlspn_affinity_forward(const void* conv_out, const void* confidence, c
         la.g.tiles_y = (H + 1) / 2;
     }
     const bool bf16 = dtype == JSPSR_BF16;
-    la.use_tma = confidence && make_init_tmap(&la.tmap, confidence, B, H, W, bf16, la.tile_h);
-    cudaError_t ce = launch_nlspn_affinity(conv_out, confidence, aff_scale_const, offset_out, aff_out, nullptr, nullptr,
+    const bool wide = choose_wide(W);
+    la.use_tma = confidence && make_init_tmap(&la.tmap, confidence, B, H, W, bf16, la.tile_h, wide);
+    cudaError_t ce = (wide ? wide::launch_nlspn_affinity : narrow::launch_nlspn_affinity)(conv_out, confidence, aff_scale_const, offset_out, aff_out, nullptr, nullptr,
                                            nullptr, nullptr, nullptr, nullptr, la.g, la.tile_h, la.use_tma, la.tmap,
                                            affinity, legacy, bf16, true, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "nlspn_affinity_forward launch");
@@ -296,8 +323,9 @@ int jspsr_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff,
         la.g.tiles_y = (H + 1) / 2;
     }
     const bool bf16 = dtype == JSPSR_BF16;
-    la.use_tma = confidence && make_init_tmap(&la.tmap, confidence, B, H, W, bf16, la.tile_h);
-    cudaError_t ce = launch_nlspn_affinity(conv_out, confidence, aff_scale_const, nullptr, nullptr, grad_offset, grad_aff,
+    const bool wide = choose_wide(W);
+    la.use_tma = confidence && make_init_tmap(&la.tmap, confidence, B, H, W, bf16, la.tile_h, wide);
+    cudaError_t ce = (wide ? wide::launch_nlspn_affinity : narrow::launch_nlspn_affinity)(conv_out, confidence, aff_scale_const, nullptr, nullptr, grad_offset, grad_aff,
                                            grad_conv_out, grad_confidence, grad_scale, workspace, la.g, la.tile_h,
                                            la.use_tma, la.tmap, affinity, 0, bf16, false, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "nlspn_affinity_backward launch");

@@ -12,6 +12,7 @@
 #include "spn_kernels.cuh"
 
 namespace jspsr {
+inline namespace JSPSR_VARIANT {
 
 enum { AFF_AS = 0, AFF_ASS = 1, AFF_TC = 2, AFF_TGASS = 3 };
 
@@ -381,4 +382,5 @@ cudaError_t launch_nlspn_affinity(const void* conv_out, const void* confidence, 
     return bf16 ? aff_dispatch<__nv_bfloat16, false>(a) : aff_dispatch<float, false>(a);
 }
 
+}  // namespace JSPSR_VARIANT
 }  // namespace jspsr

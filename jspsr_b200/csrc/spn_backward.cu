@@ -11,6 +11,7 @@
 #include "spn_kernels.cuh"
 
 namespace jspsr {
+inline namespace JSPSR_VARIANT {
 
 template <typename T>
 __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, const Geom& g, int hi, int wi, float v) {
@@ -321,7 +322,6 @@ static cudaError_t launch_bwd_th(const LaunchArgs& la) {
 template <typename T>
 static cudaError_t launch_bwd_dtype(const LaunchArgs& la) {
     switch (la.tile_h) {
-        case 16: return launch_bwd_th<T, 16>(la);
         case 8: return launch_bwd_th<T, 8>(la);
         case 4: return launch_bwd_th<T, 4>(la);
         case 2: return launch_bwd_th<T, 2>(la);
@@ -333,4 +333,5 @@ cudaError_t launch_spn_backward(const LaunchArgs& la) {
     return la.bf16 ? launch_bwd_dtype<__nv_bfloat16>(la) : launch_bwd_dtype<float>(la);
 }
 
+}  // namespace JSPSR_VARIANT
 }  // namespace jspsr

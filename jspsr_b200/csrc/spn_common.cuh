@@ -1,11 +1,15 @@
 // Shared device helpers for the propagation kernels (sm_100a only).
 #pragma once
-#include <cuda.h>
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "spn_types.cuh"
+
+// The kernels are compiled twice, once per staged-halo size; JSPSR_VARIANT names the inline
+// namespace so both sets of symbols can live in one library (see Makefile, abi.cu).
+#ifndef JSPSR_VARIANT
+#define JSPSR_VARIANT narrow
+#endif
 
 namespace jspsr {
+inline namespace JSPSR_VARIANT {
 
 // ---------------------------------------------------------------------------
 // Tile geometry.  One CTA owns a TILE_H x TILE_W block of output pixels of one
@@ -15,37 +19,32 @@ namespace jspsr {
 // [SH][SW] box so one 3-D TMA box copy (zero-filled outside the image, which is
 // exactly torchvision's zero-outside rule) can fill it.
 // ---------------------------------------------------------------------------
-constexpr int TILE_W = 128;
 // Rows per CTA are a template parameter TH in {16, 8, 4, 2}: 16 for large problems (least
 // halo overhead, 8 pixels per thread), smaller for small batches so that the grid still
 // covers all 148 SMs a few times over and a thread's serial chain of pixels stays short
 // (the reference's own batch of 70 tiles is only 560 CTAs at TH = 16).
-constexpr int HALO_T = 6, HALO_B = 7;   // rows above / below  (bottom needs the +1 bilinear row)
+// Two halo sizes (measured, B200): the wide one keeps offsets up to +-13 rows / +-14 columns on
+// chip and is 2-25 % faster on tile batches (sigma 1.5 .. 4 px offsets), the narrow one (+-5 px) is
+// 5-9 % faster on whole rasters, where every staged row is a separate 32 KB-strided DRAM segment.
+#ifdef JSPSR_HALO_WIDE
+constexpr int HALO_T = 14, HALO_B = 15;  // rows above / below  (bottom needs the +1 bilinear row)
+#else
+constexpr int HALO_T = 6, HALO_B = 7;
+#endif
 // cols left / right.  Measured on B200 (tools/tma_probe.cu): the innermost TMA box
 // coordinate must be 16-byte aligned (c0 * sizeof(T) % 16 == 0; negative is fine, an
 // unaligned c0 raises "illegal instruction"), rows are free.  x0 is a multiple of 128, so
 // a left halo of 8 keeps x0 - 8 aligned for fp32 and bf16; SW must be a multiple of 8
 // elements for the bf16 box (inner extent multiple of 16 bytes).
+#ifdef JSPSR_HALO_WIDE
+constexpr int HALO_L = 16, HALO_R = 16;
+#else
 constexpr int HALO_L = 8, HALO_R = 8;
+#endif
 constexpr int SW = TILE_W + HALO_L + HALO_R;  // 144
 constexpr int staged_rows(int th) { return th + HALO_T + HALO_B; }  // 29 for TH = 16
-constexpr int THREADS = 256;
-constexpr int WARPS = THREADS / 32;
 static_assert(SW % 8 == 0 && HALO_L % 8 == 0 && TILE_W % 8 == 0, "TMA inner box extent / origin must be multiples of 16 bytes");
 static_assert(SW <= 256 && staged_rows(16) <= 256, "TMA box extents are limited to 256");
-
-enum { NORM_NONE = 0, NORM_RESIDUAL = 1, NORM_SUM = 2 };
-
-// Geometry of one call.  Rows are expressed in GLOBAL image coordinates so that
-// a row strip (multi-GPU sharding) computes bit-identical positions.
-struct Geom {
-    int B, H, W;          // rows/cols of weight/offset/out held by this call (the strip)
-    int H_img;            // rows of the whole image
-    int row0;             // global row of out row 0
-    int init_row0;        // global row of init buffer row 0
-    int init_rows;        // rows present in the init buffer
-    int tiles_x, tiles_y;
-};
 
 // ---------------------------------------------------------------------------
 // element access
@@ -183,4 +182,5 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+}  // namespace JSPSR_VARIANT
 }  // namespace jspsr

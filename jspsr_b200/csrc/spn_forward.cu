@@ -9,6 +9,7 @@
 #include "spn_kernels.cuh"
 
 namespace jspsr {
+inline namespace JSPSR_VARIANT {
 
 // CS: compile-time channel stride H*W (0 = runtime).  With CS known (the reference's
 // 128x128 tiles: 16384) the 27 channel loads of a pixel share one address register with
@@ -166,8 +167,12 @@ static cudaError_t launch_fwd_dtype(const LaunchArgs& la) {
     return cudaGetLastError();
 }
 
+int stage_box_cols() { return SW; }
+int stage_box_rows(int th) { return staged_rows(th); }
+
 cudaError_t launch_spn_forward(const LaunchArgs& la) {
     return la.bf16 ? launch_fwd_dtype<__nv_bfloat16>(la) : launch_fwd_dtype<float>(la);
 }
 
+}  // namespace JSPSR_VARIANT
 }  // namespace jspsr

@@ -4,6 +4,7 @@
 #include "spn_common.cuh"
 
 namespace jspsr {
+inline namespace JSPSR_VARIANT {
 
 constexpr int FWD_MIN_BLOCKS = 4;  // 1024 threads/SM, <= 64 registers/thread
 constexpr int BWD_MIN_BLOCKS = 3;
@@ -146,43 +147,12 @@ __device__ __noinline__ SlowTap slow_tap(const T* __restrict__ init_b, const Geo
     return t;
 }
 
-// Host-side launch descriptor (filled by abi.cu)
-struct LaunchArgs {
-    const void* init = nullptr;
-    const void* weight = nullptr;
-    const void* offset = nullptr;
-    const float* w9 = nullptr;
-    const float* b1 = nullptr;
-    void* out = nullptr;
-    // backward only
-    const void* grad_out = nullptr;
-    float* grad_init = nullptr;
-    void* grad_weight = nullptr;
-    void* grad_offset = nullptr;
-    float* grad_w9 = nullptr;
-    float* grad_b1 = nullptr;
-    void* workspace = nullptr;
-    bool accumulate = false;
-    Geom g{};
-    int mode = NORM_RESIDUAL;
-    float scale = 1.f;
-    bool bf16 = false;
-    bool use_tma = false;
-    int* status = nullptr;
-    int tile_h = 16;  // rows per CTA (16 / 8 / 4 / 2), chosen by abi.cu; the TMA box is encoded to match
-    int tiles_y_of(int th) const { return (g.H + th - 1) / th; }
-    cudaStream_t stream = nullptr;
-    CUtensorMap tmap{};
-};
-
+// per-variant entry points used by abi.cu
 cudaError_t launch_spn_forward(const LaunchArgs& la);
 cudaError_t launch_spn_backward(const LaunchArgs& la);
+int stage_box_cols();        // extents of the staged DEM box = the TMA box
+int stage_box_rows(int th);
 
-// reduction workspace layout (caller-owned, zero on entry, zero on exit)
-struct alignas(16) ReduceWs {
-    double sums[12];          // grad_w[0..8], grad_b, spare
-    unsigned int ticket;      // CTAs that have contributed
-    unsigned int pad[3];
-};
 
+}  // namespace JSPSR_VARIANT
 }  // namespace jspsr

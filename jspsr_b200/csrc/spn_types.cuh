@@ -1,0 +1,64 @@
+// Halo-independent types shared by abi.cu and both kernel variants.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jspsr {
+
+constexpr int TILE_W = 128;   // columns per CTA
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+
+enum { NORM_NONE = 0, NORM_RESIDUAL = 1, NORM_SUM = 2 };
+
+// Geometry of one call.  Rows are expressed in GLOBAL image coordinates so that
+// a row strip (multi-GPU sharding) computes bit-identical positions.
+struct Geom {
+    int B, H, W;          // rows/cols of weight/offset/out held by this call (the strip)
+    int H_img;            // rows of the whole image
+    int row0;             // global row of out row 0
+    int init_row0;        // global row of init buffer row 0
+    int init_rows;        // rows present in the init buffer
+    int tiles_x, tiles_y;
+};
+
+// Host-side launch descriptor (filled by abi.cu)
+struct LaunchArgs {
+    const void* init = nullptr;
+    const void* weight = nullptr;
+    const void* offset = nullptr;
+    const float* w9 = nullptr;
+    const float* b1 = nullptr;
+    void* out = nullptr;
+    // backward only
+    const void* grad_out = nullptr;
+    float* grad_init = nullptr;
+    void* grad_weight = nullptr;
+    void* grad_offset = nullptr;
+    float* grad_w9 = nullptr;
+    float* grad_b1 = nullptr;
+    void* workspace = nullptr;
+    bool accumulate = false;
+    Geom g{};
+    int mode = NORM_RESIDUAL;
+    float scale = 1.f;
+    bool bf16 = false;
+    bool use_tma = false;
+    int* status = nullptr;
+    int tile_h = 16;  // rows per CTA (16 / 8 / 4 / 2), chosen by abi.cu; the TMA box is encoded to match
+    cudaStream_t stream = nullptr;
+    CUtensorMap tmap{};
+};
+
+
+// reduction workspace layout (caller-owned, zero on entry, zero on exit)
+struct alignas(16) ReduceWs {
+    double sums[12];          // grad_w[0..8], grad_b, spare
+    unsigned int ticket;      // CTAs that have contributed
+    unsigned int pad[3];
+};
+
+
+}  // namespace jspsr

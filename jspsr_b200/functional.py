@@ -265,7 +265,20 @@ class _Propagate(torch.autograd.Function):
                 gw if ctx.needs_input_grad[3] else None, gb if ctx.needs_input_grad[4] else None, None, None)
 
 
+def _common_dtype(*tensors):
+    """Mixed dtypes (e.g. under torch.autocast, where torchvision's operator casts everything to fp32):
+    promote to float32; a uniform bf16 / fp32 set is used as is."""
+    dts = {t.dtype for t in tensors}
+    if len(dts) == 1:
+        return tensors
+    return tuple(t.float() for t in tensors)
+
+
 def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) -> torch.Tensor:
+    init, weight, offset = _common_dtype(init, weight, offset)
+    if init.shape[0] == 0:  # empty batch: nothing to launch (the reference returns an empty tensor too)
+        _check_shapes(init, weight, offset)
+        return init.new_empty(init.shape) + 0 * (weight.sum() + offset.sum() + w.sum() + b.sum())
     return _Propagate.apply(init, weight, offset, w, b, norm_mode, scale)
 
 
