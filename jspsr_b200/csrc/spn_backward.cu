@@ -25,7 +25,7 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
 // CS : compile-time channel stride H*W (0 = runtime), see spn_forward.cu.
 // TH : rows per CTA.  `mode` is a runtime, warp-uniform switch.
 template <typename T, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH>
-__global__ void __launch_bounds__(THREADS, BWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(THREADS, sizeof(T) == 2 ? BWD_MIN_BLOCKS_BF16 : BWD_MIN_BLOCKS)
 spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, const T* __restrict__ weight,
                     const T* __restrict__ offset, const float* __restrict__ w9, float* __restrict__ grad_init,
                     T* __restrict__ grad_weight, T* __restrict__ grad_offset, float* __restrict__ grad_w9,

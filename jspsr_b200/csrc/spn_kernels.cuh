@@ -7,7 +7,8 @@ namespace jspsr {
 inline namespace JSPSR_VARIANT {
 
 constexpr int FWD_MIN_BLOCKS = 4;  // 1024 threads/SM, <= 64 registers/thread
-constexpr int BWD_MIN_BLOCKS = 3;
+constexpr int BWD_MIN_BLOCKS = 3;       // fp32: 80 registers beat 64 + spills (measured)
+constexpr int BWD_MIN_BLOCKS_BF16 = 4;  // bf16 is issue-bound: the extra resident CTA is worth 5 %
 constexpr int pixels_per_thread(int th) { return th * TILE_W / THREADS; }  // 8 for TH = 16
 
 // Pixel `it` of a thread inside the TH x 128 block.  A warp always covers 32 consecutive x of
