@@ -1,0 +1,42 @@
+"""Small run through every kernel family for compute-sanitizer (memcheck / racecheck)."""
+import os, sys, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import jspsr_b200
+from jspsr_b200 import functional as F
+torch.manual_seed(0)
+for dt in (torch.float32, torch.bfloat16):
+    for (B, H, W, sig) in ((2, 40, 128, 1.5), (1, 37, 150, 6.0), (1, 20, 260, 2.0), (3, 9, 7, 1.0)):
+        init = torch.rand(B, 1, H, W, device="cuda").to(dt).requires_grad_()
+        weight = torch.rand(B, 9, H, W, device="cuda").to(dt).requires_grad_()
+        offset = (sig * torch.randn(B, 18, H, W, device="cuda")).to(dt).requires_grad_()
+        for mode_mod in (jspsr_b200.PostProcessor(3, True, 0.5), jspsr_b200.PostProcessor(3, False, 1.0)):
+            m = mode_mod.cuda()
+            out = m(init, weight, offset)
+            out.float().square().mean().backward()
+        for tma in ("0", "1"):
+            os.environ["JSPSR_SPN_DISABLE_TMA"] = tma
+            F.spn_forward(init.detach(), weight.detach(), offset.detach(), m.w, m.b, 1, 1.0)
+        os.environ["JSPSR_SPN_DISABLE_TMA"] = "0"
+        for halo in ("narrow", "wide"):
+            os.environ["JSPSR_SPN_HALO"] = halo
+            F.spn_backward(torch.randn_like(init), init.detach(), weight.detach(), offset.detach(), m.w, 1, 1.0)
+        os.environ.pop("JSPSR_SPN_HALO")
+        F.spn_iterate(init.detach(), weight.detach() * 0.1, offset.detach(), 3)
+        F.offset_absmax(offset.detach())
+args = types.SimpleNamespace(prop_time=3, affinity="TGASS", affinity_gamma=0.5, conf_prop=True, preserve_input=True, legacy=False)
+nl = jspsr_b200.NLSPN(args, 8, 1, 3, 3).cuda()
+with torch.no_grad():
+    nl.conv_offset_aff.weight.normal_(0, 0.3); nl.conv_offset_aff.bias.normal_(0, 0.5)
+g = torch.randn(2, 8, 33, 140, device="cuda", requires_grad=True)
+c = torch.rand(2, 1, 33, 140, device="cuda", requires_grad=True)
+f0 = torch.rand(2, 1, 33, 140, device="cuda", requires_grad=True)
+fix = torch.rand(2, 1, 33, 140, device="cuda") * (torch.rand(2, 1, 33, 140, device="cuda") > 0.7)
+feat, lst, off, aff, gam = nl(f0, g, c, fix)
+(feat.sum() + lst[0].sum()).backward()
+# strips
+ti = torch.rand(1, 1, 64, 128, device="cuda"); tw = torch.rand(1, 9, 64, 128, device="cuda"); to = torch.randn(1, 18, 64, 128, device="cuda")
+st = torch.zeros(1, dtype=torch.int32, device="cuda")
+F.spn_forward_strip(ti[:, :, 10:50].contiguous(), tw[:, :, 16:40].contiguous(), to[:, :, 16:40].contiguous(), None, None, 0, 0.0, 64, 16, 10, st)
+torch.cuda.synchronize()
+print("sanitize case done")
