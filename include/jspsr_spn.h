@@ -63,7 +63,8 @@ typedef enum { JSPSR_F32 = 0, JSPSR_BF16 = 1 } jspsr_dtype;
 typedef enum { JSPSR_AFF_AS = 0, JSPSR_AFF_ASS = 1, JSPSR_AFF_TC = 2, JSPSR_AFF_TGASS = 3 } jspsr_affinity;
 
 /* flags for jspsr_spn_backward */
-#define JSPSR_BWD_ACCUMULATE 1u /* grad_weight/grad_offset += (fixed-affinity T-step loop) instead of = */
+#define JSPSR_BWD_ACCUMULATE 1u /* grad_weight/grad_offset += (fixed-affinity T-step loop) instead of =;
+                                   implemented together with grad_init only (JSPSR_ERR_UNSUPPORTED otherwise) */
 
 int jspsr_version(void);
 const char *jspsr_last_error(void);

@@ -43,6 +43,9 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+// used by host_pipeline.cu so that every entry point reports through jspsr_last_error()
+int jspsr_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+
 static int cuda_fail(cudaError_t e, const char* what) {
     return fail(JSPSR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
@@ -192,6 +195,9 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
         return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
     if (grad_w9 && !workspace) return fail(JSPSR_ERR_BAD_ARG, "workspace is required when grad_w9 is requested");
     if (grad_b1 && !grad_w9) return fail(JSPSR_ERR_BAD_ARG, "grad_b1 without grad_w9 is not supported");
+    if ((flags & JSPSR_BWD_ACCUMULATE) && !grad_init)
+        return fail(JSPSR_ERR_UNSUPPORTED, "JSPSR_BWD_ACCUMULATE is implemented for the fixed-affinity loop only "
+                                           "(grad_init required)");
     const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
     if (int e = check_align(grad_out, es, "grad_out")) return e;
     if (int e = check_align(init, es, "init")) return e;

@@ -8,6 +8,8 @@
 #include "../../include/jspsr_spn.h"
 #include "spn_kernels.cuh"
 
+int jspsr_internal_fail(int code, const char* msg);  // abi.cu: sets the thread's last-error message
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static size_t slot_bytes(int chunk_B, int H, int W, size_t es) {
     const size_t px = (size_t)chunk_B * H * W;
@@ -23,8 +25,9 @@ extern "C" int jspsr_spn_forward_host(const void* init, const void* weight, cons
                                       const float* b1, void* out, int B, int H, int W, int norm_mode, float scale,
                                       int dtype, void* dev_scratch, size_t scratch_bytes, int chunk_B) {
     if (!init || !weight || !offset || !w9 || !b1 || !out || !dev_scratch || chunk_B <= 0 || B <= 0 || H <= 0 || W <= 0)
-        return JSPSR_ERR_BAD_ARG;
-    if (scratch_bytes < jspsr_spn_host_scratch_bytes(chunk_B, H, W, dtype)) return JSPSR_ERR_BAD_ARG;
+        return jspsr_internal_fail(JSPSR_ERR_BAD_ARG, "forward_host: null pointer or non-positive dimension");
+    if (scratch_bytes < jspsr_spn_host_scratch_bytes(chunk_B, H, W, dtype))
+        return jspsr_internal_fail(JSPSR_ERR_BAD_ARG, "forward_host: dev_scratch is smaller than jspsr_spn_host_scratch_bytes()");
     const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
     const size_t px = (size_t)H * W;
     char* base = (char*)dev_scratch;
@@ -35,10 +38,11 @@ extern "C" int jspsr_spn_forward_host(const void* init, const void* weight, cons
     cudaEvent_t ready;
     int rc = JSPSR_OK;
     cudaError_t ce;
-    if (cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking) != cudaSuccess) return JSPSR_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking) != cudaSuccess)
+        return jspsr_internal_fail(JSPSR_ERR_CUDA, "forward_host: cudaStreamCreate failed");
     if (cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking) != cudaSuccess) {
         cudaStreamDestroy(st[0]);
-        return JSPSR_ERR_CUDA;
+        return jspsr_internal_fail(JSPSR_ERR_CUDA, "forward_host: cudaStreamCreate failed");
     }
     cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
     cudaMemcpyAsync(d_w9, w9, 9 * sizeof(float), cudaMemcpyHostToDevice, st[0]);
@@ -68,6 +72,7 @@ extern "C" int jspsr_spn_forward_host(const void* init, const void* weight, cons
     cudaStreamDestroy(st[0]);
     cudaStreamDestroy(st[1]);
     if (rc != JSPSR_OK) return rc;
-    if (ce != cudaSuccess || ce2 != cudaSuccess) return JSPSR_ERR_CUDA;
+    if (ce != cudaSuccess || ce2 != cudaSuccess)
+        return jspsr_internal_fail(JSPSR_ERR_CUDA, cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
     return JSPSR_OK;
 }
