@@ -6,8 +6,9 @@
 //   writes grad_affinity[9], grad_offset[18]            (dense, one owner per element)
 //          grad_w[9], grad_b                            (warp shuffle -> CTA -> fp64 atomics,
 //                                                        last CTA publishes and re-zeroes)
-//          grad_init (optional)                         (scatter: shared-memory tile of
-//                                                        atomics, flushed with global REDs)
+//          grad_init (optional)                         (scatter: block-floating-point shared-memory
+//                                                        tile of native integer atomics, flushed
+//                                                        with global vector REDs)
 #include "spn_kernels.cuh"
 
 namespace jspsr {
@@ -20,6 +21,32 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
     if ((unsigned)br >= (unsigned)g.init_rows) return;
     atomicAdd(gi_b + (size_t)br * g.W + wi, v);
 }
+
+// grad_init accumulation tile.  sm_100a has no native shared-memory fp32 add: atomicAdd(float*) on shared
+// memory is an LDS + ATOMS.CAST.SPIN loop (measured: 36 of them per pixel double the kernel time, 0.46 of the
+// HBM roofline; lane-private tile copies buy 9 %, a hand-written atomicCAS loop is 4.7x slower).  Native
+// ATOMS.ADD exists for 32-bit integers, so the tile is block floating point: a pre-pass over the CTA's own
+// pixels sums |grad_out * m_k * w_k| over all taps (S); every cell's final magnitude is <= S because the four
+// bilinear coefficients of a tap sum to 1, so with scale = 2^e, S * 2^e <= 2^29, no cell can overflow, the
+// scaling itself is exact, and each contribution is rounded once to S * 2^-29 (typically ~1e-6 of the largest
+// contribution, far below fp32 atomics' own order-dependent rounding).  Sums inside a CTA are exact integers,
+// i.e. independent of the order the atomics land in.  A non-finite S poisons the CTA's cells with NaN.
+struct GiScale {
+    float scale, inv;
+    int poison;
+};
+__device__ __forceinline__ GiScale gi_scale_from_sum(float S) {
+    GiScale r;
+    r.poison = !(S < 3.0e38f);  // inf or NaN somewhere in this CTA's gradients
+    int ex = 0;
+    if (!r.poison && S > 0.f) frexpf(S, &ex);  // S < 2^ex
+    int e = 29 - ex;
+    e = max(-120, min(120, e));
+    r.scale = ldexpf(1.f, e);
+    r.inv = ldexpf(1.f, -e);
+    return r;
+}
+__device__ __forceinline__ void gi_add(int* cell, float v_scaled) { atomicAdd(cell, __float2int_rn(v_scaled)); }
 
 // ACC: grad_weight / grad_offset are added to (fixed-affinity T-step loop) instead of written.
 // CS : compile-time channel stride H*W (0 = runtime), see spn_forward.cu.
@@ -34,7 +61,9 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     constexpr int SH = staged_rows(TH);
     constexpr int PPT = pixels_per_thread(TH);
     __shared__ __align__(128) T tile[SH * SW];
-    __shared__ __align__(16) float gtile[GRAD_INIT ? SH * SW : 1];
+    __shared__ __align__(16) int gtile[GRAD_INIT ? SH * SW : 4];  // fixed-point accumulation tile
+    __shared__ float s_gi[WARPS];
+    __shared__ GiScale s_gis;
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_w[9];
     __shared__ float s_red[WARPS][10];
@@ -44,7 +73,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
     if (GRAD_INIT) {
-        for (int i = threadIdx.x; i < SH * SW; i += THREADS) gtile[i] = 0.f;
+        for (int i = threadIdx.x; i < SH * SW / 4; i += THREADS) reinterpret_cast<int4*>(gtile)[i] = make_int4(0, 0, 0, 0);
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -58,7 +87,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     T* goff_b = grad_offset + (size_t)c.b * 18 * cs;
     float* gi_b = GRAD_INIT ? grad_init + (size_t)c.b * g.init_rows * g.W : nullptr;
     const T* tile_lo = tile + c.r_lo * SW;
-    float* gtile_lo = gtile + (GRAD_INIT ? c.r_lo * SW : 0);
+    int* gtile_lo = gtile + (GRAD_INIT ? c.r_lo * SW : 0);
 
     float a[9], oh[9], ow[9], go;
     auto load_inputs = [&](int it, bool& active, size_t& p) {
@@ -114,8 +143,43 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
 
     bool active;
     size_t p;
+    float gscale = 0.f;
+    if (GRAD_INIT) {
+        // pre-pass: S = sum over this CTA's pixels and taps of |grad_out * m_k * w_k| (+ the residual term);
+        // runs while the TMA box is in flight, its 10 channels are re-read from L2 by the main loop
+        float wabs[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wabs[k] = fabsf(w9 ? __ldg(w9 + k) : 1.f);
+        float part = 0.f;
+#pragma unroll 1
+        for (int it = 0; it < PPT; ++it) {
+            const int y = c.y0 + pix_row<TH, true>(it), x = c.x0 + pix_col<TH, true>(it);
+            if (y < g.H && x < g.W) {
+                const size_t q = (size_t)y * g.W + x;
+                const float gq = to_f32(gout_b[q]);
+                float m[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) m[k] = to_f32(wgt_b[q + k * cs]);
+                normalise9(m, mode);
+                float sa = (mode == NORM_RESIDUAL) ? fabsf(scale) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sa = fmaf(fabsf(m[k]), wabs[k], sa);
+                part = fmaf(fabsf(gq), sa, part);
+            }
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_gi[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float S = 0.f;
+#pragma unroll
+            for (int wi = 0; wi < WARPS; ++wi) S += s_gi[wi];
+            s_gis = gi_scale_from_sum(S);
+        }
+    }
     load_inputs(0, active, p);
     stage_tile_wait<TMA>(&bar);
+    if (GRAD_INIT) gscale = s_gis.scale;  // published before the barrier inside stage_tile_wait
 
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
@@ -161,13 +225,14 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
             }
             if (GRAD_INIT) {
                 if (t.ok) {
-                    const float ch = gkm * t.lh, cl = gkm - ch;  // rows h0+1 / h0
+                    const float gks = gkm * gscale;              // exact: the scale is a power of two
+                    const float ch = gks * t.lh, cl = gks - ch;  // rows h0+1 / h0
                     const float c2 = cl * t.lw, c4 = ch * t.lw;
-                    float* gt = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
-                    atomicAdd(gt, cl - c2);
-                    if (c2 != 0.f) atomicAdd(gt + 1, c2);            // zero for integer columns (centre tap)
-                    if (ch != c4) atomicAdd(gt + SW, ch - c4);       // zero for integer rows
-                    if (c4 != 0.f) atomicAdd(gt + SW + 1, c4);
+                    int* gt = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
+                    gi_add(gt, cl - c2);
+                    if (c2 != 0.f) gi_add(gt + 1, c2);            // zero for integer columns (centre tap)
+                    if (ch != c4) gi_add(gt + SW, ch - c4);       // zero for integer rows
+                    if (c4 != 0.f) gi_add(gt + SW + 1, c4);
                 }
             }
         }
@@ -203,7 +268,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
             const float mean = __fdiv_rn(sg, 9.f);
 #pragma unroll
             for (int k = 0; k < 9; ++k) gm[k] -= mean;
-            if (GRAD_INIT) atomicAdd(gtile + (ry + HALO_T) * SW + (cx + HALO_L), scale * go);
+            if (GRAD_INIT) gi_add(gtile + (ry + HALO_T) * SW + (cx + HALO_L), (scale * go) * gscale);
         } else if (mode == NORM_SUM) {
             float dot = 0.f;
 #pragma unroll
@@ -228,10 +293,12 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     if (GRAD_INIT) {
         __syncthreads();
         const bool vec_ok = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad_init) & 15) == 0);
+        const float ginv = s_gis.poison ? __int_as_float(0x7fc00000) : s_gis.inv;
         for (int i = threadIdx.x; i < SH * (SW / 4); i += THREADS) {
             const int r = i / (SW / 4), q = (i - r * (SW / 4)) * 4;
-            const float4 v = *reinterpret_cast<const float4*>(gtile + r * SW + q);
-            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            const int4 iv = *reinterpret_cast<const int4*>(gtile + r * SW + q);
+            if ((iv.x | iv.y | iv.z | iv.w) == 0 && !s_gis.poison) continue;
+            const float4 v = make_float4((float)iv.x * ginv, (float)iv.y * ginv, (float)iv.z * ginv, (float)iv.w * ginv);
             const int gy = c.oy + r, gx = c.ox + q;
             const int br = gy - g.init_row0;
             if ((unsigned)gy >= (unsigned)g.H_img || (unsigned)br >= (unsigned)g.init_rows) continue;
