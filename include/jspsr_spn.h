@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 100 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 101 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,
@@ -115,6 +115,27 @@ int jspsr_spn_forward_strip(const void *init, const void *weight, const void *of
                             const float *w9, const float *b1, void *out, int B, int Hs, int W,
                             int H_img, int row0, int init_row0, int init_rows, int norm_mode,
                             float scale, int dtype, int *status, void *stream);
+
+/*
+ * Generator tail + propagation in one kernel (new boundary - the
+ * reference runs these as separate modules).  Replaces, for the last two layers of
+ * Generator.forward and the PostProcessor call that consumes them,
+ *   weight = conv_weight(feature)  = sigmoid(1x1 conv, C -> 9)        models/components/spn.py:41-44,66
+ *   offset = conv_offset(feature)  = 1x1 conv, C -> 16, then the zero centre pair is
+ *            inserted (view/chunk/insert/cat)                          models/components/spn.py:45-52,67-73
+ *   out    = PostProcessor.forward(init, weight, offset)               models/components/spn.py:99-118
+ *            (called at models/JSPSR.py:375, models/EDSR.py:134)
+ * feature [B,C,H,W] fp32 is the output of Generator.block (spn.py:65); conv_w is [25,C] row-major:
+ * rows 0..8 = conv_weight[0].weight[9,C,1,1], rows 9..24 = conv_offset.conv[0].weight[16,C,1,1];
+ * conv_b [25] the two biases in the same order (all on device, conv_w 16-byte aligned).
+ * The contraction runs on the tensor cores (tcgen05, tf32 with a 3-product split: fp32-level accuracy).
+ * weight_out [B,9,H,W] / offset_out [B,18,H,W]: both NULL (inference) or both given - they receive what
+ * the Generator would have returned, which is what jspsr_spn_backward needs.  C = 64, fp32 only.
+ */
+int jspsr_gen_spn_forward(const void *init, const void *feature, const float *conv_w,
+                          const float *conv_b, const float *w9, const float *b1, void *out,
+                          void *weight_out, void *offset_out, int B, int C, int H, int W,
+                          int norm_mode, float scale, int dtype, void *stream);
 
 /* max |row offset| and max |column offset| over a [B,18,H,W] tensor -> out2[2] (device,
  * combined with max so several calls may fold into one pair; zero it first).  Used to

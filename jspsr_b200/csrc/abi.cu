@@ -28,6 +28,8 @@ cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const 
                                       void* grad_conv_out, float* grad_confidence, float* grad_scale, void* workspace,  \
                                       const Geom& g, int tile_h, bool use_tma, const CUtensorMap& tmap, int affinity,   \
                                       int legacy, bool bf16, bool forward, cudaStream_t stream);                        \
+    cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const void* feature, int C, const float* conv_w,           \
+                                       const float* conv_b, void* weight_out, void* offset_out);                        \
     }
 JSPSR_DECLARE_VARIANT(narrow)
 JSPSR_DECLARE_VARIANT(wide)
@@ -222,6 +224,42 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     }
     cudaError_t ce = wide ? wide::launch_spn_backward(la) : narrow::launch_spn_backward(la);
     if (ce != cudaSuccess) return cuda_fail(ce, "spn_backward launch");
+    return JSPSR_OK;
+}
+
+int jspsr_gen_spn_forward(const void* init, const void* feature, const float* conv_w, const float* conv_b,
+                          const float* w9, const float* b1, void* out, void* weight_out, void* offset_out, int B, int C,
+                          int H, int W, int norm_mode, float scale, int dtype, void* stream) {
+    if (int e = check_common(B, H, W, norm_mode, dtype)) return e;
+    if (dtype != JSPSR_F32) return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is implemented for fp32 tensors");
+    if (C != 64)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is instantiated for C = 64 feature channels "
+                                           "(Generator bc = 16, configs/*.yml num_feature = 32), got C = %d", C);
+    if (!init || !feature || !conv_w || !conv_b || !w9 || !b1 || !out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    if ((weight_out == nullptr) != (offset_out == nullptr))
+        return fail(JSPSR_ERR_BAD_ARG, "weight_out and offset_out must be given together");
+    if (int e = check_align(init, 4, "init")) return e;
+    if (int e = check_align(feature, 4, "feature")) return e;
+    if (int e = check_align(conv_w, 16, "conv_w")) return e;
+    if (int e = check_align(conv_b, 4, "conv_b")) return e;
+    if (int e = check_align(out, 4, "out")) return e;
+    if (int e = check_align(weight_out, 4, "weight_out")) return e;
+    if (int e = check_align(offset_out, 4, "offset_out")) return e;
+    LaunchArgs la;
+    if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 16)) return e;
+    if (la.tile_h < 8) {  // instantiated for 16 and 8 rows per CTA
+        la.tile_h = 8;
+        la.g.tiles_y = (H + 7) / 8;
+    }
+    la.init = init; la.w9 = w9; la.b1 = b1; la.out = out;
+    la.mode = norm_mode; la.scale = scale; la.bf16 = false; la.stream = (cudaStream_t)stream;
+    // the operand buffers leave room for the narrow staged tile at two CTAs per SM (JSPSR_SPN_HALO=wide overrides)
+    bool wide = false;
+    if (const char* e = getenv("JSPSR_SPN_HALO")) wide = e[0] == 'w';
+    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, false, la.tile_h, wide);
+    cudaError_t ce = (wide ? wide::launch_gen_spn_forward : narrow::launch_gen_spn_forward)(la, feature, C, conv_w, conv_b,
+                                                                                            weight_out, offset_out);
+    if (ce != cudaSuccess) return cuda_fail(ce, "gen_spn_forward launch");
     return JSPSR_OK;
 }
 

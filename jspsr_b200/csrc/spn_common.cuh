@@ -125,7 +125,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // zero either way; whether a zero row is *legitimate* (outside the image) or a
 // missing halo row is decided per tap through [r_lo, r_lo + r_span).
 // ---------------------------------------------------------------------------
-template <typename T, bool TMA, int TH>
+template <typename T, bool TMA, int TH, int NT = THREADS>
 __device__ __forceinline__ void stage_tile_begin(T* tile, uint64_t* bar, const CUtensorMap* tmap, const T* init,
                                                  const Geom& g, int b, int ox, int oy_buf) {
     constexpr int SH = staged_rows(TH);
@@ -138,7 +138,7 @@ __device__ __forceinline__ void stage_tile_begin(T* tile, uint64_t* bar, const C
         }
     } else {
         const T* src = init + (size_t)b * g.init_rows * g.W;
-        for (int i = threadIdx.x; i < SH * SW; i += THREADS) {
+        for (int i = threadIdx.x; i < SH * SW; i += NT) {
             int r = i / SW, c = i - r * SW;
             int br = oy_buf + r, gx = ox + c;
             T v = from_f32<T>(0.f);

@@ -152,6 +152,40 @@ def spn_forward_strip(init_buf, weight, offset, w, b, norm_mode, scale, H_img, r
     return out
 
 
+def gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: float = 1.0, want_weight_offset=False):
+    """Generator tail (two 1x1 convolutions, sigmoid, zero centre pair: spn.py:41-52,66-73) fused with the
+    propagation (spn.py:99-118).  conv_w [25,C] / conv_b [25]: conv_weight rows first, then conv_offset rows.
+    Returns out, or (out, weight [B,9,H,W], offset [B,18,H,W]) when `want_weight_offset`."""
+    _require_cuda(init, feature, conv_w, conv_b, w, b)
+    if init.dim() != 4 or init.shape[1] != 1:
+        raise RuntimeError(f"init must be [B,1,H,W], got {tuple(init.shape)}")
+    B, _, H, W = init.shape
+    if feature.dim() != 4 or feature.shape[0] != B or tuple(feature.shape[2:]) != (H, W):
+        raise RuntimeError(f"feature must be [B,C,H,W] with B,H,W = {(B, H, W)}, got {tuple(feature.shape)}")
+    C = feature.shape[1]
+    if tuple(conv_w.shape) != (25, C) or tuple(conv_b.shape) != (25,):
+        raise RuntimeError(f"conv_w must be [25,{C}] and conv_b [25], got {tuple(conv_w.shape)} / {tuple(conv_b.shape)}")
+    if init.dtype != torch.float32 or feature.dtype != torch.float32:
+        raise RuntimeError("gen_spn_forward is implemented for float32 tensors")
+    init, feature = init.contiguous(), feature.contiguous()
+    conv_w = conv_w.detach().to(torch.float32).contiguous()
+    conv_b = conv_b.detach().to(torch.float32).contiguous()
+    w9 = _w9(w, init)
+    b1 = b.detach().to(device=init.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(init)
+    weight = offset = None
+    if want_weight_offset:
+        weight = torch.empty(B, 9, H, W, dtype=torch.float32, device=init.device)
+        offset = torch.empty(B, 18, H, W, dtype=torch.float32, device=init.device)
+    with torch.cuda.device(init.device):
+        rc = _lib.lib().jspsr_gen_spn_forward(_ptr(init), _ptr(feature), _ptr(conv_w), _ptr(conv_b), _ptr(w9), _ptr(b1),
+                                              _ptr(out), _ptr(weight), _ptr(offset), B, C, H, W, norm_mode, float(scale),
+                                              F32, _stream_ptr(init))
+    _lib.check(rc, "jspsr_gen_spn_forward")
+    _count()
+    return (out, weight, offset) if want_weight_offset else out
+
+
 def offset_absmax(offset: torch.Tensor) -> torch.Tensor:
     """[max |row offset|, max |col offset|] as a 2-element fp32 device tensor."""
     _require_cuda(offset)
@@ -263,6 +297,45 @@ class _Propagate(torch.autograd.Function):
             gw, gb = gw.to(w.dtype).reshape(w.shape), gb.to(w.dtype)
         return (gi, gwt if ctx.needs_input_grad[1] else None, goff if ctx.needs_input_grad[2] else None,
                 gw if ctx.needs_input_grad[3] else None, gb if ctx.needs_input_grad[4] else None, None, None)
+
+
+class _GenPropagate(torch.autograd.Function):
+    """Generator tail + propagation.  Forward: one fused kernel that also materialises weight/offset when a
+    gradient is needed.  Backward: the fused propagation backward kernel, then the (tiny-N) 1x1-convolution
+    gradients as plain library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, init, feature, conv_w, conv_b, w, b, norm_mode, scale):
+        need = any(ctx.needs_input_grad)
+        if not need:
+            return gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode, scale)
+        out, weight, offset = gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode, scale, True)
+        ctx.save_for_backward(init, feature, conv_w, weight, offset, w)
+        ctx.norm_mode, ctx.scale = norm_mode, scale
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        init, feature, conv_w, weight, offset, w = ctx.saved_tensors
+        need_init = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[4] or ctx.needs_input_grad[5]
+        gi, gwt, goff, gw, gb = spn_backward(grad_out, init, weight, offset, w, ctx.norm_mode, ctx.scale,
+                                             need_grad_init=need_init, need_grad_w=need_w)
+        B, C, H, W = feature.shape
+        # pre-activation gradients [B,25,H,W]: sigmoid' for the 9 weights, the 16 non-centre offset channels
+        gz = torch.cat((gwt * weight * (1.0 - weight), goff[:, :8], goff[:, 10:]), dim=1)
+        g_conv_b = gz.sum(dim=(0, 2, 3)) if ctx.needs_input_grad[3] else None
+        g_conv_w = torch.einsum("bnhw,bchw->nc", gz, feature) if ctx.needs_input_grad[2] else None
+        g_feat = torch.einsum("bnhw,nc->bchw", gz, conv_w.to(gz.dtype)) if ctx.needs_input_grad[1] else None
+        if gw is not None:
+            gw, gb = gw.to(w.dtype).reshape(w.shape), gb.to(w.dtype)
+        return (gi if need_init else None, g_feat, g_conv_w, g_conv_b, gw if ctx.needs_input_grad[4] else None,
+                gb if ctx.needs_input_grad[5] else None, None, None)
+
+
+def gen_propagate(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: float = 1.0) -> torch.Tensor:
+    return _GenPropagate.apply(init, feature, conv_w, conv_b, w, b, norm_mode, scale)
 
 
 def _common_dtype(*tensors):
