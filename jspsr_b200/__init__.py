@@ -7,7 +7,7 @@ are drop-in replacements for models.components.spn.PostProcessor,
 models.LRRU.Post_process_deconv and models.components.nlspn.NLSPN of
 xandercai/JSPSR (same constructor, forward signature and state_dict keys).
 """
-from .modules import NLSPN, Post_process_deconv, PostProcessor  # noqa: F401
+from .modules import NLSPN, Post_process_deconv, PostProcessor, generator_postprocess  # noqa: F401
 from . import functional  # noqa: F401
 
 __version__ = "1.0"

@@ -50,6 +50,31 @@ class PostProcessor(nn.Module):
         return F.propagate(init_dem, weight, offset, self.w, self.b, mode, float(self.scale))
 
 
+def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, context, init_dem=None):
+    """The two lines `weight, offset = self.generator(dem, context)` and
+    `out = self.postprocessor(dem.detach(), weight, offset)` of models/JSPSR.py:371-375 (models/EDSR.py:133-134)
+    with the Generator's last two layers fused into the propagation kernel.
+
+    `generator` is the reference's own models.components.spn.Generator (or any module with the same
+    sub-modules: convd1, convd2, convf1, convf2, conv, block, conv_weight, conv_offset); its body up to `block`
+    (spn.py:57-65: cuDNN convolutions, not on the hot path) runs as is, its parameters stay where they are, so
+    checkpoints and optimizer groups are unchanged.  `postprocessor` is a PostProcessor (either implementation).
+    The weight/offset tensors never exist in inference; with autograd they are written once by the fused kernel
+    and consumed by the fused backward."""
+    d2 = generator.convd2(generator.convd1(dem))
+    f2 = generator.convf2(generator.convf1(context))
+    feature = generator.block(generator.conv(torch.cat((d2, f2), dim=1)))
+    cw, co = generator.conv_weight[0], generator.conv_offset.conv[0]
+    if generator.kernel_size != 3 or cw.kernel_size != (1, 1) or co.kernel_size != (1, 1):
+        raise NotImplementedError("generator_postprocess needs the reference's 3x3 window and 1x1 output convolutions")
+    conv_w = torch.cat((cw.weight.flatten(1), co.weight.flatten(1)), dim=0)
+    conv_b = torch.cat((cw.bias, co.bias))
+    mode = NORM_RESIDUAL if postprocessor.residual else NORM_SUM
+    init = dem.detach() if init_dem is None else init_dem
+    return F.gen_propagate(init, feature, conv_w, conv_b, postprocessor.w, postprocessor.b, mode,
+                           float(postprocessor.scale))
+
+
 class Post_process_deconv(nn.Module, ABC):
     """models/LRRU.py:250-298 (`args` needs .kernel_size and .dkn_residual)."""
 

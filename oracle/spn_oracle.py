@@ -12,6 +12,9 @@ What it follows (reference tree = xandercai/JSPSR, paths relative to it):
   deform_conv2d -> + scale*init)
 * ``models/LRRU.py:267-298``           Post_process_deconv.forward (same, no scale)
 * ``models/components/nlspn.py:77-235`` NLSPN affinity front-end + T-step loop
+* ``models/components/spn.py:41-52,66-73`` Generator tail (the two 1x1 convolutions that
+  produce weight and offset, sigmoid, zero centre pair) - pinned by
+  ``tests/golden/make_golden_generator.py``'s fixtures (gen_*.npz)
 * the arithmetic itself lives in a THIRD-PARTY dependency that is not vendored
   in the reference: ``torchvision.ops.deform_conv2d`` (DCNv2, modulated).
   Reference pin: torchvision 0.16 / torch 2.1.0 (``ReadMe.md:9-19``,
@@ -210,6 +213,42 @@ def postprocessor_backward(grad_out, init, weight, offset, w9, mode=NORM_RESIDUA
 # --------------------------------------------------------------------------
 # a7: NLSPN affinity front-end (nlspn.py:77-175), after the 3x3 conv
 # --------------------------------------------------------------------------
+# ---------------------------------------------------------------------------
+# Generator tail (models/components/spn.py:41-52, 66-73): the last two layers of
+# Generator.forward, applied to `feature` = the output of Generator.block (spn.py:65)
+# ---------------------------------------------------------------------------
+def generator_tail(feature, conv_weight_w, conv_weight_b, conv_offset_w, conv_offset_b):
+    """weight = sigmoid(conv1x1(feature)) [B,9,H,W] (spn.py:41-44,66);
+    offset = conv1x1(feature) [B,16,H,W] viewed as 8 (dy,dx) pairs with a zero pair inserted at index 4
+    (spn.py:45-52,67-73) -> [B,18,H,W]."""
+    dt = feature.dtype
+    B, C, H, W = feature.shape
+    cw = conv_weight_w.reshape(K, C).astype(dt)
+    co = conv_offset_w.reshape(2 * (K - 1), C).astype(dt)
+    zw = np.einsum("nc,bchw->bnhw", cw, feature) + conv_weight_b.astype(dt).reshape(1, -1, 1, 1)
+    zo = np.einsum("nc,bchw->bnhw", co, feature) + conv_offset_b.astype(dt).reshape(1, -1, 1, 1)
+    weight = (1.0 / (1.0 + np.exp(-zw))).astype(dt)
+    offset = np.concatenate((zo[:, :K - 1], np.zeros((B, 2, H, W), dtype=dt), zo[:, K - 1:]), axis=1)
+    return weight, offset
+
+
+def generator_tail_backward(grad_weight, grad_offset, feature, weight, conv_weight_w, conv_offset_w):
+    """Autograd of generator_tail: gradients w.r.t. feature and the four convolution parameters."""
+    dt = feature.dtype
+    B, C, H, W = feature.shape
+    cw = conv_weight_w.reshape(K, C).astype(dt)
+    co = conv_offset_w.reshape(2 * (K - 1), C).astype(dt)
+    gzw = grad_weight * weight * (1.0 - weight)
+    gzo = np.concatenate((grad_offset[:, :K - 1], grad_offset[:, K + 1:]), axis=1)  # the centre pair has no source
+    return dict(
+        grad_feature=np.einsum("bnhw,nc->bchw", gzw, cw) + np.einsum("bnhw,nc->bchw", gzo, co),
+        grad_conv_weight_w=np.einsum("bnhw,bchw->nc", gzw, feature).reshape(conv_weight_w.shape),
+        grad_conv_weight_b=gzw.sum(axis=(0, 2, 3)),
+        grad_conv_offset_w=np.einsum("bnhw,bchw->nc", gzo, feature).reshape(conv_offset_w.shape),
+        grad_conv_offset_b=gzo.sum(axis=(0, 2, 3)),
+    )
+
+
 def nlspn_offset_affinity(offset_aff, confidence, aff_scale_const, affinity="TGASS",
                           conf_prop=True, legacy=False):
     """offset_aff [B,24,H,W] = output of conv_offset_aff (nlspn.py:81).

@@ -30,7 +30,7 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 12, names
+    assert len(names) == 13, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in include/jspsr_spn.h but not exported"
@@ -54,6 +54,10 @@ def test_argument_validation_needs_no_gpu(lib):
         (lambda: h.jspsr_spn_forward(None, one, one, one, one, one, 1, 8, 8, 1, 1.0, 0, None), -1, "null"),
         (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 1 << 25, 8, 1, 1.0, 0, None), -2, "2^24"),
         (lambda: h.jspsr_spn_forward(ctypes.c_void_p(18), one, one, one, one, one, 1, 8, 8, 1, 1.0, 0, None), -4, "aligned"),
+        (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, None, None, 1, 32, 8, 8, 1, 1.0, 0, None), -2, "C = 64"),
+        (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 1, None), -2, "fp32"),
+        (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, one, None, 1, 64, 8, 8, 1, 1.0, 0, None), -1, "together"),
+        (lambda: h.jspsr_gen_spn_forward(one, one, ctypes.c_void_p(20), one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 0, None), -4, "conv_w"),
         (lambda: h.jspsr_spn_iterate(one, one, one, None, None, one, None, 1, 8, 8, 0, 0, None), -1, "T="),
         (lambda: h.jspsr_spn_iterate(one, one, one, one, None, one, None, 1, 8, 8, 2, 0, None), -1, "together"),
         (lambda: h.jspsr_spn_forward_strip(one, one, one, one, one, one, 1, 8, 8, 4, 0, 0, 4, 1, 1.0, 0, None, None), -1,

@@ -11,6 +11,7 @@ from oracle import spn_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PP = sorted(glob.glob(os.path.join(GOLDEN, "pp_*.npz")) + glob.glob(os.path.join(GOLDEN, "lrru_*.npz")))
 NL = sorted(glob.glob(os.path.join(GOLDEN, "nlspn_*.npz")))
+GEN = sorted(glob.glob(os.path.join(GOLDEN, "gen_*.npz")))
 
 
 def _close(a, b, rtol, atol, what):
@@ -22,7 +23,36 @@ def _close(a, b, rtol, atol, what):
 
 
 def test_fixtures_present():
-    assert len(PP) == 10 and len(NL) == 5
+    assert len(PP) == 10 and len(NL) == 5 and len(GEN) == 3
+
+
+@pytest.mark.parametrize("path", GEN, ids=[os.path.basename(p)[:-4] for p in GEN])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_generator_tail_matches_reference(path, prec):
+    """Generator.conv_weight / conv_offset / zero-centre insert + PostProcessor, forward and all gradients,
+    against the reference's own Generator run (tests/golden/make_golden_generator.py)."""
+    z = np.load(path)
+    dt = np.float64 if prec == "f64" else np.float32
+    rtol, atol = (1e-11, 1e-11) if prec == "f64" else (1e-5, 4e-6)
+    feature = z["in_feature"].astype(dt)
+    cww, cwb, cow, cob = (z["in_" + k].astype(dt) for k in ("conv_weight_w", "conv_weight_b", "conv_offset_w", "conv_offset_b"))
+    weight, offset = O.generator_tail(feature, cww, cwb, cow, cob)
+    _close(weight, z[prec + "_weight"], rtol, atol, "weight")
+    _close(offset, z[prec + "_offset"], rtol, atol, "offset")
+    assert (offset[:, 8:10] == 0).all()
+    init, gout = z["in_init"].astype(dt), z["in_grad_out"].astype(dt)
+    w9, b1 = z["in_w"].astype(dt).reshape(9), z["in_b"].astype(dt)[0]
+    mode, scale = int(z["norm_mode"]), float(z["scale"])
+    # the propagation consumes the reference's own weight/offset here so that the two stages are pinned separately
+    wr, orf = z[prec + "_weight"].astype(dt), z[prec + "_offset"].astype(dt)
+    _close(O.postprocessor_forward(init, wr, orf, w9, b1, mode, scale), z[prec + "_out"], rtol, atol, "out")
+    g = O.postprocessor_backward(gout, init, wr, orf, w9, mode, scale)
+    gt = O.generator_tail_backward(g["grad_weight"], g["grad_offset"], feature, wr, cww, cow)
+    for k, v in gt.items():
+        ref = z[f"{prec}_{k}"]
+        sk = max(1.0, float(np.abs(ref).max()))
+        loose = 1 if prec == "f64" and k != "grad_feature" else 50   # f64 grad_feature is stored as float32
+        _close(v, ref, max(rtol, 1e-6 if k == "grad_feature" else rtol), atol * sk * loose, k)
 
 
 @pytest.mark.parametrize("path", PP, ids=[os.path.basename(p)[:-4] for p in PP])
