@@ -8,14 +8,13 @@
 //
 // The two 1x1 convolutions are one [128 pixels x C] x [C x 25] contraction per image row segment: it runs on
 // the 5th-generation tensor cores (tcgen05.mma, kind::tf32, M = 128, N = 32, K = 8; accumulator in TMEM).
-// A thread owns one pixel column of the tile: it loads its pixel's C features (each load instruction is one
-// coalesced 128-byte line per warp), splits them into tf32 hi + lo parts, stores them into shared memory in
-// the canonical K-major no-swizzle operand layout (core matrix = 8 pixels x 16 bytes), one elected thread
-// issues the MMAs, and after the commit every thread reads ITS pixel's 25 results back from its TMEM lane
-// (tcgen05.ld 32x32b) - exactly the registers the 9-tap gather needs.  fp32 accuracy comes from the 3-product
+// A producer thread owns one pixel column of the tile: it loads its pixel's C features (each load instruction
+// is one coalesced 128-byte line per warp), splits them into tf32 hi + lo parts and stores them into shared
+// memory in the canonical K-major no-swizzle operand layout (core matrix = 8 pixels x 16 bytes); one elected
+// thread issues the MMAs; after the commit the consumer thread of the same pixel reads ITS 25 results back
+// from its TMEM lane (tcgen05.ld 32x32b) - exactly the registers the 9-tap gather needs.  fp32 accuracy comes from the 3-product
 // split  A_hi*B_hi + A_lo*B_hi + A_hi*B_mid  (hi parts rounded to nearest tf32, so the dropped terms are
 // <= 2^-23 relative; measured with tools/umma_probe.cu).
-// The next row's features are requested before the current row's taps, so HBM latency hides behind the gather.
 #include <cstdlib>
 
 #include "spn_kernels.cuh"
@@ -26,6 +25,7 @@ inline namespace JSPSR_VARIANT {
 constexpr int GEN_THREADS = 128;  // one thread per pixel of a 128-pixel row segment = one TMEM lane each
 constexpr int GEN_N = 32;         // MMA N: 9 weight + 16 offset rows, padded
 constexpr int GEN_NOUT = 25;
+constexpr int GEN_CTA_THREADS = 2 * GEN_THREADS + 32;  // consumers + producers + the MMA warp
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     // shared-memory matrix descriptor, SWIZZLE_NONE, K-major: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
@@ -57,12 +57,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when all MMAs issued so far are complete
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // C: feature channels (bc * 4 of the Generator: 64 for JSPSR's num_feature = 32, 128 for cat_only / EDSR).
 // TH: rows per CTA.  WRITE_WO: also store weight [B,9,H,W] and offset [B,18,H,W] (what the backward needs).
 // CS: compile-time channel stride H*W (0 = runtime): the C feature loads of a pixel then share one address
 // register with immediate offsets.
+//
+// Warp-specialised: 288 threads = 4 consumer warps + 4 producer warps (one thread per pixel column each) + 1 MMA warp.
+//   producers (warps 4-7): stream the row's features from HBM, split to tf32 hi/lo, store the A operand;
+//   MMA warp  (warp 8)   : one lane issues the row's 24 MMAs into accumulator (row & 1) and commits;
+//   consumers (warps 0-3): read their pixel's 25 results from their TMEM lane, release the accumulator, run the
+//                          Generator epilogue and the 9-tap gather, store the output.
+// mbarriers: a_full (128 producers have stored the row's operand), a_free (its MMAs have finished reading it),
+// acc_full[2] (accumulator complete), acc_empty[2] (all 128 consumers have read it).
+// Measured steps (2048 tiles): every thread doing all jobs in turn, 8 warps per SM: 3.4 ms (latency-bound, 35 %
+// issue rate); producers + consumers with a producer lane issuing the MMAs: 2.9 ms (the ~300 uniform-datapath
+// instructions of the issue sat on the producers' critical path, ahead of their next loads).
 template <int C, bool TMA, int TH, bool WRITE_WO, int CS>
-__global__ void __launch_bounds__(GEN_THREADS)
+__global__ void __launch_bounds__(GEN_CTA_THREADS, 2)
 gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__ feature,
                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                        const float* __restrict__ w9, const float* __restrict__ b1, float* __restrict__ out,
@@ -79,18 +97,23 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
     unsigned char* b_hi = a_lo + A_BYTES;
     unsigned char* b_mid = b_hi + B_BYTES;
     float* tile = reinterpret_cast<float*>(b_mid + B_BYTES);  // [SH][SW], 128-byte aligned (all sizes are multiples of 128)
-    __shared__ __align__(8) uint64_t bar_tile, bar_mma;
+    __shared__ __align__(8) uint64_t bar_tile, bar_a_full, bar_a_free, bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_w[10], s_bias[GEN_N];
 
     const int t = threadIdx.x, warp = t >> 5;
     const TileCtx c = make_tile_ctx<TH>(g);
-    stage_tile_begin<float, TMA, TH, GEN_THREADS>(tile, &bar_tile, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
+    stage_tile_begin<float, TMA, TH, GEN_CTA_THREADS>(tile, &bar_tile, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     if (t < 9) s_w[t] = w9 ? w9[t] : 1.f;
     if (t == 9) s_w[9] = b1 ? b1[0] : 0.f;
     if (t < GEN_N) s_bias[t] = t < GEN_NOUT ? conv_b[t] : 0.f;
     if (t == 32) {
-        mbar_init(&bar_mma, 1);
+        mbar_init(&bar_a_full, GEN_THREADS);
+        mbar_init(&bar_a_free, 1);
+        mbar_init(&bar_acc_full[0], 1);
+        mbar_init(&bar_acc_full[1], 1);
+        mbar_init(&bar_acc_empty[0], GEN_THREADS);
+        mbar_init(&bar_acc_empty[1], GEN_THREADS);
         fence_mbar_init();
     }
     if (warp == 0) {  // 64 TMEM columns: two [128 x 32] fp32 accumulators (rows alternate)
@@ -99,7 +122,7 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // B operand: row n = output channel (9 weight rows, 16 offset rows, 7 zero rows), K-major, split hi + mid
-    for (int i = t; i < GEN_N * (C / 4); i += GEN_THREADS) {
+    for (int i = t; i < GEN_N * (C / 4); i += GEN_CTA_THREADS) {
         const int n = i % GEN_N, kc = i / GEN_N;
         float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), mid = hi;
         if (n < GEN_NOUT) {
@@ -111,150 +134,154 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         *reinterpret_cast<float4*>(b_hi + off) = hi;
         *reinterpret_cast<float4*>(b_mid + off) = mid;
     }
+    fence_proxy_async();  // B operand: generic-proxy stores -> visible to the tensor core's async proxy
 
     const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
-    const int x = c.x0 + t;
+    const int px = t & (GEN_THREADS - 1);  // pixel column of this thread inside the tile (both roles)
+    const int x = c.x0 + px;
     const bool col_ok = x < g.W;
-    const float* feat_b = feature + (size_t)c.b * C * cs;
-    const float* init_b = init + (size_t)c.b * g.init_rows * g.W;
-    float* out_b = out + (size_t)c.b * cs;
-    const float* tile_lo = tile + c.r_lo * SW;
-    const uint32_t a_off = (t / 8) * SBO + (t % 8) * 16;  // this pixel's row inside every K chunk
     // instruction descriptor: D fp32 | A, B tf32 | both K-major | N = 32 | M = 128
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((GEN_N >> 3) << 17) | ((GEN_THREADS >> 4) << 24);
 
-    // This pixel's features of the next row to contract: requested right after the previous row's MMAs were
-    // issued, in flight while that row's taps run.  (A second register set, two rows ahead, was measured slower:
-    // 3.63 vs 3.33 ms - the duplicated loop body thrashes the instruction cache.)
-    float f0[C];
-    uint32_t tmem = 0;  // TMEM base address, read once the allocation is published
-    auto load_row = [&](int r, float (&f)[C]) {
-        const int y = c.y0 + r;
-        if (r < TH && col_ok && y < g.H) {
-            const float* p = feat_b + (size_t)y * g.W + x;
-#pragma unroll
-            for (int k = 0; k < C; ++k) f[k] = ld_stream(p + (size_t)k * cs);
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; ++k) f[k] = 0.f;
-        }
-    };
-    // A operand of one row: hi / lo parts, 16 bytes (4 channels) per store; then the MMAs into accumulator r & 1
-    auto stage_and_issue = [&](int r, const float (&f)[C]) {
-#pragma unroll
-        for (int kc = 0; kc < C / 4; ++kc) {
-            float4 hi = make_float4(tf32_rn(f[4 * kc]), tf32_rn(f[4 * kc + 1]), tf32_rn(f[4 * kc + 2]), tf32_rn(f[4 * kc + 3]));
-            float4 lo = make_float4(f[4 * kc] - hi.x, f[4 * kc + 1] - hi.y, f[4 * kc + 2] - hi.z, f[4 * kc + 3] - hi.w);
-            *reinterpret_cast<float4*>(a_hi + kc * LBO_A + a_off) = hi;
-            *reinterpret_cast<float4*>(a_lo + kc * LBO_A + a_off) = lo;
-        }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // orders earlier tcgen05.ld before the new MMAs
-        __syncthreads();
-        if (t == 0) {
+    if (warp == 8) {
+        // =========================== MMA warp ===========================
+        __syncthreads();  // setup complete (TMEM address, barriers, B operand)
+        const uint32_t tmem = s_tmem;
+#pragma unroll 1
+        for (int r = 0; r < TH; ++r) {
+            mbar_wait(&bar_a_full, (uint32_t)(r & 1));                                      // operand of row r is in place
+            if (r >= 2) mbar_wait(&bar_acc_empty[r & 1], (uint32_t)(((r >> 1) - 1) & 1));  // consumers drained row r-2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d_tmem = tmem + (uint32_t)(r & 1) * GEN_N;
+            if ((t & 31) == 0) {
+                const uint32_t d_tmem = tmem + (uint32_t)(r & 1) * GEN_N;
 #pragma unroll
-            for (int ks = 0; ks < C / 8; ++ks) {  // K = 8 tf32 per MMA = two 16-byte chunks
-                const uint64_t dah = umma_desc_kmajor(smem_u32(a_hi) + ks * 2 * LBO_A, LBO_A, SBO);
-                const uint64_t dal = umma_desc_kmajor(smem_u32(a_lo) + ks * 2 * LBO_A, LBO_A, SBO);
-                const uint64_t dbh = umma_desc_kmajor(smem_u32(b_hi) + ks * 2 * LBO_B, LBO_B, SBO);
-                const uint64_t dbm = umma_desc_kmajor(smem_u32(b_mid) + ks * 2 * LBO_B, LBO_B, SBO);
-                umma_tf32(d_tmem, dah, dbh, IDESC, ks > 0 ? 1u : 0u);
-                umma_tf32(d_tmem, dal, dbh, IDESC, 1u);
-                umma_tf32(d_tmem, dah, dbm, IDESC, 1u);
+                for (int ks = 0; ks < C / 8; ++ks) {  // K = 8 tf32 per MMA = two 16-byte chunks
+                    const uint64_t dah = umma_desc_kmajor(smem_u32(a_hi) + ks * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dal = umma_desc_kmajor(smem_u32(a_lo) + ks * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dbh = umma_desc_kmajor(smem_u32(b_hi) + ks * 2 * LBO_B, LBO_B, SBO);
+                    const uint64_t dbm = umma_desc_kmajor(smem_u32(b_mid) + ks * 2 * LBO_B, LBO_B, SBO);
+                    umma_tf32(d_tmem, dah, dbh, IDESC, ks > 0 ? 1u : 0u);
+                    umma_tf32(d_tmem, dal, dbh, IDESC, 1u);
+                    umma_tf32(d_tmem, dah, dbm, IDESC, 1u);
+                }
+                umma_commit(&bar_a_free);
+                umma_commit(&bar_acc_full[r & 1]);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma))
-                         : "memory");
+            __syncwarp();
         }
-    };
-    // Generator epilogue + propagation of row r (its accumulator must be complete)
-    auto finish_row = [&](int r) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r & 1) * GEN_N, v);
-        const int ry = r, y = c.y0 + r;
-        if (!col_ok || y >= g.H) return;
-        const size_t p = (size_t)y * g.W + x;
-        float a[9], oh[9], ow[9];
+    } else if (warp >= 4) {
+        // =========================== producers ===========================
+        const float* feat_b = feature + (size_t)c.b * C * cs;
+        const uint32_t a_off = (px / 8) * SBO + (px % 8) * 16;  // this pixel's row inside every K chunk
+        float f[C];
+        auto load_row = [&](int r) {
+            const int y = c.y0 + r;
+            if (r < TH && col_ok && y < g.H) {
+                const float* p = feat_b + (size_t)y * g.W + x;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float z = v[k] + s_bias[k];
-            a[k] = __frcp_rn(1.f + expf(-z));  // correctly rounded reciprocal == 1 / (1 + e)
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k == 4) {
-                oh[k] = ow[k] = 0.f;  // zero centre pair (spn.py:69-73)
+                for (int k = 0; k < C; ++k) f[k] = ld_stream(p + (size_t)k * cs);
             } else {
-                const int n = k < 4 ? k : k - 1;
-                oh[k] = v[9 + 2 * n] + s_bias[9 + 2 * n];
-                ow[k] = v[10 + 2 * n] + s_bias[10 + 2 * n];
+#pragma unroll
+                for (int k = 0; k < C; ++k) f[k] = 0.f;
             }
+        };
+        load_row(0);
+        __syncthreads();  // setup complete (TMEM address, barriers, B operand)
+        const uint32_t tmem = s_tmem;
+#pragma unroll 1
+        for (int r = 0; r < TH; ++r) {
+            if (r > 0) mbar_wait(&bar_a_free, (uint32_t)((r - 1) & 1));  // MMA(r-1) no longer reads the A buffers
+#pragma unroll
+            for (int kc = 0; kc < C / 4; ++kc) {  // hi / lo parts, 16 bytes (4 channels) per store
+                float4 hi = make_float4(tf32_rn(f[4 * kc]), tf32_rn(f[4 * kc + 1]), tf32_rn(f[4 * kc + 2]), tf32_rn(f[4 * kc + 3]));
+                float4 lo = make_float4(f[4 * kc] - hi.x, f[4 * kc + 1] - hi.y, f[4 * kc + 2] - hi.z, f[4 * kc + 3] - hi.w);
+                *reinterpret_cast<float4*>(a_hi + kc * LBO_A + a_off) = hi;
+                *reinterpret_cast<float4*>(a_lo + kc * LBO_A + a_off) = lo;
+            }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            mbar_arrive(&bar_a_full);
+            load_row(r + 1);  // in flight while the MMAs run and the consumers gather
         }
-        if (WRITE_WO) {
-            float* pw = weight_out + (size_t)c.b * 9 * cs + p;
-            float* po = offset_out + (size_t)c.b * 18 * cs + p;
+    } else {
+        // =========================== consumers ===========================
+        const float* init_b = init + (size_t)c.b * g.init_rows * g.W;
+        float* out_b = out + (size_t)c.b * cs;
+        const float* tile_lo = tile + c.r_lo * SW;
+        stage_tile_wait<TMA>(&bar_tile);  // __syncthreads (pairs with the producers') + the DEM box has landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem = s_tmem;
+#pragma unroll 1
+        for (int r = 0; r < TH; ++r) {
+            mbar_wait(&bar_acc_full[r & 1], (uint32_t)((r >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r & 1) * GEN_N, v);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&bar_acc_empty[r & 1]);
+
+            const int y = c.y0 + r;
+            if (!col_ok || y >= g.H) continue;
+            const size_t p = (size_t)y * g.W + x;
+            float a[9], oh[9], ow[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                st_stream(pw + (size_t)k * cs, a[k]);
-                st_stream(po + (size_t)(2 * k) * cs, oh[k]);
-                st_stream(po + (size_t)(2 * k + 1) * cs, ow[k]);
+                const float z = v[k] + s_bias[k];
+                a[k] = __frcp_rn(1.f + expf(-z));  // correctly rounded reciprocal == 1 / (1 + e)
             }
-        }
-        // propagation: identical to spn_forward_kernel's pixel body
-        normalise9(a, mode);
-        const float fy = (float)(g.row0 + y), fx = (float)x;
-        const float hk[3] = {fy - 1.f, fy, fy + 1.f};
-        const float wk[3] = {fx - 1.f, fx, fx + 1.f};
-        unsigned slow = 0u;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const FastTap tp = fast_tap<float>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
-            const float val = bilerp(tp.v1, tp.v2, tp.v3, tp.v4, tp.lh, tp.lw);
-            a[k] = tp.ok ? (s_w[k] * a[k]) * val : a[k];
-            slow |= tp.ok ? 0u : (1u << k);
-        }
-        if (slow) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                if (slow & (1u << k)) {
-                    const SlowTap tp = slow_tap<float>(init_b, g, hk[k / 3] + oh[k], wk[k % 3] + ow[k], nullptr);
-                    a[k] = (s_w[k] * a[k]) * bilerp(tp.v1, tp.v2, tp.v3, tp.v4, tp.lh, tp.lw);
+                if (k == 4) {
+                    oh[k] = ow[k] = 0.f;  // zero centre pair (spn.py:69-73)
+                } else {
+                    const int n = k < 4 ? k : k - 1;
+                    oh[k] = v[9 + 2 * n] + s_bias[9 + 2 * n];
+                    ow[k] = v[10 + 2 * n] + s_bias[10 + 2 * n];
                 }
             }
-        }
-        float acc = a[0];
+            if (WRITE_WO) {
+                float* pw = weight_out + (size_t)c.b * 9 * cs + p;
+                float* po = offset_out + (size_t)c.b * 18 * cs + p;
 #pragma unroll
-        for (int k = 1; k < 9; ++k) acc += a[k];
-        acc += s_w[9];
-        if (mode == NORM_RESIDUAL) acc = fmaf(scale, tile[(ry + HALO_T) * SW + (t + HALO_L)], acc);
-        st_stream(out_b + p, acc);
-    };
-
-    load_row(0, f0);
-    stage_tile_wait<TMA>(&bar_tile);  // also publishes s_tmem, the barriers, s_w / s_bias and the B operand (generic proxy)
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tmem = s_tmem;
-
-    // Row pipeline.  Step r: wait for MMA(r-1) (frees the A buffers, completes accumulator (r-1) & 1) -> stage
-    // A(r), issue MMA(r) into accumulator r & 1 -> request row r+1 -> finish row r-1 while MMA(r) runs.
-    // One mbarrier suffices: commits and waits strictly alternate.
-#pragma unroll 1
-    for (int r = 0; r <= TH; ++r) {
-        if (r > 0) {
-            mbar_wait(&bar_mma, (uint32_t)((r - 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int k = 0; k < 9; ++k) {
+                    st_stream(pw + (size_t)k * cs, a[k]);
+                    st_stream(po + (size_t)(2 * k) * cs, oh[k]);
+                    st_stream(po + (size_t)(2 * k + 1) * cs, ow[k]);
+                }
+            }
+            // propagation: identical to spn_forward_kernel's pixel body
+            normalise9(a, mode);
+            const float fy = (float)(g.row0 + y), fx = (float)x;
+            const float hk[3] = {fy - 1.f, fy, fy + 1.f};
+            const float wk[3] = {fx - 1.f, fx, fx + 1.f};
+            unsigned slow = 0u;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const FastTap tp = fast_tap<float>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+                const float val = bilerp(tp.v1, tp.v2, tp.v3, tp.v4, tp.lh, tp.lw);
+                a[k] = tp.ok ? (s_w[k] * a[k]) * val : a[k];
+                slow |= tp.ok ? 0u : (1u << k);
+            }
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (slow & (1u << k)) {
+                        const SlowTap tp = slow_tap<float>(init_b, g, hk[k / 3] + oh[k], wk[k % 3] + ow[k], nullptr);
+                        a[k] = (s_w[k] * a[k]) * bilerp(tp.v1, tp.v2, tp.v3, tp.v4, tp.lh, tp.lw);
+                    }
+                }
+            }
+            float acc = a[0];
+#pragma unroll
+            for (int k = 1; k < 9; ++k) acc += a[k];
+            acc += s_w[9];
+            if (mode == NORM_RESIDUAL) acc = fmaf(scale, tile[(r + HALO_T) * SW + (px + HALO_L)], acc);
+            st_stream(out_b + p, acc);
         }
-        if (r < TH) {
-            stage_and_issue(r, f0);
-            load_row(r + 1, f0);
-        }
-        if (r > 0) finish_row(r - 1);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(64));
 }
 
 template <int C, bool TMA, int TH, bool WO, int CS>
@@ -265,7 +292,7 @@ static cudaError_t launch_gen_one(const LaunchArgs& la, const float* feature, co
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    gen_spn_forward_kernel<C, TMA, TH, WO, CS><<<grid, GEN_THREADS, dyn, la.stream>>>(
+    gen_spn_forward_kernel<C, TMA, TH, WO, CS><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>(
         (const float*)la.init, feature, conv_w, conv_b, la.w9, la.b1, (float*)la.out, weight_out, offset_out, la.g, la.mode,
         la.scale, la.tmap);
     return cudaGetLastError();
