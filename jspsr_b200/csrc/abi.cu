@@ -28,8 +28,8 @@ cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const 
                                       void* grad_conv_out, float* grad_confidence, float* grad_scale, void* workspace,  \
                                       const Geom& g, int tile_h, bool use_tma, const CUtensorMap& tmap, int affinity,   \
                                       int legacy, bool bf16, bool forward, cudaStream_t stream);                        \
-    cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const void* feature, int C, const float* conv_w,           \
-                                       const float* conv_b, void* weight_out, void* offset_out);                        \
+    cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature, int C,  \
+                                       const float* conv_w, const float* conv_b, void* weight_out, void* offset_out);   \
     }
 JSPSR_DECLARE_VARIANT(narrow)
 JSPSR_DECLARE_VARIANT(wide)
@@ -105,6 +105,21 @@ static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, 
                      const_cast<void*>(init), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// TMA descriptor for the feature tensor viewed as [B*C planes][H][W]; box = one 128-pixel row segment of C planes
+static bool make_feature_tmap(CUtensorMap* map, const void* feature, int B, int C, int H, int W) {
+    if (tma_disabled_by_env()) return false;
+    if (((uintptr_t)feature & 15) != 0 || ((size_t)W * 4) % 16 != 0 || C > 256) return false;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * C};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * 4 * (cuuint64_t)H};
+    cuuint32_t box[3] = {(cuuint32_t)TILE_W, 1u, (cuuint32_t)C};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(feature), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int check_common(int B, int H, int W, int norm_mode, int dtype) {
@@ -256,9 +271,11 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
     // the operand buffers leave room for the narrow staged tile at two CTAs per SM (JSPSR_SPN_HALO=wide overrides)
     bool wide = false;
     if (const char* e = getenv("JSPSR_SPN_HALO")) wide = e[0] == 'w';
-    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, false, la.tile_h, wide);
-    cudaError_t ce = (wide ? wide::launch_gen_spn_forward : narrow::launch_gen_spn_forward)(la, feature, C, conv_w, conv_b,
-                                                                                            weight_out, offset_out);
+    CUtensorMap tmap_feat{};
+    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, false, la.tile_h, wide) &&
+                 make_feature_tmap(&tmap_feat, feature, B, C, H, W);
+    cudaError_t ce = (wide ? wide::launch_gen_spn_forward : narrow::launch_gen_spn_forward)(la, tmap_feat, feature, C, conv_w,
+                                                                                            conv_b, weight_out, offset_out);
     if (ce != cudaSuccess) return cuda_fail(ce, "gen_spn_forward launch");
     return JSPSR_OK;
 }

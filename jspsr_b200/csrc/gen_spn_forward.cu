@@ -8,11 +8,12 @@
 //
 // The two 1x1 convolutions are one [128 pixels x C] x [C x 25] contraction per image row segment: it runs on
 // the 5th-generation tensor cores (tcgen05.mma, kind::tf32, M = 128, N = 32, K = 8; accumulator in TMEM).
-// A producer thread owns one pixel column of the tile: it loads its pixel's C features (each load instruction
-// is one coalesced 128-byte line per warp), splits them into tf32 hi + lo parts and stores them into shared
-// memory in the canonical K-major no-swizzle operand layout (core matrix = 8 pixels x 16 bytes); one elected
-// thread issues the MMAs; after the commit the consumer thread of the same pixel reads ITS 25 results back
-// from its TMEM lane (tcgen05.ld 32x32b) - exactly the registers the 9-tap gather needs.  fp32 accuracy comes from the 3-product
+// Feature rows ([C planes] x [128 pixels]) arrive by TMA in a shared-memory ring; a producer thread owns one
+// pixel column: it reads its pixel's C features from the ring, splits them into tf32 hi + lo parts and writes
+// them into ITS lane of tensor memory (tcgen05.st) - the A operand is read by the MMAs straight from TMEM;
+// the B operand (the 25 x C weights, hi + mid parts) sits in shared memory in the canonical K-major
+// no-swizzle layout; after the commit the consumer thread of the same pixel reads ITS 25 results back from
+// its TMEM lane (tcgen05.ld 32x32b) - exactly the registers the 9-tap gather needs.  fp32 accuracy comes from the 3-product
 // split  A_hi*B_hi + A_lo*B_hi + A_hi*B_mid  (hi parts rounded to nearest tf32, so the dropped terms are
 // <= 2^-23 relative; measured with tools/umma_probe.cu).
 #include <cstdlib>
@@ -25,7 +26,7 @@ inline namespace JSPSR_VARIANT {
 constexpr int GEN_THREADS = 128;  // one thread per pixel of a 128-pixel row segment = one TMEM lane each
 constexpr int GEN_N = 32;         // MMA N: 9 weight + 16 offset rows, padded
 constexpr int GEN_NOUT = 25;
-constexpr int GEN_CTA_THREADS = 2 * GEN_THREADS + 32;  // consumers + producers + the MMA warp
+constexpr int GEN_CTA_THREADS = 2 * GEN_THREADS + 64;  // consumers + producers + the MMA warp + the TMA warp
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     // shared-memory matrix descriptor, SWIZZLE_NONE, K-major: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
@@ -63,41 +64,68 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when all MMAs issued so far are complete
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// A operand from tensor memory (lane = row of A = pixel, one tf32 per column), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
+constexpr int GEN_STAGES = 2;  // feature rows in flight per CTA (32 KB each at C = 64)
 
 // C: feature channels (bc * 4 of the Generator: 64 for JSPSR's num_feature = 32, 128 for cat_only / EDSR).
+// TMA: the DEM box AND the feature rows arrive by TMA (needs 16-byte aligned rows); otherwise bounds-checked loads.
 // TH: rows per CTA.  WRITE_WO: also store weight [B,9,H,W] and offset [B,18,H,W] (what the backward needs).
-// CS: compile-time channel stride H*W (0 = runtime): the C feature loads of a pixel then share one address
-// register with immediate offsets.
 //
-// Warp-specialised: 288 threads = 4 consumer warps + 4 producer warps (one thread per pixel column each) + 1 MMA warp.
-//   producers (warps 4-7): stream the row's features from HBM, split to tf32 hi/lo, store the A operand;
-//   MMA warp  (warp 8)   : one lane issues the row's 24 MMAs into accumulator (row & 1) and commits;
+// Warp-specialised, 320 threads:
+//   TMA warp  (warp 9)   : one lane keeps GEN_STAGES feature rows ([C][128] boxes) in flight into a shared-memory ring;
+//   producers (warps 4-7): one thread per pixel column: read the pixel's C features from the ring (conflict-free),
+//                          split them to tf32 hi / lo and write them into ITS TMEM lane (tcgen05.st) - the A operand
+//                          never touches shared memory;
+//   MMA warp  (warp 8)   : one lane issues the row's 24 MMAs (A from TMEM, B from shared memory) into accumulator
+//                          (row & 1) and commits;
 //   consumers (warps 0-3): read their pixel's 25 results from their TMEM lane, release the accumulator, run the
 //                          Generator epilogue and the 9-tap gather, store the output.
-// mbarriers: a_full (128 producers have stored the row's operand), a_free (its MMAs have finished reading it),
-// acc_full[2] (accumulator complete), acc_empty[2] (all 128 consumers have read it).
+// mbarriers: full/empty[stage] (ring), a_full (128 producers have written the row's operand), a_free (its MMAs
+// have finished reading it), acc_full[2] (accumulator complete), acc_empty[2] (all 128 consumers have read it).
+// TMEM (256 columns per CTA, two CTAs per SM): A_hi [0,64) | A_lo [64,128) | accumulators [128,160), [160,192).
 // Measured steps (2048 tiles): every thread doing all jobs in turn, 8 warps per SM: 3.4 ms (latency-bound, 35 %
-// issue rate); producers + consumers with a producer lane issuing the MMAs: 2.9 ms (the ~300 uniform-datapath
-// instructions of the issue sat on the producers' critical path, ahead of their next loads).
-template <int C, bool TMA, int TH, bool WRITE_WO, int CS>
+// issue rate); producers + consumers with a producer lane issuing the MMAs: 2.9 ms; dedicated MMA warp: 2.6 ms
+// (producers held at most 64 KB of loads in flight per SM in registers: 0.52 of the HBM roofline by Little's law).
+template <int C, bool TMA, int TH, bool WRITE_WO>
 __global__ void __launch_bounds__(GEN_CTA_THREADS, 2)
 gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__ feature,
                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                        const float* __restrict__ w9, const float* __restrict__ b1, float* __restrict__ out,
                        float* __restrict__ weight_out, float* __restrict__ offset_out, const Geom g, const int mode,
-                       const float scale, const __grid_constant__ CUtensorMap tmap) {
+                       const float scale, const __grid_constant__ CUtensorMap tmap,
+                       const __grid_constant__ CUtensorMap tmap_feat) {
     constexpr int SH = staged_rows(TH);
-    constexpr uint32_t SBO = 128;                      // bytes between 8-row groups (rows = pixels / output channels)
-    constexpr uint32_t LBO_A = GEN_THREADS / 8 * 128;  // bytes between 16-byte K chunks of A: 2048
-    constexpr uint32_t LBO_B = GEN_N / 8 * 128;        // ... of B: 512
-    constexpr int A_BYTES = GEN_THREADS * C * 4, B_BYTES = GEN_N * C * 4;
+    constexpr uint32_t SBO = 128;                // bytes between 8-row groups of B (rows = output channels)
+    constexpr uint32_t LBO_B = GEN_N / 8 * 128;  // bytes between 16-byte K chunks of B: 512
+    constexpr int STAGE_BYTES = GEN_THREADS * C * 4, B_BYTES = GEN_N * C * 4;
+    constexpr int RING_BYTES = TMA ? GEN_STAGES * STAGE_BYTES : 0;
+    constexpr uint32_t COL_A_HI = 0, COL_A_LO = C, COL_ACC = 2 * C;  // TMEM column map
+    constexpr uint32_t TMEM_COLS = 256;
+    static_assert(2 * C + 2 * GEN_N <= TMEM_COLS, "TMEM budget");
     extern __shared__ __align__(1024) unsigned char dsm[];
-    unsigned char* a_hi = dsm;
-    unsigned char* a_lo = a_hi + A_BYTES;
-    unsigned char* b_hi = a_lo + A_BYTES;
+    unsigned char* ring = dsm;                       // [GEN_STAGES][C][128] fp32 (TMA only)
+    unsigned char* b_hi = dsm + RING_BYTES;
     unsigned char* b_mid = b_hi + B_BYTES;
     float* tile = reinterpret_cast<float*>(b_mid + B_BYTES);  // [SH][SW], 128-byte aligned (all sizes are multiples of 128)
-    __shared__ __align__(8) uint64_t bar_tile, bar_a_full, bar_a_free, bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_tile, bar_full[GEN_STAGES], bar_empty[GEN_STAGES], bar_a_full, bar_a_free,
+        bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_w[10], s_bias[GEN_N];
 
@@ -108,6 +136,10 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
     if (t == 9) s_w[9] = b1 ? b1[0] : 0.f;
     if (t < GEN_N) s_bias[t] = t < GEN_NOUT ? conv_b[t] : 0.f;
     if (t == 32) {
+        for (int i = 0; i < GEN_STAGES; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], GEN_THREADS);
+        }
         mbar_init(&bar_a_full, GEN_THREADS);
         mbar_init(&bar_a_free, 1);
         mbar_init(&bar_acc_full[0], 1);
@@ -116,9 +148,9 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         mbar_init(&bar_acc_empty[1], GEN_THREADS);
         fence_mbar_init();
     }
-    if (warp == 0) {  // 64 TMEM columns: two [128 x 32] fp32 accumulators (rows alternate)
+    if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // B operand: row n = output channel (9 weight rows, 16 offset rows, 7 zero rows), K-major, split hi + mid
@@ -136,33 +168,44 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
     }
     fence_proxy_async();  // B operand: generic-proxy stores -> visible to the tensor core's async proxy
 
-    const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
-    const int px = t & (GEN_THREADS - 1);  // pixel column of this thread inside the tile (both roles)
+    const size_t cs = (size_t)g.H * g.W;
+    const int px = t & (GEN_THREADS - 1);  // pixel column of this thread inside the tile (producers and consumers)
     const int x = c.x0 + px;
     const bool col_ok = x < g.W;
     // instruction descriptor: D fp32 | A, B tf32 | both K-major | N = 32 | M = 128
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((GEN_N >> 3) << 17) | ((GEN_THREADS >> 4) << 24);
 
-    if (warp == 8) {
+    if (warp == 9) {
+        // =========================== TMA warp: feature rows into the ring ===========================
+        __syncthreads();  // setup complete
+        if (TMA && (t & 31) == 0) {
+#pragma unroll 1
+            for (int r = 0; r < TH; ++r) {
+                const int s = r % GEN_STAGES;
+                if (r >= GEN_STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((r / GEN_STAGES) - 1) & 1));
+                mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
+                // box {128 columns, 1 row, C planes}; columns / rows outside the image arrive as zeros
+                tma_load_3d(ring + s * STAGE_BYTES, &tmap_feat, &bar_full[s], c.x0, c.y0 + r, c.b * C);
+            }
+        }
+    } else if (warp == 8) {
         // =========================== MMA warp ===========================
         __syncthreads();  // setup complete (TMEM address, barriers, B operand)
         const uint32_t tmem = s_tmem;
 #pragma unroll 1
         for (int r = 0; r < TH; ++r) {
-            mbar_wait(&bar_a_full, (uint32_t)(r & 1));                                      // operand of row r is in place
+            mbar_wait(&bar_a_full, (uint32_t)(r & 1));                                      // operand of row r is in TMEM
             if (r >= 2) mbar_wait(&bar_acc_empty[r & 1], (uint32_t)(((r >> 1) - 1) & 1));  // consumers drained row r-2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if ((t & 31) == 0) {
-                const uint32_t d_tmem = tmem + (uint32_t)(r & 1) * GEN_N;
+                const uint32_t d_tmem = tmem + COL_ACC + (uint32_t)(r & 1) * GEN_N;
 #pragma unroll
-                for (int ks = 0; ks < C / 8; ++ks) {  // K = 8 tf32 per MMA = two 16-byte chunks
-                    const uint64_t dah = umma_desc_kmajor(smem_u32(a_hi) + ks * 2 * LBO_A, LBO_A, SBO);
-                    const uint64_t dal = umma_desc_kmajor(smem_u32(a_lo) + ks * 2 * LBO_A, LBO_A, SBO);
+                for (int ks = 0; ks < C / 8; ++ks) {  // K = 8 tf32 per MMA: 8 TMEM columns of A, two 16-byte chunks of B
                     const uint64_t dbh = umma_desc_kmajor(smem_u32(b_hi) + ks * 2 * LBO_B, LBO_B, SBO);
                     const uint64_t dbm = umma_desc_kmajor(smem_u32(b_mid) + ks * 2 * LBO_B, LBO_B, SBO);
-                    umma_tf32(d_tmem, dah, dbh, IDESC, ks > 0 ? 1u : 0u);
-                    umma_tf32(d_tmem, dal, dbh, IDESC, 1u);
-                    umma_tf32(d_tmem, dah, dbm, IDESC, 1u);
+                    umma_tf32_ts(d_tmem, tmem + COL_A_HI + ks * 8, dbh, IDESC, ks > 0 ? 1u : 0u);
+                    umma_tf32_ts(d_tmem, tmem + COL_A_LO + ks * 8, dbh, IDESC, 1u);
+                    umma_tf32_ts(d_tmem, tmem + COL_A_HI + ks * 8, dbm, IDESC, 1u);
                 }
                 umma_commit(&bar_a_free);
                 umma_commit(&bar_acc_full[r & 1]);
@@ -172,42 +215,48 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
     } else if (warp >= 4) {
         // =========================== producers ===========================
         const float* feat_b = feature + (size_t)c.b * C * cs;
-        const uint32_t a_off = (px / 8) * SBO + (px % 8) * 16;  // this pixel's row inside every K chunk
-        float f[C];
-        auto load_row = [&](int r) {
-            const int y = c.y0 + r;
-            if (r < TH && col_ok && y < g.H) {
-                const float* p = feat_b + (size_t)y * g.W + x;
-#pragma unroll
-                for (int k = 0; k < C; ++k) f[k] = ld_stream(p + (size_t)k * cs);
-            } else {
-#pragma unroll
-                for (int k = 0; k < C; ++k) f[k] = 0.f;
-            }
-        };
-        load_row(0);
-        __syncthreads();  // setup complete (TMEM address, barriers, B operand)
-        const uint32_t tmem = s_tmem;
+        __syncthreads();  // setup complete
+        const uint32_t lane_tmem = s_tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
         for (int r = 0; r < TH; ++r) {
-            if (r > 0) mbar_wait(&bar_a_free, (uint32_t)((r - 1) & 1));  // MMA(r-1) no longer reads the A buffers
+            const int s = r % GEN_STAGES;
+            const float* stage = reinterpret_cast<const float*>(ring + s * STAGE_BYTES) + px;
+            const int y = c.y0 + r;
+            const bool row_ok = col_ok && y < g.H;
+            const float* gp = feat_b + (size_t)y * g.W + x;
+            if (TMA) mbar_wait(&bar_full[s], (uint32_t)((r / GEN_STAGES) & 1));       // the row has landed
+            if (r > 0) mbar_wait(&bar_a_free, (uint32_t)((r - 1) & 1));               // MMA(r-1) no longer reads A
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int kc = 0; kc < C / 4; ++kc) {  // hi / lo parts, 16 bytes (4 channels) per store
-                float4 hi = make_float4(tf32_rn(f[4 * kc]), tf32_rn(f[4 * kc + 1]), tf32_rn(f[4 * kc + 2]), tf32_rn(f[4 * kc + 3]));
-                float4 lo = make_float4(f[4 * kc] - hi.x, f[4 * kc + 1] - hi.y, f[4 * kc + 2] - hi.z, f[4 * kc + 3] - hi.w);
-                *reinterpret_cast<float4*>(a_hi + kc * LBO_A + a_off) = hi;
-                *reinterpret_cast<float4*>(a_lo + kc * LBO_A + a_off) = lo;
+            for (int k0 = 0; k0 < C; k0 += 16) {  // 16 channels at a time: ring / HBM -> registers -> hi, lo -> TMEM lane
+                float hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v;
+                    if (TMA) v = stage[(k0 + j) * GEN_THREADS];
+                    else v = row_ok ? ld_stream(gp + (size_t)(k0 + j) * cs) : 0.f;
+                    hi[j] = v;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = hi[j];
+                    hi[j] = tf32_rn(v);
+                    lo[j] = v - hi[j];
+                }
+                tmem_st16(lane_tmem + COL_A_HI + k0, hi);
+                tmem_st16(lane_tmem + COL_A_LO + k0, lo);
             }
-            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            if (TMA) mbar_arrive(&bar_empty[s]);  // every read of the stage has been consumed into registers above
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&bar_a_full);
-            load_row(r + 1);  // in flight while the MMAs run and the consumers gather
         }
     } else {
         // =========================== consumers ===========================
         const float* init_b = init + (size_t)c.b * g.init_rows * g.W;
         float* out_b = out + (size_t)c.b * cs;
         const float* tile_lo = tile + c.r_lo * SW;
-        stage_tile_wait<TMA>(&bar_tile);  // __syncthreads (pairs with the producers') + the DEM box has landed
+        stage_tile_wait<TMA>(&bar_tile);  // __syncthreads (pairs with the other roles') + the DEM box has landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem = s_tmem;
 #pragma unroll 1
@@ -215,7 +264,7 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
             mbar_wait(&bar_acc_full[r & 1], (uint32_t)((r >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r & 1) * GEN_N, v);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + COL_ACC + (uint32_t)(r & 1) * GEN_N, v);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&bar_acc_empty[r & 1]);
 
@@ -281,47 +330,45 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(64));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(TMEM_COLS));
 }
 
-template <int C, bool TMA, int TH, bool WO, int CS>
-static cudaError_t launch_gen_one(const LaunchArgs& la, const float* feature, const float* conv_w, const float* conv_b,
-                                  float* weight_out, float* offset_out) {
-    const size_t dyn = (size_t)2 * GEN_THREADS * C * 4 + (size_t)2 * GEN_N * C * 4 + (size_t)staged_rows(TH) * SW * 4;
-    static const cudaError_t attr = cudaFuncSetAttribute(gen_spn_forward_kernel<C, TMA, TH, WO, CS>,
+template <int C, bool TMA, int TH, bool WO>
+static cudaError_t launch_gen_one(const LaunchArgs& la, const CUtensorMap& tmap_feat, const float* feature,
+                                  const float* conv_w, const float* conv_b, float* weight_out, float* offset_out) {
+    const size_t dyn = (TMA ? (size_t)GEN_STAGES * GEN_THREADS * C * 4 : 0) + (size_t)2 * GEN_N * C * 4 +
+                       (size_t)staged_rows(TH) * SW * 4;
+    static const cudaError_t attr = cudaFuncSetAttribute(gen_spn_forward_kernel<C, TMA, TH, WO>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    gen_spn_forward_kernel<C, TMA, TH, WO, CS><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>(
+    gen_spn_forward_kernel<C, TMA, TH, WO><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>(
         (const float*)la.init, feature, conv_w, conv_b, la.w9, la.b1, (float*)la.out, weight_out, offset_out, la.g, la.mode,
-        la.scale, la.tmap);
+        la.scale, la.tmap, tmap_feat);
     return cudaGetLastError();
 }
 
 template <int C, int TH>
-static cudaError_t launch_gen_c(const LaunchArgs& la, const float* feature, const float* conv_w, const float* conv_b,
-                                float* weight_out, float* offset_out) {
+static cudaError_t launch_gen_c(const LaunchArgs& la, const CUtensorMap& tmap_feat, const float* feature,
+                                const float* conv_w, const float* conv_b, float* weight_out, float* offset_out) {
     const bool wo = weight_out != nullptr;
-    if (la.use_tma && (size_t)la.g.H * la.g.W == 16384) {  // the reference's 128x128 planes
-        return wo ? launch_gen_one<C, true, TH, true, 16384>(la, feature, conv_w, conv_b, weight_out, offset_out)
-                  : launch_gen_one<C, true, TH, false, 16384>(la, feature, conv_w, conv_b, weight_out, offset_out);
-    }
     if (la.use_tma) {
-        return wo ? launch_gen_one<C, true, TH, true, 0>(la, feature, conv_w, conv_b, weight_out, offset_out)
-                  : launch_gen_one<C, true, TH, false, 0>(la, feature, conv_w, conv_b, weight_out, offset_out);
+        return wo ? launch_gen_one<C, true, TH, true>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+                  : launch_gen_one<C, true, TH, false>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
     }
-    return wo ? launch_gen_one<C, false, TH, true, 0>(la, feature, conv_w, conv_b, weight_out, offset_out)
-              : launch_gen_one<C, false, TH, false, 0>(la, feature, conv_w, conv_b, weight_out, offset_out);
+    return wo ? launch_gen_one<C, false, TH, true>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+              : launch_gen_one<C, false, TH, false>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
 }
 
-// la.tile_h must be 16 or 8 (abi.cu); the TMA box is encoded for the same value
-cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const void* feature, int C, const float* conv_w,
-                                   const float* conv_b, void* weight_out, void* offset_out) {
+// la.tile_h must be 16 or 8 (abi.cu); la.use_tma says that BOTH tensor maps (DEM box, feature rows) are valid
+cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature, int C,
+                                   const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
     const float* f = (const float*)feature;
     float* wo = (float*)weight_out;
     float* oo = (float*)offset_out;
     if (C == 64) {
-        return la.tile_h == 16 ? launch_gen_c<64, 16>(la, f, conv_w, conv_b, wo, oo) : launch_gen_c<64, 8>(la, f, conv_w, conv_b, wo, oo);
+        return la.tile_h == 16 ? launch_gen_c<64, 16>(la, tmap_feat, f, conv_w, conv_b, wo, oo)
+                               : launch_gen_c<64, 8>(la, tmap_feat, f, conv_w, conv_b, wo, oo);
     }
     return cudaErrorNotSupported;
 }
