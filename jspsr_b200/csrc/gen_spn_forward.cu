@@ -61,14 +61,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The MMA warp runs these CONVERGED (all 32 lanes, one elected lane issues): inside a divergent `if (lane == 0)`
+// the compiler cannot keep addresses and descriptors on the uniform datapath and wraps every MMA in an
+// ELECT / R2UR / branch sequence (~100 cycles each, measured: the issue loop was the kernel's critical path).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when all MMAs issued so far are complete
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+        : "memory");
 }
 // A operand from tensor memory (lane = row of A = pixel, one tf32 per column), B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -82,7 +88,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         : "memory");
 }
 
-constexpr int GEN_STAGES = 2;  // feature rows in flight per CTA (32 KB each at C = 64)
+constexpr int GEN_STAGES = 2;    // feature rows in flight into shared memory per CTA (32 KB each at C = 64)
+constexpr int GEN_L2_AHEAD = 4;  // further rows in flight into L2 (TMA prefetch)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 
 // C: feature channels (bc * 4 of the Generator: 64 for JSPSR's num_feature = 32, 128 for cat_only / EDSR).
 // TMA: the DEM box AND the feature rows arrive by TMA (needs 16-byte aligned rows); otherwise bounds-checked loads.
@@ -97,8 +109,9 @@ constexpr int GEN_STAGES = 2;  // feature rows in flight per CTA (32 KB each at 
 //                          (row & 1) and commits;
 //   consumers (warps 0-3): read their pixel's 25 results from their TMEM lane, release the accumulator, run the
 //                          Generator epilogue and the 9-tap gather, store the output.
-// mbarriers: full/empty[stage] (ring), a_full (128 producers have written the row's operand), a_free (its MMAs
-// have finished reading it), acc_full[2] (accumulator complete), acc_empty[2] (all 128 consumers have read it).
+// mbarriers: full/empty[stage] (ring), a_full[half] (128 producers have written that K half of the row's operand),
+// a_free[half] (its MMAs have finished reading it) - two halves so that the producers fill one while the MMAs
+// read the other -, acc_full[2] (accumulator complete), acc_empty[2] (all 128 consumers have read it).
 // TMEM (256 columns per CTA, two CTAs per SM): A_hi [0,64) | A_lo [64,128) | accumulators [128,160), [160,192).
 // Measured steps (2048 tiles): every thread doing all jobs in turn, 8 warps per SM: 3.4 ms (latency-bound, 35 %
 // issue rate); producers + consumers with a producer lane issuing the MMAs: 2.9 ms; dedicated MMA warp: 2.6 ms
@@ -124,10 +137,11 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
     unsigned char* b_hi = dsm + RING_BYTES;
     unsigned char* b_mid = b_hi + B_BYTES;
     float* tile = reinterpret_cast<float*>(b_mid + B_BYTES);  // [SH][SW], 128-byte aligned (all sizes are multiples of 128)
-    __shared__ __align__(8) uint64_t bar_tile, bar_full[GEN_STAGES], bar_empty[GEN_STAGES], bar_a_full, bar_a_free,
+    __shared__ __align__(8) uint64_t bar_tile, bar_full[GEN_STAGES], bar_empty[GEN_STAGES], bar_a_full[2], bar_a_free[2],
         bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_w[10], s_bias[GEN_N];
+    __shared__ float s_w[10];
+    __shared__ __align__(16) float s_bias[GEN_N];
 
     const int t = threadIdx.x, warp = t >> 5;
     const TileCtx c = make_tile_ctx<TH>(g);
@@ -140,8 +154,10 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], GEN_THREADS);
         }
-        mbar_init(&bar_a_full, GEN_THREADS);
-        mbar_init(&bar_a_free, 1);
+        for (int i = 0; i < 2; ++i) {  // per K half (channels [0, C/2) and [C/2, C))
+            mbar_init(&bar_a_full[i], GEN_THREADS);
+            mbar_init(&bar_a_free[i], 1);
+        }
         mbar_init(&bar_acc_full[0], 1);
         mbar_init(&bar_acc_full[1], 1);
         mbar_init(&bar_acc_empty[0], GEN_THREADS);
@@ -179,9 +195,13 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         // =========================== TMA warp: feature rows into the ring ===========================
         __syncthreads();  // setup complete
         if (TMA && (t & 31) == 0) {
+            // the ring holds GEN_STAGES rows; rows further ahead are pulled into L2 so that ring fills are L2 hits
+            for (int r = GEN_STAGES; r < GEN_STAGES + GEN_L2_AHEAD && r < TH; ++r)
+                tma_prefetch_3d(&tmap_feat, c.x0, c.y0 + r, c.b * C);
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
                 const int s = r % GEN_STAGES;
+                if (r + GEN_STAGES + GEN_L2_AHEAD < TH) tma_prefetch_3d(&tmap_feat, c.x0, c.y0 + r + GEN_STAGES + GEN_L2_AHEAD, c.b * C);
                 if (r >= GEN_STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((r / GEN_STAGES) - 1) & 1));
                 mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
                 // box {128 columns, 1 row, C planes}; columns / rows outside the image arrive as zeros
@@ -194,21 +214,23 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         const uint32_t tmem = s_tmem;
 #pragma unroll 1
         for (int r = 0; r < TH; ++r) {
-            mbar_wait(&bar_a_full, (uint32_t)(r & 1));                                      // operand of row r is in TMEM
-            if (r >= 2) mbar_wait(&bar_acc_empty[r & 1], (uint32_t)(((r >> 1) - 1) & 1));  // consumers drained row r-2
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if ((t & 31) == 0) {
-                const uint32_t d_tmem = tmem + COL_ACC + (uint32_t)(r & 1) * GEN_N;
+            const uint32_t d_tmem = tmem + COL_ACC + (uint32_t)(r & 1) * GEN_N;
 #pragma unroll
-                for (int ks = 0; ks < C / 8; ++ks) {  // K = 8 tf32 per MMA: 8 TMEM columns of A, two 16-byte chunks of B
+            for (int h = 0; h < 2; ++h) {  // the two K halves are pipelined against the producers
+                mbar_wait(&bar_a_full[h], (uint32_t)(r & 1));                                   // half h of row r is in TMEM
+                if (h == 0 && r >= 2) mbar_wait(&bar_acc_empty[r & 1], (uint32_t)(((r >> 1) - 1) & 1));  // row r-2 drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int kq = 0; kq < C / 16; ++kq) {  // K = 8 tf32 per MMA: 8 TMEM columns of A, two 16-byte chunks of B
+                    const int ks = h * (C / 16) + kq;
                     const uint64_t dbh = umma_desc_kmajor(smem_u32(b_hi) + ks * 2 * LBO_B, LBO_B, SBO);
                     const uint64_t dbm = umma_desc_kmajor(smem_u32(b_mid) + ks * 2 * LBO_B, LBO_B, SBO);
                     umma_tf32_ts(d_tmem, tmem + COL_A_HI + ks * 8, dbh, IDESC, ks > 0 ? 1u : 0u);
                     umma_tf32_ts(d_tmem, tmem + COL_A_LO + ks * 8, dbh, IDESC, 1u);
                     umma_tf32_ts(d_tmem, tmem + COL_A_HI + ks * 8, dbm, IDESC, 1u);
                 }
-                umma_commit(&bar_a_free);
-                umma_commit(&bar_acc_full[r & 1]);
+                umma_commit(&bar_a_free[h]);
+                if (h == 1) umma_commit(&bar_acc_full[r & 1]);
             }
             __syncwarp();
         }
@@ -225,10 +247,12 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
             const bool row_ok = col_ok && y < g.H;
             const float* gp = feat_b + (size_t)y * g.W + x;
             if (TMA) mbar_wait(&bar_full[s], (uint32_t)((r / GEN_STAGES) & 1));       // the row has landed
-            if (r > 0) mbar_wait(&bar_a_free, (uint32_t)((r - 1) & 1));               // MMA(r-1) no longer reads A
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int k0 = 0; k0 < C; k0 += 16) {  // 16 channels at a time: ring / HBM -> registers -> hi, lo -> TMEM lane
+                if (k0 % (C / 2) == 0 && r > 0) {  // MMAs of row r-1 no longer read this K half of A
+                    mbar_wait(&bar_a_free[k0 / (C / 2)], (uint32_t)((r - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 float hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -245,11 +269,13 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
                 }
                 tmem_st16(lane_tmem + COL_A_HI + k0, hi);
                 tmem_st16(lane_tmem + COL_A_LO + k0, lo);
+                if ((k0 + 16) % (C / 2) == 0) {  // a K half is complete: hand it to the MMA warp
+                    if (TMA && k0 + 16 == C) mbar_arrive(&bar_empty[s]);  // every read of the stage is in registers
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&bar_a_full[(k0 + 16) / (C / 2) - 1]);
+                }
             }
-            if (TMA) mbar_arrive(&bar_empty[s]);  // every read of the stage has been consumed into registers above
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&bar_a_full);
         }
     } else {
         // =========================== consumers ===========================
@@ -273,9 +299,15 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
             const size_t p = (size_t)y * g.W + x;
             float a[9], oh[9], ow[9];
 #pragma unroll
+            for (int q = 0; q < 7; ++q) {  // + bias (broadcast 16-byte reads)
+                const float4 bq = reinterpret_cast<const float4*>(s_bias)[q];
+                v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+            }
+#pragma unroll
             for (int k = 0; k < 9; ++k) {
-                const float z = v[k] + s_bias[k];
-                a[k] = __frcp_rn(1.f + expf(-z));  // correctly rounded reciprocal == 1 / (1 + e)
+                // sigmoid = 1 / (1 + 2^(-z log2 e)): ex2.approx + rcp.approx (2 + 1 ulp; the argument rounding adds
+                // |z| * 1e-7 relative to e^-z, i.e. < 5e-7 absolute on the weight for |z| < 20)
+                a[k] = __fdividef(1.f, 1.f + __expf(-v[k]));
             }
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
@@ -283,8 +315,8 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
                     oh[k] = ow[k] = 0.f;  // zero centre pair (spn.py:69-73)
                 } else {
                     const int n = k < 4 ? k : k - 1;
-                    oh[k] = v[9 + 2 * n] + s_bias[9 + 2 * n];
-                    ow[k] = v[10 + 2 * n] + s_bias[10 + 2 * n];
+                    oh[k] = v[9 + 2 * n];
+                    ow[k] = v[10 + 2 * n];
                 }
             }
             if (WRITE_WO) {

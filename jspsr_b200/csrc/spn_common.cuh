@@ -98,7 +98,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n"  // suspend-time hint: sleep, do not spin
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
