@@ -412,7 +412,8 @@ def side_numbers(torch, F, device, B):
     init, weight, offset, gout, w, b = make_inputs(torch, B, device, torch.float32, 4322)
     g = timed(lambda: F.spn_backward(gout, init, weight, offset, w, 1, 1.0, need_grad_init=True))
     out["backward_with_grad_init"] = {"ms": g, "frac_of_hbm_peak": 228 * npix / (g * 1e-3) / 1e9 / peak,
-                                      "note": "scatter through shared-memory atomics (CAS loops); used by NLSPN only"}
+                                      "note": "scatter into a block-floating-point tile of native integer shared-memory "
+                                              "atomics (exact, order-independent inside a CTA); used by NLSPN only"}
     T = 6
     aff = weight * 0.1
     it = timed(lambda: F.spn_iterate(init, aff, offset, T), n=3)
@@ -420,6 +421,38 @@ def side_numbers(torch, F, device, B):
                             "frac_of_hbm_peak_compulsory": (4 + 108 + 4 * T) * npix / (it * 1e-3) / 1e9 / peak,
                             "frac_of_hbm_peak_as_run": 116 * T * npix / (it * 1e-3) / 1e9 / peak,
                             "note": "T launches of the forward kernel, all T outputs kept"}
+    del aff, gout, weight, offset
+    torch.cuda.empty_cache()
+    # the Generator's last two layers (1x1 convolutions 64 -> 9 / 16, sigmoid, zero
+    # centre pair; spn.py:41-52,66-73) fused into the propagation forward; contraction on tcgen05 (3xTF32)
+    C = 64
+    g_ = torch.Generator(device=device).manual_seed(4323)
+    feat = torch.randn(B, C, TILE, TILE, device=device, generator=g_)
+    cw = 0.15 * torch.randn(25, C, device=device, generator=g_)
+    cw[9:] *= 1.3
+    cb = 0.1 * torch.randn(25, device=device, generator=g_)
+    fused = timed(lambda: F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0, False))
+    fused_wo = timed(lambda: F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0, True))
+    cwt, cot = cw[:9].reshape(9, C, 1, 1).contiguous(), cw[9:].reshape(16, C, 1, 1).contiguous()
+
+    def unfused():  # the reference's sequence (spn.py:66-73 + 99-118) with torch's convolutions and OUR propagation kernel
+        weight = torch.sigmoid(torch.nn.functional.conv2d(feat, cwt, cb[:9]))
+        o = torch.nn.functional.conv2d(feat, cot, cb[9:]).view(B, 8, 2, TILE, TILE)
+        lo = list(torch.chunk(o, 8, dim=1))
+        lo.insert(4, torch.zeros((B, 1, 2, TILE, TILE), device=device))
+        return F.spn_forward(init, weight, torch.cat(lo, dim=1).view(B, -1, TILE, TILE), w, b, 1, 1.0)
+
+    un = timed(unfused, n=3)
+    by = (C * 4 + 8) * npix
+    out["generator_tail_fused"] = {
+        "ms": fused, "gpix_per_s": npix / (fused * 1e-3) / 1e9, "algorithmic_bytes_per_pixel": C * 4 + 8,
+        "frac_of_hbm_peak": by / (fused * 1e-3) / 1e9 / peak,
+        "ms_with_weight_offset_written": fused_wo,
+        "frac_of_hbm_peak_with_weight_offset_written": (by + 108 * npix) / (fused_wo * 1e-3) / 1e9 / peak,
+        "unfused_ms": un, "speedup_vs_unfused": un / fused,
+        "note": "gen_spn_forward_kernel: TMA ring -> tf32 hi/lo split into TMEM lanes -> tcgen05.mma (A from TMEM, "
+                "3-product split, fp32-level accuracy) -> per-pixel epilogue + 9-tap gather; unfused = torch 1x1 "
+                "convolutions (TF32 allowed, torch's default) + sigmoid + chunk/insert/cat + spn_forward_kernel"}
     return out
 
 
