@@ -89,7 +89,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 }
 
 constexpr int GEN_STAGES = 2;    // feature rows in flight into shared memory per CTA (32 KB each at C = 64)
-constexpr int GEN_L2_AHEAD = 4;  // further rows in flight into L2 (TMA prefetch)
+// Further rows pulled into L2 by TMA prefetch.  Measured and rejected (kept behind JSPSR_GEN_L2_AHEAD): 0 rows 1.52 ms,
+// 2 rows 1.54 ms, 4 rows 1.73 ms with 10.5 GB read from DRAM for 8.7 GB of data - prefetched lines are evicted
+// before the ring asks for them.
+constexpr int GEN_L2_AHEAD = 0;
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
                  "r"(c0), "r"(c1), "r"(c2)
@@ -115,14 +118,15 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 // TMEM (256 columns per CTA, two CTAs per SM): A_hi [0,64) | A_lo [64,128) | accumulators [128,160), [160,192).
 // Measured steps (2048 tiles): every thread doing all jobs in turn, 8 warps per SM: 3.4 ms (latency-bound, 35 %
 // issue rate); producers + consumers with a producer lane issuing the MMAs: 2.9 ms; dedicated MMA warp: 2.6 ms
-// (producers held at most 64 KB of loads in flight per SM in registers: 0.52 of the HBM roofline by Little's law).
+// (producers held at most 64 KB of loads in flight per SM in registers: 0.52 of the HBM roofline by Little's law);
+// this version: 1.52 ms = 0.89 of the HBM roofline (0.98 when weight/offset are also written).
 template <int C, bool TMA, int TH, bool WRITE_WO>
 __global__ void __launch_bounds__(GEN_CTA_THREADS, 2)
 gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__ feature,
                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                        const float* __restrict__ w9, const float* __restrict__ b1, float* __restrict__ out,
                        float* __restrict__ weight_out, float* __restrict__ offset_out, const Geom g, const int mode,
-                       const float scale, const __grid_constant__ CUtensorMap tmap,
+                       const float scale, const int l2_ahead, const __grid_constant__ CUtensorMap tmap,
                        const __grid_constant__ CUtensorMap tmap_feat) {
     constexpr int SH = staged_rows(TH);
     constexpr uint32_t SBO = 128;                // bytes between 8-row groups of B (rows = output channels)
@@ -195,13 +199,14 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         // =========================== TMA warp: feature rows into the ring ===========================
         __syncthreads();  // setup complete
         if (TMA && (t & 31) == 0) {
-            // the ring holds GEN_STAGES rows; rows further ahead are pulled into L2 so that ring fills are L2 hits
-            for (int r = GEN_STAGES; r < GEN_STAGES + GEN_L2_AHEAD && r < TH; ++r)
+            // optional (off by default, see GEN_L2_AHEAD): rows beyond the ring pulled into L2
+            for (int r = GEN_STAGES; r < GEN_STAGES + l2_ahead && r < TH; ++r)
                 tma_prefetch_3d(&tmap_feat, c.x0, c.y0 + r, c.b * C);
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
                 const int s = r % GEN_STAGES;
-                if (r + GEN_STAGES + GEN_L2_AHEAD < TH) tma_prefetch_3d(&tmap_feat, c.x0, c.y0 + r + GEN_STAGES + GEN_L2_AHEAD, c.b * C);
+                if (l2_ahead > 0 && r + GEN_STAGES + l2_ahead < TH)
+                    tma_prefetch_3d(&tmap_feat, c.x0, c.y0 + r + GEN_STAGES + l2_ahead, c.b * C);
                 if (r >= GEN_STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((r / GEN_STAGES) - 1) & 1));
                 mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
                 // box {128 columns, 1 row, C planes}; columns / rows outside the image arrive as zeros
@@ -374,9 +379,11 @@ static cudaError_t launch_gen_one(const LaunchArgs& la, const CUtensorMap& tmap_
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
+    int l2_ahead = GEN_L2_AHEAD;
+    if (const char* e = getenv("JSPSR_GEN_L2_AHEAD")) l2_ahead = atoi(e);  // experiment switch
     gen_spn_forward_kernel<C, TMA, TH, WO><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>(
         (const float*)la.init, feature, conv_w, conv_b, la.w9, la.b1, (float*)la.out, weight_out, offset_out, la.g, la.mode,
-        la.scale, la.tmap, tmap_feat);
+        la.scale, l2_ahead, la.tmap, tmap_feat);
     return cudaGetLastError();
 }
 
