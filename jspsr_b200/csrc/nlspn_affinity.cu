@@ -17,6 +17,7 @@ inline namespace JSPSR_VARIANT {
 enum { AFF_AS = 0, AFF_ASS = 1, AFF_TC = 2, AFF_TGASS = 3 };
 
 constexpr int AFF_MIN_BLOCKS = 3;
+constexpr int AFF_BWD_MIN_BLOCKS = 2;  // 128 registers: at 80 the backward spilled (STL/LDL were its top stall)
 
 // tanh(x/100) / gamma' with the reference's operation order; the two divisions become multiplications
 // by correctly rounded reciprocals (<= 1 ulp each)
@@ -125,8 +126,14 @@ nlspn_affinity_fwd_kernel(const T* __restrict__ conv_out, const T* __restrict__ 
     }
 }
 
-template <typename T, bool CONF, bool TMA, int TH>
-__global__ void __launch_bounds__(THREADS, AFF_MIN_BLOCKS)
+// CS: compile-time channel stride (0 = runtime).  ITILE: grad_confidence is scattered into a block-floating-point
+// tile of native integer atomics (spn_backward.cu); its scale comes from a pre-pass BOUND on the CTA's sum of
+// |contributions|: |dL/d(sample_n)| <= 2 * max_m|g_m| * inv * |t_n| with inv <= 1 for the clamped (ASS, TGASS) and the
+// unnormalised (TC) affinities; AS (unclamped) has no such bound without the gathers and keeps the fp32 tile.
+// The bound can overestimate the true sum by orders of magnitude (large raw affinities), so the tile is the
+// two-level form (gi_add2: coarse + residual tile in dynamic shared memory, 45 bits in total).
+template <typename T, bool CONF, bool TMA, int TH, int CS, bool ITILE>
+__global__ void __launch_bounds__(THREADS, AFF_BWD_MIN_BLOCKS)
 nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict__ grad_aff,
                           const T* __restrict__ conv_out, const T* __restrict__ conf, const float* __restrict__ gamma_p,
                           T* __restrict__ grad_conv, float* __restrict__ grad_conf, float* __restrict__ grad_scale,
@@ -135,19 +142,24 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
     constexpr int SH = staged_rows(TH);
     constexpr int PPT = pixels_per_thread(TH);
     __shared__ __align__(128) T tile[CONF ? SH * SW : 8];
-    __shared__ __align__(16) float gtile[CONF ? SH * SW : 4];
+    __shared__ __align__(16) float gtile[CONF ? SH * SW : 4];  // fp32, or int32 bit patterns when ITILE
+    extern __shared__ __align__(16) int gtile_res[];           // ITILE: residual tile [SH * SW]
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_red[WARPS];
+    __shared__ GiScale s_gis;
     __shared__ bool s_last;
 
     const TileCtx c = make_tile_ctx<TH>(g);
     if (CONF) {
         stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, conf, g, c.b, c.ox, c.oy - g.init_row0);
-        for (int i = threadIdx.x; i < SH * SW; i += THREADS) gtile[i] = 0.f;
+        for (int i = threadIdx.x; i < SH * SW; i += THREADS) {
+            gtile[i] = 0.f;  // all-zero bits in both formats
+            if (ITILE) gtile_res[i] = 0;
+        }
     }
     const bool scatter = CONF && grad_conf != nullptr;
 
-    const size_t cs = (size_t)g.H * g.W;
+    const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
     const T* cv_b = conv_out + (size_t)c.b * 24 * cs;
     const T* go_b = grad_offset + (size_t)c.b * 18 * cs;
     const T* ga_b = grad_aff + (size_t)c.b * 9 * cs;
@@ -183,9 +195,42 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
 
     bool active;
     size_t p;
+    float gscale = 0.f;
+    if (CONF && ITILE) {
+        // pre-pass: S >= sum over this CTA of |dL/d(confidence sample)| from the affinity gradients alone
+        float part = 0.f;
+        if (scatter) {
+#pragma unroll 1
+            for (int it = 0; it < PPT; ++it) {
+                const int y = c.y0 + pix_row<TH, true>(it), x = c.x0 + pix_col<TH, true>(it);
+                if (y < g.H && x < g.W) {
+                    const size_t q = (size_t)y * g.W + x;
+                    const float gcen = to_f32(ga_b[q + 4 * cs]);
+                    float gmax = 0.f, tsum = 0.f;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        gmax = fmaxf(gmax, fabsf(to_f32(ga_b[q + tap_index(n) * cs]) - gcen));
+                        // |t_n|: tanh types are bounded by 1 / gamma', the raw types are the convolution output
+                        tsum += tanh_type ? fabsf(rgam) : fabsf(to_f32(cv_b[q + (16 + n) * cs]));
+                    }
+                    part = fmaf(2.f * gmax, tsum, part);
+                }
+            }
+        }
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float S = 0.f;
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) S += s_red[i];
+            s_gis = gi_scale_from_sum(S);
+        }
+    }
     load_inputs(0, active, p);
     if (CONF) stage_tile_wait<TMA>(&bar);
     else __syncthreads();
+    if (CONF && ITILE) gscale = s_gis.scale;  // published before the barrier above
 
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
@@ -262,12 +307,22 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
                     }
                 } else {
                     const FastTap t = fast_tap<T>(tile_lo, c, h, w);  // geometry only (values unused)
-                    const float ch = gv * t.lh, cl = gv - ch, c2 = cl * t.lw, c4 = ch * t.lw;
+                    const float gvs = ITILE ? gv * gscale : gv;       // exact: the scale is a power of two
+                    const float ch = gvs * t.lh, cl = gvs - ch, c2 = cl * t.lw, c4 = ch * t.lw;
                     float* gtp = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);
-                    atomicAdd(gtp, cl - c2);
-                    atomicAdd(gtp + 1, c2);
-                    atomicAdd(gtp + SW, ch - c4);
-                    atomicAdd(gtp + SW + 1, c4);
+                    if (ITILE) {
+                        int* gip = reinterpret_cast<int*>(gtp);
+                        int* grp = gtile_res + (gtp - gtile);
+                        gi_add2(gip, grp, cl - c2);
+                        gi_add2(gip + 1, grp + 1, c2);
+                        gi_add2(gip + SW, grp + SW, ch - c4);
+                        gi_add2(gip + SW + 1, grp + SW + 1, c4);
+                    } else {
+                        atomicAdd(gtp, cl - c2);
+                        atomicAdd(gtp + 1, c2);
+                        atomicAdd(gtp + SW, ch - c4);
+                        atomicAdd(gtp + SW + 1, c4);
+                    }
                 }
             }
             float gaf = gt;
@@ -282,10 +337,21 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
     if (scatter) {  // flush the accumulation tile: contributions to cells outside the image are dropped
         __syncthreads();
         const bool vec_ok = (g.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad_conf) & 15) == 0);
+        const bool poison = ITILE && s_gis.poison;
+        const float ginv = poison ? __int_as_float(0x7fc00000) : s_gis.inv;
         for (int i = threadIdx.x; i < SH * (SW / 4); i += THREADS) {
             const int r = i / (SW / 4), q = (i - r * (SW / 4)) * 4;
-            const float4 v = *reinterpret_cast<const float4*>(gtile + r * SW + q);
-            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            float4 v = *reinterpret_cast<const float4*>(gtile + r * SW + q);
+            if (ITILE) {
+                const int4 iv = *reinterpret_cast<const int4*>(gtile + r * SW + q);
+                const int4 ir = *reinterpret_cast<const int4*>(gtile_res + r * SW + q);
+                if ((iv.x | iv.y | iv.z | iv.w | ir.x | ir.y | ir.z | ir.w) == 0 && !poison) continue;
+                const float k = 1.f / 65536.f;
+                v = make_float4(fmaf((float)ir.x, k, (float)iv.x) * ginv, fmaf((float)ir.y, k, (float)iv.y) * ginv,
+                                fmaf((float)ir.z, k, (float)iv.z) * ginv, fmaf((float)ir.w, k, (float)iv.w) * ginv);
+            } else if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) {
+                continue;
+            }
             const int gy = c.oy + r, gx = c.ox + q;
             if ((unsigned)gy >= (unsigned)g.H_img) continue;
             float* dst = gcf_b + (size_t)gy * g.W + gx;
@@ -340,12 +406,30 @@ static void aff_fwd_launch(const AffArgs& a) {
     nlspn_affinity_fwd_kernel<T, CONF, TMA, TH><<<grid, THREADS, 0, a.stream>>>(
         (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.offset_out, (T*)a.aff_out, a.g, a.affinity, a.legacy, a.tmap);
 }
-template <typename T, bool CONF, bool TMA, int TH>
-static void aff_bwd_launch(const AffArgs& a) {
+template <typename T, bool CONF, bool TMA, int TH, int CS, bool ITILE>
+static void aff_bwd_launch_one(const AffArgs& a) {
     dim3 grid((unsigned)((size_t)a.g.tiles_x * a.g.tiles_y * a.g.B));
-    nlspn_affinity_bwd_kernel<T, CONF, TMA, TH><<<grid, THREADS, 0, a.stream>>>(
+    const size_t dyn = ITILE ? (size_t)staged_rows(TH) * SW * sizeof(int) : 0;
+    if (dyn > 0) {  // static + dynamic shared memory exceed 48 KB with the wide halo: opt in once per instantiation
+        static const cudaError_t attr = cudaFuncSetAttribute(nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE>,
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        (void)attr;
+    }
+    nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE><<<grid, THREADS, dyn, a.stream>>>(
         (const T*)a.grad_offset, (const T*)a.grad_aff, (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.grad_conv,
         a.grad_conf, a.grad_scale, (ReduceWs*)a.ws, a.g, a.affinity, a.tmap);
+}
+template <typename T, bool CONF, bool TMA, int TH>
+static void aff_bwd_launch(const AffArgs& a) {
+    const bool cs128 = TMA && (size_t)a.g.H * a.g.W == 16384;  // the reference's 128x128 planes
+    const bool itile = CONF && a.affinity != AFF_AS;
+    if (cs128) {
+        if (itile) aff_bwd_launch_one<T, CONF, TMA, TH, 16384, CONF>(a);
+        else aff_bwd_launch_one<T, CONF, TMA, TH, 16384, false>(a);
+    } else {
+        if (itile) aff_bwd_launch_one<T, CONF, TMA, TH, 0, CONF>(a);
+        else aff_bwd_launch_one<T, CONF, TMA, TH, 0, false>(a);
+    }
 }
 
 template <typename T, bool FWD, bool CONF, bool TMA, int TH>

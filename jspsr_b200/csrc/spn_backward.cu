@@ -27,27 +27,10 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
 // HBM roofline; lane-private tile copies buy 9 %, a hand-written atomicCAS loop is 4.7x slower).  Native
 // ATOMS.ADD exists for 32-bit integers, so the tile is block floating point: a pre-pass over the CTA's own
 // pixels sums |grad_out * m_k * w_k| over all taps (S); every cell's final magnitude is <= S because the four
-// bilinear coefficients of a tap sum to 1, so with scale = 2^e, S * 2^e <= 2^29, no cell can overflow, the
-// scaling itself is exact, and each contribution is rounded once to S * 2^-29 (typically ~1e-6 of the largest
+// bilinear coefficients of a tap sum to 1, so with scale = 2^e, S * 2^e <= 2^30, no cell can overflow, the
+// scaling itself is exact, and each contribution is rounded once to S * 2^-30 (typically ~1e-5 of the mean
 // contribution, far below fp32 atomics' own order-dependent rounding).  Sums inside a CTA are exact integers,
 // i.e. independent of the order the atomics land in.  A non-finite S poisons the CTA's cells with NaN.
-struct GiScale {
-    float scale, inv;
-    int poison;
-};
-__device__ __forceinline__ GiScale gi_scale_from_sum(float S) {
-    GiScale r;
-    r.poison = !(S < 3.0e38f);  // inf or NaN somewhere in this CTA's gradients
-    int ex = 0;
-    if (!r.poison && S > 0.f) frexpf(S, &ex);  // S < 2^ex
-    int e = 29 - ex;
-    e = max(-120, min(120, e));
-    r.scale = ldexpf(1.f, e);
-    r.inv = ldexpf(1.f, -e);
-    return r;
-}
-__device__ __forceinline__ void gi_add(int* cell, float v_scaled) { atomicAdd(cell, __float2int_rn(v_scaled)); }
-
 // ACC: grad_weight / grad_offset are added to (fixed-affinity T-step loop) instead of written.
 // CS : compile-time channel stride H*W (0 = runtime), see spn_forward.cu.
 // TH : rows per CTA.  `mode` is a runtime, warp-uniform switch.

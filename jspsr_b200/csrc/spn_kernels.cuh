@@ -148,6 +148,32 @@ __device__ __noinline__ SlowTap slow_tap(const T* __restrict__ init_b, const Geo
     return t;
 }
 
+// Block-floating-point accumulation tile for the gradient scatters (grad_init, grad_confidence): see spn_backward.cu
+struct GiScale {
+    float scale, inv;
+    int poison;
+};
+__device__ __forceinline__ GiScale gi_scale_from_sum(float S) {
+    GiScale r;
+    r.poison = !(S < 3.0e38f);  // inf or NaN somewhere in this CTA's gradients
+    int ex = 0;
+    if (!r.poison && S > 0.f) frexpf(S, &ex);  // S < 2^ex
+    int e = 30 - ex;  // S * 2^e < 2^30; the per-add rounding slack (<= 0.5 each) keeps every cell below 2^31
+    e = max(-120, min(120, e));
+    r.scale = ldexpf(1.f, e);
+    r.inv = ldexpf(1.f, -e);
+    return r;
+}
+__device__ __forceinline__ void gi_add(int* cell, float v_scaled) { atomicAdd(cell, __float2int_rn(v_scaled)); }
+// Two-tile form for scales that come from a loose bound: the rounding residual of the coarse add goes, in units
+// of 2^-16 of the coarse quantum, into a second integer tile (|residual| <= 2^15 per add, so 2^15 adds cannot
+// overflow it): 16 more bits of precision for one more native atomic.
+__device__ __forceinline__ void gi_add2(int* cell, int* cell_lo, float v_scaled) {
+    const int hi = __float2int_rn(v_scaled);
+    atomicAdd(cell, hi);
+    atomicAdd(cell_lo, __float2int_rn((v_scaled - (float)hi) * 65536.f));
+}
+
 // per-variant entry points used by abi.cu
 cudaError_t launch_spn_forward(const LaunchArgs& la);
 cudaError_t launch_spn_backward(const LaunchArgs& la);
