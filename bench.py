@@ -408,7 +408,16 @@ def side_numbers(torch, F, device, B):
                       "fwd_frac_of_hbm_peak": FWD_BYTES["bf16"] * npix / (f * 1e-3) / 1e9 / peak,
                       "bwd_frac_of_hbm_peak": BWD_BYTES["bf16"] * npix / (g * 1e-3) / 1e9 / peak,
                       "note": "bf16 I/O, fp32 arithmetic; issue-bound (see profiles/r01_summary.md), not HBM-bound"}
-    del init, weight, offset, gout
+    # torch.autocast(bfloat16) training: bf16 weight/offset from the Generator, fp32 DEM and grad_out (JSPSR_MIXED kernels)
+    init32, gout32 = init.float(), gout.float()
+    f = timed(lambda: F.spn_forward(init32, weight, offset, w, b, 1, 1.0))
+    g = timed(lambda: F.spn_backward(gout32, init32, weight, offset, w, 1, 1.0, need_grad_init=False))
+    out["autocast_bf16"] = {"fwd_ms": f, "bwd_ms": g, "gpix_iter_per_s_fwd_bwd": npix / ((f + g) * 1e-3) / 1e9,
+                            "fwd_frac_of_hbm_peak": 62 * npix / (f * 1e-3) / 1e9 / peak,
+                            "bwd_frac_of_hbm_peak": (8 + 54 + 54) * npix / (g * 1e-3) / 1e9 / peak,
+                            "note": "bf16 weight/offset and their gradients, fp32 DEM / out / grad_out: 62 B/pixel forward, "
+                                    "116 backward; issue-bound like the all-bf16 kernels"}
+    del init, weight, offset, gout, init32, gout32
     init, weight, offset, gout, w, b = make_inputs(torch, B, device, torch.float32, 4322)
     g = timed(lambda: F.spn_backward(gout, init, weight, offset, w, 1, 1.0, need_grad_init=True))
     out["backward_with_grad_init"] = {"ms": g, "frac_of_hbm_peak": 228 * npix / (g * 1e-3) / 1e9 / peak,

@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 101 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 102 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,
@@ -57,7 +57,14 @@ typedef enum {
     JSPSR_NORM_SUM = 2       /* m_k = a_k / sum_j a_j: spn.py:102-103, LRRU.py:270-271 */
 } jspsr_norm_mode;
 
-typedef enum { JSPSR_F32 = 0, JSPSR_BF16 = 1 } jspsr_dtype;
+typedef enum {
+    JSPSR_F32 = 0,
+    JSPSR_BF16 = 1,
+    JSPSR_MIXED = 2 /* jspsr_spn_forward / jspsr_spn_backward only: weight, offset and their gradients bf16;
+                       init, out and grad_out fp32 - the tensors torch.autocast(bfloat16) hands to
+                       PostProcessor.forward (bf16 Generator outputs, fp32 DEM), which torchvision's
+                       operator promotes to fp32 */
+} jspsr_dtype;
 
 /* NLSPN affinity flavours, models/components/nlspn.py:35-56,92-99,162-166 */
 typedef enum { JSPSR_AFF_AS = 0, JSPSR_AFF_ASS = 1, JSPSR_AFF_TC = 2, JSPSR_AFF_TGASS = 3 } jspsr_affinity;

@@ -14,7 +14,7 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libjspsr_spn.so")
 
 NORM_NONE, NORM_RESIDUAL, NORM_SUM = 0, 1, 2
-F32, BF16 = 0, 1
+F32, BF16, MIXED = 0, 1, 2  # MIXED: bf16 weight/offset (+ gradients), fp32 init/out/grad_out (torch.autocast)
 AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 BWD_ACCUMULATE = 1
 

@@ -127,7 +127,8 @@ static int check_common(int B, int H, int W, int norm_mode, int dtype) {
     if (H > (1 << 24) || W > (1 << 24))
         return fail(JSPSR_ERR_UNSUPPORTED, "H and W are limited to 2^24 (fp32 pixel coordinates must be exact)");
     if (norm_mode < 0 || norm_mode > 2) return fail(JSPSR_ERR_BAD_ARG, "norm_mode %d is not 0/1/2", norm_mode);
-    if (dtype != JSPSR_F32 && dtype != JSPSR_BF16) return fail(JSPSR_ERR_BAD_ARG, "dtype %d is not 0 (f32) / 1 (bf16)", dtype);
+    if (dtype != JSPSR_F32 && dtype != JSPSR_BF16 && dtype != JSPSR_MIXED)
+        return fail(JSPSR_ERR_BAD_ARG, "dtype %d is not 0 (f32) / 1 (bf16) / 2 (mixed)", dtype);
     return 0;
 }
 static int check_align(const void* p, size_t a, const char* name) {
@@ -177,20 +178,22 @@ int jspsr_spn_forward_strip(const void* init, const void* weight, const void* of
         H_img > (1 << 24))
         return fail(JSPSR_ERR_BAD_ARG, "inconsistent strip geometry (Hs=%d H_img=%d row0=%d init_row0=%d init_rows=%d)", Hs,
                     H_img, row0, init_row0, init_rows);
-    const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
-    if (int e = check_align(init, es, "init")) return e;
+    const size_t es = dtype == JSPSR_F32 ? 4 : 2;      // weight / offset
+    const size_t esi = dtype == JSPSR_BF16 ? 2 : 4;    // init / out
+    if (int e = check_align(init, esi, "init")) return e;
     if (int e = check_align(weight, es, "weight")) return e;
     if (int e = check_align(offset, es, "offset")) return e;
-    if (int e = check_align(out, es, "out")) return e;
+    if (int e = check_align(out, esi, "out")) return e;
     if (int e = check_align(w9, 4, "w9")) return e;
     if (int e = check_align(b1, 4, "b1")) return e;
     LaunchArgs la;
     if (int e = fill_geom(&la, B, Hs, W, H_img, row0, init_row0, init_rows, 16)) return e;
     la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9; la.b1 = b1; la.out = out;
-    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.status = status;
+    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
+    la.status = status;
     la.stream = (cudaStream_t)stream;
     const bool wide = choose_wide(W);
-    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, la.bf16, la.tile_h, wide);
+    la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, dtype == JSPSR_BF16, la.tile_h, wide);
     cudaError_t ce = wide ? wide::launch_spn_forward(la) : narrow::launch_spn_forward(la);
     if (ce != cudaSuccess) return cuda_fail(ce, "spn_forward launch");
     return JSPSR_OK;
@@ -215,9 +218,10 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     if ((flags & JSPSR_BWD_ACCUMULATE) && !grad_init)
         return fail(JSPSR_ERR_UNSUPPORTED, "JSPSR_BWD_ACCUMULATE is implemented for the fixed-affinity loop only "
                                            "(grad_init required)");
-    const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
-    if (int e = check_align(grad_out, es, "grad_out")) return e;
-    if (int e = check_align(init, es, "init")) return e;
+    const size_t es = dtype == JSPSR_F32 ? 4 : 2;      // weight / offset and their gradients
+    const size_t esi = dtype == JSPSR_BF16 ? 2 : 4;    // grad_out / init
+    if (int e = check_align(grad_out, esi, "grad_out")) return e;
+    if (int e = check_align(init, esi, "init")) return e;
     if (int e = check_align(weight, es, "weight")) return e;
     if (int e = check_align(offset, es, "offset")) return e;
     if (int e = check_align(grad_weight, es, "grad_weight")) return e;
@@ -230,9 +234,10 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     la.grad_init = grad_init; la.grad_weight = grad_weight; la.grad_offset = grad_offset;
     la.grad_w9 = grad_w9; la.grad_b1 = grad_b1; la.workspace = workspace;
     la.accumulate = (flags & JSPSR_BWD_ACCUMULATE) != 0;
-    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_BF16; la.stream = (cudaStream_t)stream;
+    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
+    la.stream = (cudaStream_t)stream;
     const bool wide = choose_wide(W);
-    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, la.bf16, la.tile_h, wide);
+    la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, dtype == JSPSR_BF16, la.tile_h, wide);
     if (grad_init) {
         cudaError_t ce = cudaMemsetAsync(grad_init, 0, (size_t)B * H * W * sizeof(float), la.stream);
         if (ce != cudaSuccess) return cuda_fail(ce, "grad_init memset");
@@ -282,6 +287,7 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
 
 int jspsr_spn_offset_absmax(const void* offset, int B, int H, int W, int dtype, float* out2, void* stream) {
     if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (dtype == JSPSR_MIXED) return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_spn_offset_absmax: the mixed dtype is implemented for jspsr_spn_forward/backward");
     if (!offset || !out2) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
     cudaError_t ce = launch_offset_absmax(offset, 0, (size_t)H * W, B, dtype == JSPSR_BF16, out2, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "offset_absmax launch");
@@ -292,6 +298,7 @@ int jspsr_spn_iterate(const void* feat_init, const void* aff, const void* offset
                       const void* mask_fix, void* list_out, void* scratch, int B, int H, int W, int T, int dtype,
                       void* stream) {
     if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (dtype == JSPSR_MIXED) return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_spn_iterate: the mixed dtype is implemented for jspsr_spn_forward/backward");
     if (T <= 0) return fail(JSPSR_ERR_BAD_ARG, "T=%d must be positive", T);
     if (!feat_init || !aff || !offset || !list_out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
     if ((feat_fix == nullptr) != (mask_fix == nullptr))
@@ -345,6 +352,7 @@ int jspsr_nlspn_affinity_forward(const void* conv_out, const void* confidence, c
                                  int dtype, void* stream) {
     if (int e = check_common(B, H, W, 0, dtype)) return e;
     if (!conv_out || !offset_out || !aff_out || !aff_scale_const) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
+    if (dtype == JSPSR_MIXED) return fail(JSPSR_ERR_UNSUPPORTED, "the mixed dtype is implemented for jspsr_spn_forward/backward");
     if (affinity < 0 || affinity > 3) return fail(JSPSR_ERR_BAD_ARG, "affinity %d is not AS/ASS/TC/TGASS", affinity);
     if (legacy && !confidence) return fail(JSPSR_ERR_BAD_ARG, "legacy only has an effect with confidence propagation");
     LaunchArgs la;  // geometry + TMA descriptor of the confidence map (the staged tensor of this kernel)
@@ -370,6 +378,7 @@ int jspsr_nlspn_affinity_backward(const void* grad_offset, const void* grad_aff,
     if (int e = check_common(B, H, W, 0, dtype)) return e;
     if (!grad_offset || !grad_aff || !conv_out || !grad_conv_out || !aff_scale_const)
         return fail(JSPSR_ERR_BAD_ARG, "null pointer");
+    if (dtype == JSPSR_MIXED) return fail(JSPSR_ERR_UNSUPPORTED, "the mixed dtype is implemented for jspsr_spn_forward/backward");
     if (affinity < 0 || affinity > 3) return fail(JSPSR_ERR_BAD_ARG, "affinity %d is not AS/ASS/TC/TGASS", affinity);
     if (grad_scale && !workspace) return fail(JSPSR_ERR_BAD_ARG, "workspace is required when grad_scale is requested");
     if (grad_confidence && !confidence) return fail(JSPSR_ERR_BAD_ARG, "grad_confidence without confidence");

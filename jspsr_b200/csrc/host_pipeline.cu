@@ -26,6 +26,8 @@ extern "C" int jspsr_spn_forward_host(const void* init, const void* weight, cons
                                       int dtype, void* dev_scratch, size_t scratch_bytes, int chunk_B) {
     if (!init || !weight || !offset || !w9 || !b1 || !out || !dev_scratch || chunk_B <= 0 || B <= 0 || H <= 0 || W <= 0)
         return jspsr_internal_fail(JSPSR_ERR_BAD_ARG, "forward_host: null pointer or non-positive dimension");
+    if (dtype != JSPSR_F32 && dtype != JSPSR_BF16)
+        return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "forward_host: dtype must be 0 (f32) or 1 (bf16)");
     if (scratch_bytes < jspsr_spn_host_scratch_bytes(chunk_B, H, W, dtype))
         return jspsr_internal_fail(JSPSR_ERR_BAD_ARG, "forward_host: dev_scratch is smaller than jspsr_spn_host_scratch_bytes()");
     const size_t es = dtype == JSPSR_BF16 ? 2 : 4;

@@ -34,16 +34,17 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
 // ACC: grad_weight / grad_offset are added to (fixed-affinity T-step loop) instead of written.
 // CS : compile-time channel stride H*W (0 = runtime), see spn_forward.cu.
 // TH : rows per CTA.  `mode` is a runtime, warp-uniform switch.
-template <typename T, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH>
+// T: element type of weight / offset and their gradients; TI: element type of grad_out / init (see spn_forward.cu).
+template <typename T, typename TI, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH>
 __global__ void __launch_bounds__(THREADS, sizeof(T) == 2 ? BWD_MIN_BLOCKS_BF16 : BWD_MIN_BLOCKS)
-spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, const T* __restrict__ weight,
+spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, const T* __restrict__ weight,
                     const T* __restrict__ offset, const float* __restrict__ w9, float* __restrict__ grad_init,
                     T* __restrict__ grad_weight, T* __restrict__ grad_offset, float* __restrict__ grad_w9,
                     float* __restrict__ grad_b1, ReduceWs* __restrict__ ws, const Geom g, const int mode,
                     const float scale, const __grid_constant__ CUtensorMap tmap) {
     constexpr int SH = staged_rows(TH);
     constexpr int PPT = pixels_per_thread(TH);
-    __shared__ __align__(128) T tile[SH * SW];
+    __shared__ __align__(128) TI tile[SH * SW];
     __shared__ __align__(16) int gtile[GRAD_INIT ? SH * SW : 4];  // fixed-point accumulation tile
     __shared__ float s_gi[WARPS];
     __shared__ GiScale s_gis;
@@ -53,7 +54,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     __shared__ bool s_last;
 
     const TileCtx c = make_tile_ctx<TH>(g);
-    stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
+    stage_tile_begin<TI, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
     if (GRAD_INIT) {
         for (int i = threadIdx.x; i < SH * SW / 4; i += THREADS) reinterpret_cast<int4*>(gtile)[i] = make_int4(0, 0, 0, 0);
@@ -62,14 +63,14 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t cs = CS ? (size_t)CS : (size_t)g.H * g.W;
     const size_t csb = cs * sizeof(T);  // channel stride in bytes
-    const T* gout_b = gout + (size_t)c.b * cs;
+    const TI* gout_b = gout + (size_t)c.b * cs;
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
-    const T* init_b = init + (size_t)c.b * g.init_rows * g.W;
+    const TI* init_b = init + (size_t)c.b * g.init_rows * g.W;
     T* gwgt_b = grad_weight + (size_t)c.b * 9 * cs;
     T* goff_b = grad_offset + (size_t)c.b * 18 * cs;
     float* gi_b = GRAD_INIT ? grad_init + (size_t)c.b * g.init_rows * g.W : nullptr;
-    const T* tile_lo = tile + c.r_lo * SW;
+    const TI* tile_lo = tile + c.r_lo * SW;
     int* gtile_lo = gtile + (GRAD_INIT ? c.r_lo * SW : 0);
 
     float a[9], oh[9], ow[9], go;
@@ -182,7 +183,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
         acc_b += go;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const FastTap t = fast_tap<T>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+            const FastTap t = fast_tap<TI>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
             // value and both derivatives (torchvision get_coordinate_weight) share the two row differences
             const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
             const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
@@ -224,7 +225,7 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
             for (int k = 0; k < 9; ++k) {
                 if (slow & (1u << k)) {
                     const float h = hk[k / 3] + oh[k], w = wk[k % 3] + ow[k];
-                    const SlowTap t = slow_tap<T>(init_b, g, h, w, nullptr);
+                    const SlowTap t = slow_tap<TI>(init_b, g, h, w, nullptr);
                     const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
                     const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
                     const float dh = bot - top, val = fmaf(t.lh, dh, top), dw = fmaf(t.lh, d43 - d21, d21);
@@ -336,51 +337,52 @@ spn_backward_kernel(const T* __restrict__ gout, const T* __restrict__ init, cons
     }
 }
 
-template <typename T, bool TMA, bool GI, bool ACC, int CS, int TH>
+template <typename T, typename TI, bool TMA, bool GI, bool ACC, int CS, int TH>
 static void launch_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_backward_kernel<T, TMA, GI, ACC, CS, TH><<<grid, THREADS, 0, la.stream>>>(
-        (const T*)la.grad_out, (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.grad_init,
+    spn_backward_kernel<T, TI, TMA, GI, ACC, CS, TH><<<grid, THREADS, 0, la.stream>>>(
+        (const TI*)la.grad_out, (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.grad_init,
         (T*)la.grad_weight, (T*)la.grad_offset, la.grad_w9, la.grad_b1, (ReduceWs*)la.workspace, la.g, la.mode,
         la.scale, la.tmap);
 }
 
 // (TMA, CS) variants: the compile-time stride only exists for 128x128-pixel planes, which always qualify for TMA
-template <typename T, bool GI, bool ACC, int TH>
+template <typename T, typename TI, bool GI, bool ACC, int TH>
 static void launch_variant(const LaunchArgs& la) {
     const size_t cs = (size_t)la.g.H * la.g.W;
-    if (la.use_tma && cs == 16384) launch_one<T, true, GI, ACC, 16384, TH>(la);
-    else if (la.use_tma) launch_one<T, true, GI, ACC, 0, TH>(la);
-    else launch_one<T, false, GI, ACC, 0, TH>(la);
+    if (la.use_tma && cs == 16384) launch_one<T, TI, true, GI, ACC, 16384, TH>(la);
+    else if (la.use_tma) launch_one<T, TI, true, GI, ACC, 0, TH>(la);
+    else launch_one<T, TI, false, GI, ACC, 0, TH>(la);
 }
 
-template <typename T, int TH>
+template <typename T, typename TI, int TH>
 static cudaError_t launch_bwd_th(const LaunchArgs& la) {
     const bool gi = la.grad_init != nullptr;
     if (la.accumulate) {
         // only the fixed-affinity loop accumulates (NLSPN backward: grad_init always needed)
         if (!gi) return cudaErrorNotSupported;
-        launch_variant<T, true, true, TH>(la);
+        launch_variant<T, TI, true, true, TH>(la);
     } else if (gi) {
-        launch_variant<T, true, false, TH>(la);
+        launch_variant<T, TI, true, false, TH>(la);
     } else {
-        launch_variant<T, false, false, TH>(la);
+        launch_variant<T, TI, false, false, TH>(la);
     }
     return cudaGetLastError();
 }
 
-template <typename T>
+template <typename T, typename TI>
 static cudaError_t launch_bwd_dtype(const LaunchArgs& la) {
     switch (la.tile_h) {
-        case 8: return launch_bwd_th<T, 8>(la);
-        case 4: return launch_bwd_th<T, 4>(la);
-        case 2: return launch_bwd_th<T, 2>(la);
+        case 8: return launch_bwd_th<T, TI, 8>(la);
+        case 4: return launch_bwd_th<T, TI, 4>(la);
+        case 2: return launch_bwd_th<T, TI, 2>(la);
         default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t launch_spn_backward(const LaunchArgs& la) {
-    return la.bf16 ? launch_bwd_dtype<__nv_bfloat16>(la) : launch_bwd_dtype<float>(la);
+    if (la.bf16 && la.init_f32) return launch_bwd_dtype<__nv_bfloat16, float>(la);
+    return la.bf16 ? launch_bwd_dtype<__nv_bfloat16, __nv_bfloat16>(la) : launch_bwd_dtype<float, float>(la);
 }
 
 }  // namespace JSPSR_VARIANT

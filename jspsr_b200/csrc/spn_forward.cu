@@ -19,20 +19,22 @@ inline namespace JSPSR_VARIANT {
 // 128-byte aligned; when they are not (W*sizeof(T) % 128 != 0) a warp's 128-byte request straddles
 // DRAM granules and only the linear mapping, where the four warps of a row issue together, lets L2
 // merge them (measured at W = 2004: 11.1 GB read from DRAM for 7.5 GB of data with the row mapping).
-template <typename T, bool TMA, int CS, int TH, bool LINEAR>
+// T: element type of weight / offset; TI: element type of init / out (TI = float with T = bf16 is what
+// torch.autocast produces: bf16 Generator outputs, fp32 DEM; torchvision's operator promotes to fp32 there).
+template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR>
 __global__ void __launch_bounds__(THREADS, FWD_MIN_BLOCKS)
-spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, const T* __restrict__ offset,
-                   const float* __restrict__ w9, const float* __restrict__ b1, T* __restrict__ out, const Geom g,
+spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, const T* __restrict__ offset,
+                   const float* __restrict__ w9, const float* __restrict__ b1, TI* __restrict__ out, const Geom g,
                    const int mode, const float scale, int* __restrict__ status,
                    const __grid_constant__ CUtensorMap tmap) {
     constexpr int SH = staged_rows(TH);
     constexpr int PPT = pixels_per_thread(TH);
-    __shared__ __align__(128) T tile[SH * SW];
+    __shared__ __align__(128) TI tile[SH * SW];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_w[10];
 
     const TileCtx c = make_tile_ctx<TH>(g);
-    stage_tile_begin<T, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
+    stage_tile_begin<TI, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     // w9 == nullptr: frozen unit weight / zero bias (NLSPN, nlspn.py:61-65)
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
     if (threadIdx.x == 9) s_w[9] = b1 ? b1[0] : 0.f;
@@ -41,9 +43,9 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     const size_t csb = cs * sizeof(T);  // channel stride in bytes  // channel stride
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
-    const T* init_b = init + (size_t)c.b * g.init_rows * g.W;
-    T* out_b = out + (size_t)c.b * cs;
-    const T* tile_lo = tile + c.r_lo * SW;
+    const TI* init_b = init + (size_t)c.b * g.init_rows * g.W;
+    TI* out_b = out + (size_t)c.b * cs;
+    const TI* tile_lo = tile + c.r_lo * SW;
 
     // pixel `it` of this thread: linear index it*256 + tid in the TH x 128 block (a warp = 32 consecutive x)
     struct PixelIn {
@@ -116,7 +118,7 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
         unsigned slow = 0u;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const FastTap t = fast_tap<T>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+            const FastTap t = fast_tap<TI>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
             const float val = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
             a[k] = t.ok ? (s_w[k] * a[k]) * val : a[k];
             slow |= t.ok ? 0u : (1u << k);
@@ -125,7 +127,7 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 if (slow & (1u << k)) {
-                    const SlowTap t = slow_tap<T>(init_b, g, hk[k / 3] + oh[k], wk[k % 3] + ow[k], status);
+                    const SlowTap t = slow_tap<TI>(init_b, g, hk[k / 3] + oh[k], wk[k % 3] + ow[k], status);
                     a[k] = (s_w[k] * a[k]) * bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
                 }
             }
@@ -153,33 +155,33 @@ spn_forward_kernel(const T* __restrict__ init, const T* __restrict__ weight, con
     }
 }
 
-template <typename T, bool TMA, int CS, int TH, bool LINEAR>
+template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR>
 static void launch_fwd_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_forward_kernel<T, TMA, CS, TH, LINEAR><<<grid, THREADS, 0, la.stream>>>(
-        (const T*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (T*)la.out, la.g, la.mode, la.scale,
+    spn_forward_kernel<T, TI, TMA, CS, TH, LINEAR><<<grid, THREADS, 0, la.stream>>>(
+        (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (TI*)la.out, la.g, la.mode, la.scale,
         la.status, la.tmap);
 }
 
 // (TMA, CS, LINEAR) variants: the compile-time stride only exists for 128x128-pixel planes (always
 // TMA-able and row-aligned); rows that are not 128-byte aligned use the linear mapping
-template <typename T, int TH>
+template <typename T, typename TI, int TH>
 static void launch_fwd_th(const LaunchArgs& la) {
     const size_t cs = (size_t)la.g.H * la.g.W;
     const bool aligned = ((size_t)la.g.W * sizeof(T)) % 128 == 0;
-    if (la.use_tma && cs == 16384 && aligned) launch_fwd_one<T, true, 16384, TH, false>(la);
-    else if (la.use_tma && aligned) launch_fwd_one<T, true, 0, TH, false>(la);
-    else if (la.use_tma) launch_fwd_one<T, true, 0, TH, true>(la);
-    else launch_fwd_one<T, false, 0, TH, true>(la);
+    if (la.use_tma && cs == 16384 && aligned) launch_fwd_one<T, TI, true, 16384, TH, false>(la);
+    else if (la.use_tma && aligned) launch_fwd_one<T, TI, true, 0, TH, false>(la);
+    else if (la.use_tma) launch_fwd_one<T, TI, true, 0, TH, true>(la);
+    else launch_fwd_one<T, TI, false, 0, TH, true>(la);
 }
 
-template <typename T>
+template <typename T, typename TI>
 static cudaError_t launch_fwd_dtype(const LaunchArgs& la) {
     switch (la.tile_h) {
-        case 16: launch_fwd_th<T, 16>(la); break;
-        case 8: launch_fwd_th<T, 8>(la); break;
-        case 4: launch_fwd_th<T, 4>(la); break;
-        case 2: launch_fwd_th<T, 2>(la); break;
+        case 16: launch_fwd_th<T, TI, 16>(la); break;
+        case 8: launch_fwd_th<T, TI, 8>(la); break;
+        case 4: launch_fwd_th<T, TI, 4>(la); break;
+        case 2: launch_fwd_th<T, TI, 2>(la); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -189,7 +191,8 @@ int stage_box_cols() { return SW; }
 int stage_box_rows(int th) { return staged_rows(th); }
 
 cudaError_t launch_spn_forward(const LaunchArgs& la) {
-    return la.bf16 ? launch_fwd_dtype<__nv_bfloat16>(la) : launch_fwd_dtype<float>(la);
+    if (la.bf16 && la.init_f32) return launch_fwd_dtype<__nv_bfloat16, float>(la);
+    return la.bf16 ? launch_fwd_dtype<__nv_bfloat16, __nv_bfloat16>(la) : launch_fwd_dtype<float, float>(la);
 }
 
 }  // namespace JSPSR_VARIANT

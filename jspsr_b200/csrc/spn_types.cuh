@@ -44,7 +44,8 @@ struct LaunchArgs {
     Geom g{};
     int mode = NORM_RESIDUAL;
     float scale = 1.f;
-    bool bf16 = false;
+    bool bf16 = false;      // weight / offset (and their gradients) are bf16
+    bool init_f32 = false;  // with bf16: init / out / grad_out stay fp32 (JSPSR_MIXED, what torch.autocast produces)
     bool use_tma = false;
     int* status = nullptr;
     int tile_h = 16;  // rows per CTA (16 / 8 / 4 / 2), chosen by abi.cu; the TMA box is encoded to match

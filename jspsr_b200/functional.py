@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import BF16, BWD_ACCUMULATE, F32, NORM_NONE, NORM_RESIDUAL, NORM_SUM  # noqa: F401
+from ._lib import BF16, BWD_ACCUMULATE, F32, MIXED, NORM_NONE, NORM_RESIDUAL, NORM_SUM  # noqa: F401
 
 _workspaces = {}
 _launches = 0  # kernels of libjspsr_spn.so enqueued through this module (bench.py reports it)
@@ -69,9 +69,18 @@ def _check_shapes(init, weight, offset):
         raise RuntimeError(f"mask/weight must be [B,9,H,W] = {(B, 9, H, W)}, got {tuple(weight.shape)}")
     if offset.dim() != 4 or offset.shape[1] % 18 != 0 or tuple(offset.shape) != (B, 18, H, W):
         raise RuntimeError(f"offset must be [B,2*3*3,H,W] = {(B, 18, H, W)}, got {tuple(offset.shape)}")
-    if not (init.dtype == weight.dtype == offset.dtype):
-        raise RuntimeError("init, weight and offset must share one dtype")
+    if weight.dtype != offset.dtype or not (init.dtype == weight.dtype or _is_mixed(init, weight)):
+        raise RuntimeError("init, weight and offset must share one dtype (or: float32 init with bfloat16 weight/offset)")
     return B, H, W
+
+
+def _is_mixed(init, weight) -> bool:
+    """fp32 DEM with bf16 affinities/offsets: what torch.autocast(bfloat16) hands to PostProcessor.forward."""
+    return init.dtype == torch.float32 and weight.dtype == torch.bfloat16
+
+
+def _io_code(init, weight) -> int:
+    return MIXED if _is_mixed(init, weight) else _dtype_code(init)
 
 
 def _w9(w: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
@@ -94,7 +103,7 @@ def spn_forward(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) 
     out = torch.empty_like(init)
     with torch.cuda.device(init.device):
         rc = _lib.lib().jspsr_spn_forward(_ptr(init), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1), _ptr(out),
-                                          B, H, W, norm_mode, float(scale), _dtype_code(init), _stream_ptr(init))
+                                          B, H, W, norm_mode, float(scale), _io_code(init, weight), _stream_ptr(init))
     _lib.check(rc, "jspsr_spn_forward")
     _count()
     return out
@@ -124,7 +133,7 @@ def spn_backward(grad_out, init, weight, offset, w, norm_mode: int, scale: float
         rc = _lib.lib().jspsr_spn_backward(_ptr(grad_out), _ptr(init), _ptr(weight), _ptr(offset), _ptr(w9),
                                            _ptr(grad_init), _ptr(grad_weight), _ptr(grad_offset), _ptr(grad_w),
                                            _ptr(grad_b), _ptr(ws), B, H, W, norm_mode, float(scale),
-                                           _dtype_code(init), flags, _stream_ptr(init))
+                                           _io_code(init, weight), flags, _stream_ptr(init))
     _lib.check(rc, "jspsr_spn_backward")
     _count()
     return grad_init, grad_weight, grad_offset, grad_w, grad_b
@@ -338,13 +347,15 @@ def gen_propagate(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: fl
     return _GenPropagate.apply(init, feature, conv_w, conv_b, w, b, norm_mode, scale)
 
 
-def _common_dtype(*tensors):
-    """Mixed dtypes (e.g. under torch.autocast, where torchvision's operator casts everything to fp32):
-    promote to float32; a uniform bf16 / fp32 set is used as is."""
-    dts = {t.dtype for t in tensors}
-    if len(dts) == 1:
-        return tensors
-    return tuple(t.float() for t in tensors)
+def _common_dtype(init, weight, offset):
+    """A uniform bf16 / fp32 set is used as is, and so is fp32 init with bf16 weight/offset (torch.autocast: the
+    kernels read that combination directly - torchvision's operator casts everything to fp32 there, which is the
+    same arithmetic).  Any other mix is promoted to float32."""
+    if init.dtype == weight.dtype == offset.dtype:
+        return init, weight, offset
+    if weight.dtype == offset.dtype and _is_mixed(init, weight):
+        return init, weight, offset
+    return init.float(), weight.float(), offset.float()
 
 
 def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) -> torch.Tensor:

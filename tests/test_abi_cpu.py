@@ -39,7 +39,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_workspace(lib):
     h = lib.lib()
-    assert h.jspsr_version() == 101
+    assert h.jspsr_version() == 102
     assert 64 <= h.jspsr_spn_workspace_bytes() <= 4096
     assert h.jspsr_spn_host_scratch_bytes(2, 128, 128, 0) >= 2 * 2 * 128 * 128 * 4 * 29
 
@@ -58,6 +58,8 @@ def test_argument_validation_needs_no_gpu(lib):
         (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 1, None), -2, "fp32"),
         (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, one, None, 1, 64, 8, 8, 1, 1.0, 0, None), -1, "together"),
         (lambda: h.jspsr_gen_spn_forward(one, one, ctypes.c_void_p(20), one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 0, None), -4, "conv_w"),
+        (lambda: h.jspsr_spn_iterate(one, one, one, None, None, one, None, 1, 8, 8, 2, 2, None), -2, "mixed"),
+        (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 8, 8, 1, 1.0, 3, None), -1, "dtype"),
         (lambda: h.jspsr_spn_iterate(one, one, one, None, None, one, None, 1, 8, 8, 0, 0, None), -1, "T="),
         (lambda: h.jspsr_spn_iterate(one, one, one, one, None, one, None, 1, 8, 8, 2, 0, None), -1, "together"),
         (lambda: h.jspsr_spn_forward_strip(one, one, one, one, one, one, 1, 8, 8, 4, 0, 0, 4, 1, 1.0, 0, None, None), -1,
