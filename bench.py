@@ -452,6 +452,9 @@ def side_numbers(torch, F, device, B):
         return F.spn_forward(init, weight, torch.cat(lo, dim=1).view(B, -1, TILE, TILE), w, b, 1, 1.0)
 
     un = timed(unfused, n=3)
+    feat16 = feat.bfloat16()
+    fused16 = timed(lambda: F.gen_spn_forward(init, feat16, cw, cb, w, b, 1, 1.0, False))
+    fused16_wo = timed(lambda: F.gen_spn_forward(init, feat16, cw, cb, w, b, 1, 1.0, True))
     by = (C * 4 + 8) * npix
     out["generator_tail_fused"] = {
         "ms": fused, "gpix_per_s": npix / (fused * 1e-3) / 1e9, "algorithmic_bytes_per_pixel": C * 4 + 8,
@@ -459,6 +462,10 @@ def side_numbers(torch, F, device, B):
         "ms_with_weight_offset_written": fused_wo,
         "frac_of_hbm_peak_with_weight_offset_written": (by + 108 * npix) / (fused_wo * 1e-3) / 1e9 / peak,
         "unfused_ms": un, "speedup_vs_unfused": un / fused,
+        "autocast_bf16_features": {"ms": fused16, "frac_of_hbm_peak": (C * 2 + 8) * npix / (fused16 * 1e-3) / 1e9 / peak,
+                                   "ms_with_weight_offset_written": fused16_wo,
+                                   "frac_of_hbm_peak_with_weight_offset_written":
+                                       (C * 2 + 8 + 54) * npix / (fused16_wo * 1e-3) / 1e9 / peak},
         "note": "gen_spn_forward_kernel: TMA ring -> tf32 hi/lo split into TMEM lanes -> tcgen05.mma (A from TMEM, "
                 "3-product split, fp32-level accuracy) -> per-pixel epilogue + 9-tap gather; unfused = torch 1x1 "
                 "convolutions (TF32 allowed, torch's default) + sigmoid + chunk/insert/cat + spn_forward_kernel"}

@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 102 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 103 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,
@@ -137,7 +137,10 @@ int jspsr_spn_forward_strip(const void *init, const void *weight, const void *of
  * conv_b [25] the two biases in the same order (all on device, conv_w 16-byte aligned).
  * The contraction runs on the tensor cores (tcgen05, tf32 with a 3-product split: fp32-level accuracy).
  * weight_out [B,9,H,W] / offset_out [B,18,H,W]: both NULL (inference) or both given - they receive what
- * the Generator would have returned, which is what jspsr_spn_backward needs.  C = 64, fp32 only.
+ * the Generator would have returned, which is what jspsr_spn_backward needs.  C = 64.
+ * dtype JSPSR_F32: everything fp32.  dtype JSPSR_MIXED (torch.autocast): feature, weight_out, offset_out are
+ * bf16 (init / out fp32); weight and offset are rounded to bf16 before the gather, i.e. `out` is exactly
+ * jspsr_spn_forward(JSPSR_MIXED) of the tensors written.
  */
 int jspsr_gen_spn_forward(const void *init, const void *feature, const float *conv_w,
                           const float *conv_b, const float *w9, const float *b1, void *out,

@@ -108,16 +108,17 @@ static bool make_init_tmap(CUtensorMap* map, const void* init, int B, int rows, 
 }
 
 // TMA descriptor for the feature tensor viewed as [B*C planes][H][W]; box = one 128-pixel row segment of C planes
-static bool make_feature_tmap(CUtensorMap* map, const void* feature, int B, int C, int H, int W) {
+static bool make_feature_tmap(CUtensorMap* map, const void* feature, int B, int C, int H, int W, bool bf16) {
     if (tma_disabled_by_env()) return false;
-    if (((uintptr_t)feature & 15) != 0 || ((size_t)W * 4) % 16 != 0 || C > 256) return false;
+    const size_t es = bf16 ? 2 : 4;
+    if (((uintptr_t)feature & 15) != 0 || ((size_t)W * es) % 16 != 0 || C > 256) return false;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * C};
-    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * 4 * (cuuint64_t)H};
+    cuuint64_t strides[2] = {(cuuint64_t)W * es, (cuuint64_t)W * es * (cuuint64_t)H};
     cuuint32_t box[3] = {(cuuint32_t)TILE_W, 1u, (cuuint32_t)C};
     cuuint32_t estr[3] = {1u, 1u, 1u};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(feature), dims, strides, box, estr,
+    return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(feature), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -251,7 +252,10 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
                           const float* w9, const float* b1, void* out, void* weight_out, void* offset_out, int B, int C,
                           int H, int W, int norm_mode, float scale, int dtype, void* stream) {
     if (int e = check_common(B, H, W, norm_mode, dtype)) return e;
-    if (dtype != JSPSR_F32) return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is implemented for fp32 tensors");
+    if (dtype != JSPSR_F32 && dtype != JSPSR_MIXED)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward: dtype must be 0 (all fp32) or 2 (mixed: bf16 feature / "
+                                           "weight_out / offset_out, fp32 init / out)");
+    const size_t esf = dtype == JSPSR_MIXED ? 2 : 4;
     if (C != 64)
         return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is instantiated for C = 64 feature channels "
                                            "(Generator bc = 16, configs/*.yml num_feature = 32), got C = %d", C);
@@ -259,12 +263,12 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
     if ((weight_out == nullptr) != (offset_out == nullptr))
         return fail(JSPSR_ERR_BAD_ARG, "weight_out and offset_out must be given together");
     if (int e = check_align(init, 4, "init")) return e;
-    if (int e = check_align(feature, 4, "feature")) return e;
+    if (int e = check_align(feature, esf, "feature")) return e;
     if (int e = check_align(conv_w, 16, "conv_w")) return e;
     if (int e = check_align(conv_b, 4, "conv_b")) return e;
     if (int e = check_align(out, 4, "out")) return e;
-    if (int e = check_align(weight_out, 4, "weight_out")) return e;
-    if (int e = check_align(offset_out, 4, "offset_out")) return e;
+    if (int e = check_align(weight_out, esf, "weight_out")) return e;
+    if (int e = check_align(offset_out, esf, "offset_out")) return e;
     LaunchArgs la;
     if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 16)) return e;
     if (la.tile_h < 8) {  // instantiated for 16 and 8 rows per CTA
@@ -272,13 +276,14 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
         la.g.tiles_y = (H + 7) / 8;
     }
     la.init = init; la.w9 = w9; la.b1 = b1; la.out = out;
-    la.mode = norm_mode; la.scale = scale; la.bf16 = false; la.stream = (cudaStream_t)stream;
+    la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_MIXED; la.init_f32 = true;
+    la.stream = (cudaStream_t)stream;
     // the operand buffers leave room for the narrow staged tile at two CTAs per SM (JSPSR_SPN_HALO=wide overrides)
     bool wide = false;
     if (const char* e = getenv("JSPSR_SPN_HALO")) wide = e[0] == 'w';
     CUtensorMap tmap_feat{};
     la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, false, la.tile_h, wide) &&
-                 make_feature_tmap(&tmap_feat, feature, B, C, H, W);
+                 make_feature_tmap(&tmap_feat, feature, B, C, H, W, la.bf16);
     cudaError_t ce = (wide ? wide::launch_gen_spn_forward : narrow::launch_gen_spn_forward)(la, tmap_feat, feature, C, conv_w,
                                                                                             conv_b, weight_out, offset_out);
     if (ce != cudaSuccess) return cuda_fail(ce, "gen_spn_forward launch");

@@ -120,18 +120,23 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 // issue rate); producers + consumers with a producer lane issuing the MMAs: 2.9 ms; dedicated MMA warp: 2.6 ms
 // (producers held at most 64 KB of loads in flight per SM in registers: 0.52 of the HBM roofline by Little's law);
 // this version: 1.52 ms = 0.89 of the HBM roofline (0.98 when weight/offset are also written).
-template <int C, bool TMA, int TH, bool WRITE_WO>
+// FT: element type of feature and of weight_out / offset_out.  bf16 (torch.autocast: Generator.block emits bf16) is
+// exactly representable in tf32, so the lo part and its MMAs vanish (16 MMAs per row), the ring stage halves, and
+// weight / offset are rounded to bf16 BEFORE the gather - what the reference's autocast run propagates, and what
+// makes `out` bit-identical to the propagation kernel applied to the tensors written here.
+template <typename FT, int C, bool TMA, int TH, bool WRITE_WO>
 __global__ void __launch_bounds__(GEN_CTA_THREADS, 2)
-gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__ feature,
+gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ feature,
                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                        const float* __restrict__ w9, const float* __restrict__ b1, float* __restrict__ out,
-                       float* __restrict__ weight_out, float* __restrict__ offset_out, const Geom g, const int mode,
+                       FT* __restrict__ weight_out, FT* __restrict__ offset_out, const Geom g, const int mode,
                        const float scale, const int l2_ahead, const __grid_constant__ CUtensorMap tmap,
                        const __grid_constant__ CUtensorMap tmap_feat) {
     constexpr int SH = staged_rows(TH);
     constexpr uint32_t SBO = 128;                // bytes between 8-row groups of B (rows = output channels)
     constexpr uint32_t LBO_B = GEN_N / 8 * 128;  // bytes between 16-byte K chunks of B: 512
-    constexpr int STAGE_BYTES = GEN_THREADS * C * 4, B_BYTES = GEN_N * C * 4;
+    constexpr bool F16 = sizeof(FT) == 2;
+    constexpr int STAGE_BYTES = GEN_THREADS * C * (int)sizeof(FT), B_BYTES = GEN_N * C * 4;
     constexpr int RING_BYTES = TMA ? GEN_STAGES * STAGE_BYTES : 0;
     constexpr uint32_t COL_A_HI = 0, COL_A_LO = C, COL_ACC = 2 * C;  // TMEM column map
     constexpr uint32_t TMEM_COLS = 256;
@@ -231,7 +236,7 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
                     const uint64_t dbh = umma_desc_kmajor(smem_u32(b_hi) + ks * 2 * LBO_B, LBO_B, SBO);
                     const uint64_t dbm = umma_desc_kmajor(smem_u32(b_mid) + ks * 2 * LBO_B, LBO_B, SBO);
                     umma_tf32_ts(d_tmem, tmem + COL_A_HI + ks * 8, dbh, IDESC, ks > 0 ? 1u : 0u);
-                    umma_tf32_ts(d_tmem, tmem + COL_A_LO + ks * 8, dbh, IDESC, 1u);
+                    if (!F16) umma_tf32_ts(d_tmem, tmem + COL_A_LO + ks * 8, dbh, IDESC, 1u);
                     umma_tf32_ts(d_tmem, tmem + COL_A_HI + ks * 8, dbm, IDESC, 1u);
                 }
                 umma_commit(&bar_a_free[h]);
@@ -241,16 +246,16 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
         }
     } else if (warp >= 4) {
         // =========================== producers ===========================
-        const float* feat_b = feature + (size_t)c.b * C * cs;
+        const FT* feat_b = feature + (size_t)c.b * C * cs;
         __syncthreads();  // setup complete
         const uint32_t lane_tmem = s_tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
         for (int r = 0; r < TH; ++r) {
             const int s = r % GEN_STAGES;
-            const float* stage = reinterpret_cast<const float*>(ring + s * STAGE_BYTES) + px;
+            const FT* stage = reinterpret_cast<const FT*>(ring + s * STAGE_BYTES) + px;
             const int y = c.y0 + r;
             const bool row_ok = col_ok && y < g.H;
-            const float* gp = feat_b + (size_t)y * g.W + x;
+            const FT* gp = feat_b + (size_t)y * g.W + x;
             if (TMA) mbar_wait(&bar_full[s], (uint32_t)((r / GEN_STAGES) & 1));       // the row has landed
 #pragma unroll
             for (int k0 = 0; k0 < C; k0 += 16) {  // 16 channels at a time: ring / HBM -> registers -> hi, lo -> TMEM lane
@@ -262,18 +267,20 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float v;
-                    if (TMA) v = stage[(k0 + j) * GEN_THREADS];
+                    if (TMA) v = to_f32(stage[(k0 + j) * GEN_THREADS]);
                     else v = row_ok ? ld_stream(gp + (size_t)(k0 + j) * cs) : 0.f;
                     hi[j] = v;
                 }
+                if (!F16) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float v = hi[j];
-                    hi[j] = tf32_rn(v);
-                    lo[j] = v - hi[j];
+                    for (int j = 0; j < 16; ++j) {
+                        const float v = hi[j];
+                        hi[j] = tf32_rn(v);
+                        lo[j] = v - hi[j];
+                    }
+                    tmem_st16(lane_tmem + COL_A_LO + k0, lo);
                 }
                 tmem_st16(lane_tmem + COL_A_HI + k0, hi);
-                tmem_st16(lane_tmem + COL_A_LO + k0, lo);
                 if ((k0 + 16) % (C / 2) == 0) {  // a K half is complete: hand it to the MMA warp
                     if (TMA && k0 + 16 == C) mbar_arrive(&bar_empty[s]);  // every read of the stage is in registers
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -324,9 +331,17 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
                     ow[k] = v[10 + 2 * n];
                 }
             }
+            if (F16) {  // the Generator's outputs are bf16 tensors in this mode: propagate exactly what is written
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    a[k] = __bfloat162float(__float2bfloat16_rn(a[k]));
+                    oh[k] = __bfloat162float(__float2bfloat16_rn(oh[k]));
+                    ow[k] = __bfloat162float(__float2bfloat16_rn(ow[k]));
+                }
+            }
             if (WRITE_WO) {
-                float* pw = weight_out + (size_t)c.b * 9 * cs + p;
-                float* po = offset_out + (size_t)c.b * 18 * cs + p;
+                FT* pw = weight_out + (size_t)c.b * 9 * cs + p;
+                FT* po = offset_out + (size_t)c.b * 18 * cs + p;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     st_stream(pw + (size_t)k * cs, a[k]);
@@ -370,46 +385,46 @@ gen_spn_forward_kernel(const float* __restrict__ init, const float* __restrict__
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(TMEM_COLS));
 }
 
-template <int C, bool TMA, int TH, bool WO>
-static cudaError_t launch_gen_one(const LaunchArgs& la, const CUtensorMap& tmap_feat, const float* feature,
-                                  const float* conv_w, const float* conv_b, float* weight_out, float* offset_out) {
-    const size_t dyn = (TMA ? (size_t)GEN_STAGES * GEN_THREADS * C * 4 : 0) + (size_t)2 * GEN_N * C * 4 +
+template <typename FT, int C, bool TMA, int TH, bool WO>
+static cudaError_t launch_gen_one(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature,
+                                  const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
+    const size_t dyn = (TMA ? (size_t)GEN_STAGES * GEN_THREADS * C * sizeof(FT) : 0) + (size_t)2 * GEN_N * C * 4 +
                        (size_t)staged_rows(TH) * SW * 4;
-    static const cudaError_t attr = cudaFuncSetAttribute(gen_spn_forward_kernel<C, TMA, TH, WO>,
+    static const cudaError_t attr = cudaFuncSetAttribute(gen_spn_forward_kernel<FT, C, TMA, TH, WO>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
     int l2_ahead = GEN_L2_AHEAD;
     if (const char* e = getenv("JSPSR_GEN_L2_AHEAD")) l2_ahead = atoi(e);  // experiment switch
-    gen_spn_forward_kernel<C, TMA, TH, WO><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>(
-        (const float*)la.init, feature, conv_w, conv_b, la.w9, la.b1, (float*)la.out, weight_out, offset_out, la.g, la.mode,
-        la.scale, l2_ahead, la.tmap, tmap_feat);
+    gen_spn_forward_kernel<FT, C, TMA, TH, WO><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>(
+        (const float*)la.init, (const FT*)feature, conv_w, conv_b, la.w9, la.b1, (float*)la.out, (FT*)weight_out,
+        (FT*)offset_out, la.g, la.mode, la.scale, l2_ahead, la.tmap, tmap_feat);
     return cudaGetLastError();
 }
 
-template <int C, int TH>
-static cudaError_t launch_gen_c(const LaunchArgs& la, const CUtensorMap& tmap_feat, const float* feature,
-                                const float* conv_w, const float* conv_b, float* weight_out, float* offset_out) {
+template <typename FT, int C, int TH>
+static cudaError_t launch_gen_c(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature,
+                                const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
     const bool wo = weight_out != nullptr;
     if (la.use_tma) {
-        return wo ? launch_gen_one<C, true, TH, true>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
-                  : launch_gen_one<C, true, TH, false>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
+        return wo ? launch_gen_one<FT, C, true, TH, true>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+                  : launch_gen_one<FT, C, true, TH, false>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
     }
-    return wo ? launch_gen_one<C, false, TH, true>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
-              : launch_gen_one<C, false, TH, false>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
+    return wo ? launch_gen_one<FT, C, false, TH, true>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+              : launch_gen_one<FT, C, false, TH, false>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
 }
 
-// la.tile_h must be 16 or 8 (abi.cu); la.use_tma says that BOTH tensor maps (DEM box, feature rows) are valid
+// la.tile_h must be 16 or 8 (abi.cu); la.use_tma says that BOTH tensor maps (DEM box, feature rows) are valid;
+// la.bf16: feature / weight_out / offset_out are bf16 (init and out stay fp32)
 cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature, int C,
                                    const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
-    const float* f = (const float*)feature;
-    float* wo = (float*)weight_out;
-    float* oo = (float*)offset_out;
-    if (C == 64) {
-        return la.tile_h == 16 ? launch_gen_c<64, 16>(la, tmap_feat, f, conv_w, conv_b, wo, oo)
-                               : launch_gen_c<64, 8>(la, tmap_feat, f, conv_w, conv_b, wo, oo);
+    if (C != 64) return cudaErrorNotSupported;
+    if (la.bf16) {
+        return la.tile_h == 16 ? launch_gen_c<__nv_bfloat16, 64, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+                               : launch_gen_c<__nv_bfloat16, 64, 8>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
     }
-    return cudaErrorNotSupported;
+    return la.tile_h == 16 ? launch_gen_c<float, 64, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+                           : launch_gen_c<float, 64, 8>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
 }
 
 }  // namespace JSPSR_VARIANT

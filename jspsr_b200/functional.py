@@ -174,8 +174,8 @@ def gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: 
     C = feature.shape[1]
     if tuple(conv_w.shape) != (25, C) or tuple(conv_b.shape) != (25,):
         raise RuntimeError(f"conv_w must be [25,{C}] and conv_b [25], got {tuple(conv_w.shape)} / {tuple(conv_b.shape)}")
-    if init.dtype != torch.float32 or feature.dtype != torch.float32:
-        raise RuntimeError("gen_spn_forward is implemented for float32 tensors")
+    if init.dtype != torch.float32 or feature.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("gen_spn_forward needs a float32 init and a float32 or bfloat16 (torch.autocast) feature")
     init, feature = init.contiguous(), feature.contiguous()
     conv_w = conv_w.detach().to(torch.float32).contiguous()
     conv_b = conv_b.detach().to(torch.float32).contiguous()
@@ -184,12 +184,12 @@ def gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: 
     out = torch.empty_like(init)
     weight = offset = None
     if want_weight_offset:
-        weight = torch.empty(B, 9, H, W, dtype=torch.float32, device=init.device)
-        offset = torch.empty(B, 18, H, W, dtype=torch.float32, device=init.device)
+        weight = torch.empty(B, 9, H, W, dtype=feature.dtype, device=init.device)
+        offset = torch.empty(B, 18, H, W, dtype=feature.dtype, device=init.device)
     with torch.cuda.device(init.device):
         rc = _lib.lib().jspsr_gen_spn_forward(_ptr(init), _ptr(feature), _ptr(conv_w), _ptr(conv_b), _ptr(w9), _ptr(b1),
                                               _ptr(out), _ptr(weight), _ptr(offset), B, C, H, W, norm_mode, float(scale),
-                                              F32, _stream_ptr(init))
+                                              F32 if feature.dtype == torch.float32 else MIXED, _stream_ptr(init))
     _lib.check(rc, "jspsr_gen_spn_forward")
     _count()
     return (out, weight, offset) if want_weight_offset else out
@@ -334,8 +334,8 @@ class _GenPropagate(torch.autograd.Function):
         B, C, H, W = feature.shape
         # pre-activation gradients [B,25,H,W]: sigmoid' for the 9 weights, the 16 non-centre offset channels
         gz = torch.cat((gwt * weight * (1.0 - weight), goff[:, :8], goff[:, 10:]), dim=1)
-        g_conv_b = gz.sum(dim=(0, 2, 3)) if ctx.needs_input_grad[3] else None
-        g_conv_w = torch.einsum("bnhw,bchw->nc", gz, feature) if ctx.needs_input_grad[2] else None
+        g_conv_b = gz.sum(dim=(0, 2, 3), dtype=torch.float32).to(conv_w.dtype) if ctx.needs_input_grad[3] else None
+        g_conv_w = torch.einsum("bnhw,bchw->nc", gz, feature).to(conv_w.dtype) if ctx.needs_input_grad[2] else None
         g_feat = torch.einsum("bnhw,nc->bchw", gz, conv_w.to(gz.dtype)) if ctx.needs_input_grad[1] else None
         if gw is not None:
             gw, gb = gw.to(w.dtype).reshape(w.shape), gb.to(w.dtype)
