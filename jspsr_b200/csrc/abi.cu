@@ -256,9 +256,9 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
         return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward: dtype must be 0 (all fp32) or 2 (mixed: bf16 feature / "
                                            "weight_out / offset_out, fp32 init / out)");
     const size_t esf = dtype == JSPSR_MIXED ? 2 : 4;
-    if (C != 64)
-        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is instantiated for C = 64 feature channels "
-                                           "(Generator bc = 16, configs/*.yml num_feature = 32), got C = %d", C);
+    if (C != 64 && C != 128)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is instantiated for C = 64 feature channels (Generator "
+                                           "bc = 16, configs/*.yml num_feature = 32) and C = 128 (cat_only / EDSR), got C = %d", C);
     if (!init || !feature || !conv_w || !conv_b || !w9 || !b1 || !out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
     if ((weight_out == nullptr) != (offset_out == nullptr))
         return fail(JSPSR_ERR_BAD_ARG, "weight_out and offset_out must be given together");
@@ -274,6 +274,10 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
     if (la.tile_h < 8) {  // instantiated for 16 and 8 rows per CTA
         la.tile_h = 8;
         la.g.tiles_y = (H + 7) / 8;
+    }
+    if (C == 128 && la.tile_h != 16) {  // C = 128 runs one CTA per SM, 16 rows each
+        la.tile_h = 16;
+        la.g.tiles_y = (H + 15) / 16;
     }
     la.init = init; la.w9 = w9; la.b1 = b1; la.out = out;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_MIXED; la.init_f32 = true;

@@ -99,7 +99,7 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
                  : "memory");
 }
 
-// C: feature channels (bc * 4 of the Generator: 64 for JSPSR's num_feature = 32, 128 for cat_only / EDSR).
+// C: feature channels (bc * 4 of the Generator: 64 for JSPSR's num_feature = 32, 128 for cat_only / EDSR with 64 features).
 // TMA: the DEM box AND the feature rows arrive by TMA (needs 16-byte aligned rows); otherwise bounds-checked loads.
 // TH: rows per CTA.  WRITE_WO: also store weight [B,9,H,W] and offset [B,18,H,W] (what the backward needs).
 //
@@ -124,8 +124,10 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 // exactly representable in tf32, so the lo part and its MMAs vanish (16 MMAs per row), the ring stage halves, and
 // weight / offset are rounded to bf16 BEFORE the gather - what the reference's autocast run propagates, and what
 // makes `out` bit-identical to the propagation kernel applied to the tensors written here.
+// C = 128 (Generator of models/EDSR.py:104-106, `cat_only` JSPSR): the operand needs 2 x 128 TMEM columns, so the
+// CTA allocates all 512 and runs alone on its SM (ring 2 x 64 KB).
 template <typename FT, int C, bool TMA, int TH, bool WRITE_WO>
-__global__ void __launch_bounds__(GEN_CTA_THREADS, 2)
+__global__ void __launch_bounds__(GEN_CTA_THREADS, C <= 64 ? 2 : 1)
 gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ feature,
                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                        const float* __restrict__ w9, const float* __restrict__ b1, float* __restrict__ out,
@@ -139,7 +141,7 @@ gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ fe
     constexpr int STAGE_BYTES = GEN_THREADS * C * (int)sizeof(FT), B_BYTES = GEN_N * C * 4;
     constexpr int RING_BYTES = TMA ? GEN_STAGES * STAGE_BYTES : 0;
     constexpr uint32_t COL_A_HI = 0, COL_A_LO = C, COL_ACC = 2 * C;  // TMEM column map
-    constexpr uint32_t TMEM_COLS = 256;
+    constexpr uint32_t TMEM_COLS = C <= 64 ? 256 : 512;
     static_assert(2 * C + 2 * GEN_N <= TMEM_COLS, "TMEM budget");
     extern __shared__ __align__(1024) unsigned char dsm[];
     unsigned char* ring = dsm;                       // [GEN_STAGES][C][128] fp32 (TMA only)
@@ -418,6 +420,10 @@ static cudaError_t launch_gen_c(const LaunchArgs& la, const CUtensorMap& tmap_fe
 // la.bf16: feature / weight_out / offset_out are bf16 (init and out stay fp32)
 cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature, int C,
                                    const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
+    if (C == 128) {  // one CTA per SM: always 16 rows per CTA
+        return la.bf16 ? launch_gen_c<__nv_bfloat16, 128, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+                       : launch_gen_c<float, 128, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
+    }
     if (C != 64) return cudaErrorNotSupported;
     if (la.bf16) {
         return la.tile_h == 16 ? launch_gen_c<__nv_bfloat16, 64, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
