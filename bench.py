@@ -452,6 +452,34 @@ def side_numbers(torch, F, device, B):
         return F.spn_forward(init, weight, torch.cat(lo, dim=1).view(B, -1, TILE, TILE), w, b, 1, 1.0)
 
     un = timed(unfused, n=3)
+    # training step through the fused tail: forward (weight/offset written) + spn_backward_kernel in GEN_PREACT mode
+    # (writes the pre-activation gradients) + the two 1x1-convolution gradients as per-sample library GEMMs
+    featg = feat.clone().requires_grad_()
+    cwg, cbg = cw.clone().requires_grad_(), cb.clone().requires_grad_()
+    wg, bg = w.clone().requires_grad_(), b.clone().requires_grad_()
+    gout = torch.randn(B, 1, TILE, TILE, device=device, generator=g_)
+
+    def train_fused():
+        for t_ in (featg, cwg, cbg, wg, bg):
+            t_.grad = None
+        F.gen_propagate(init, featg, cwg, cbg, wg, bg, 1, 1.0).backward(gout)
+
+    cwt_g, cot_g = cwt.clone().requires_grad_(), cot.clone().requires_grad_()
+    cbw_g, cbo_g = cb[:9].clone().requires_grad_(), cb[9:].clone().requires_grad_()
+
+    def train_unfused():
+        for t_ in (featg, cwt_g, cot_g, cbw_g, cbo_g, wg, bg):
+            t_.grad = None
+        weight = torch.sigmoid(torch.nn.functional.conv2d(featg, cwt_g, cbw_g))
+        o = torch.nn.functional.conv2d(featg, cot_g, cbo_g).view(B, 8, 2, TILE, TILE)
+        lo = list(torch.chunk(o, 8, dim=1))
+        lo.insert(4, torch.zeros((B, 1, 2, TILE, TILE), device=device))
+        F.propagate(init, weight, torch.cat(lo, dim=1).view(B, -1, TILE, TILE), wg, bg, 1, 1.0).backward(gout)
+
+    tr_f = timed(train_fused, n=3)
+    tr_u = timed(train_unfused, n=2)
+    del featg, gout
+    torch.cuda.empty_cache()
     feat16 = feat.bfloat16()
     fused16 = timed(lambda: F.gen_spn_forward(init, feat16, cw, cb, w, b, 1, 1.0, False))
     fused16_wo = timed(lambda: F.gen_spn_forward(init, feat16, cw, cb, w, b, 1, 1.0, True))
@@ -462,6 +490,7 @@ def side_numbers(torch, F, device, B):
         "ms_with_weight_offset_written": fused_wo,
         "frac_of_hbm_peak_with_weight_offset_written": (by + 108 * npix) / (fused_wo * 1e-3) / 1e9 / peak,
         "unfused_ms": un, "speedup_vs_unfused": un / fused,
+        "training_step_ms": tr_f, "training_step_unfused_ms": tr_u, "training_speedup_vs_unfused": tr_u / tr_f,
         "autocast_bf16_features": {"ms": fused16, "frac_of_hbm_peak": (C * 2 + 8) * npix / (fused16 * 1e-3) / 1e9 / peak,
                                    "ms_with_weight_offset_written": fused16_wo,
                                    "frac_of_hbm_peak_with_weight_offset_written":

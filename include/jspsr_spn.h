@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 103 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 104 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,
@@ -72,6 +72,12 @@ typedef enum { JSPSR_AFF_AS = 0, JSPSR_AFF_ASS = 1, JSPSR_AFF_TC = 2, JSPSR_AFF_
 /* flags for jspsr_spn_backward */
 #define JSPSR_BWD_ACCUMULATE 1u /* grad_weight/grad_offset += (fixed-affinity T-step loop) instead of =;
                                    implemented together with grad_init only (JSPSR_ERR_UNSUPPORTED otherwise) */
+
+#define JSPSR_BWD_GEN_PREACT 2u /* generator-tail training (jspsr_gen_spn_forward's backward): grad_weight points to a
+                                   [B,25,H,W] tensor that receives the gradients w.r.t. the PRE-ACTIVATIONS of
+                                   Generator.conv_weight / conv_offset (channels 0..8: dL/dweight_k * weight_k * (1 - weight_k);
+                                   9..24: the 16 offset gradients without the centre pair); grad_offset is ignored
+                                   (may be NULL); grad_init must be NULL (the DEM is detached, models/JSPSR.py:372) */
 
 int jspsr_version(void);
 const char *jspsr_last_error(void);

@@ -17,6 +17,7 @@ NORM_NONE, NORM_RESIDUAL, NORM_SUM = 0, 1, 2
 F32, BF16, MIXED = 0, 1, 2  # MIXED: bf16 weight/offset (+ gradients), fp32 init/out/grad_out (torch.autocast)
 AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 BWD_ACCUMULATE = 1
+BWD_GEN_PREACT = 2
 
 # name -> (restype, argtypes); mirrors include/jspsr_spn.h one to one
 _SIGNATURES = {

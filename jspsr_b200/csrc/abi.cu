@@ -212,8 +212,11 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
                        void* workspace, int B, int H, int W, int norm_mode, float scale, int dtype, unsigned flags,
                        void* stream) {
     if (int e = check_common(B, H, W, norm_mode, dtype)) return e;
-    if (!grad_out || !init || !weight || !offset || !grad_weight || !grad_offset)
+    const bool preact = (flags & JSPSR_BWD_GEN_PREACT) != 0;
+    if (!grad_out || !init || !weight || !offset || !grad_weight || (!grad_offset && !preact))
         return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    if (preact && (grad_init || (flags & JSPSR_BWD_ACCUMULATE)))
+        return fail(JSPSR_ERR_UNSUPPORTED, "JSPSR_BWD_GEN_PREACT excludes grad_init and JSPSR_BWD_ACCUMULATE");
     if (grad_w9 && !workspace) return fail(JSPSR_ERR_BAD_ARG, "workspace is required when grad_w9 is requested");
     if (grad_b1 && !grad_w9) return fail(JSPSR_ERR_BAD_ARG, "grad_b1 without grad_w9 is not supported");
     if ((flags & JSPSR_BWD_ACCUMULATE) && !grad_init)
@@ -235,6 +238,7 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     la.grad_init = grad_init; la.grad_weight = grad_weight; la.grad_offset = grad_offset;
     la.grad_w9 = grad_w9; la.grad_b1 = grad_b1; la.workspace = workspace;
     la.accumulate = (flags & JSPSR_BWD_ACCUMULATE) != 0;
+    la.gen_preact = preact;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
     la.stream = (cudaStream_t)stream;
     const bool wide = choose_wide(W);

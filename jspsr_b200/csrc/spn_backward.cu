@@ -35,7 +35,11 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
 // CS : compile-time channel stride H*W (0 = runtime), see spn_forward.cu.
 // TH : rows per CTA.  `mode` is a runtime, warp-uniform switch.
 // T: element type of weight / offset and their gradients; TI: element type of grad_out / init (see spn_forward.cu).
-template <typename T, typename TI, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH>
+// GZ (generator-tail training, JSPSR_BWD_GEN_PREACT): `grad_weight` is a [B,25,H,W] tensor that receives the gradients
+// w.r.t. the PRE-ACTIVATIONS of Generator.conv_weight / conv_offset (spn.py:41-52,66-73): channels 0..8 =
+// dL/d(weight_k) * weight_k * (1 - weight_k) (sigmoid'), channels 9..24 = the 16 offset gradients without the centre
+// pair - the operand of the two 1x1-convolution gradient GEMMs, written here instead of by four elementwise passes.
+template <typename T, typename TI, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH, bool GZ = false>
 __global__ void __launch_bounds__(THREADS, sizeof(T) == 2 ? BWD_MIN_BLOCKS_BF16 : BWD_MIN_BLOCKS)
 spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, const T* __restrict__ weight,
                     const T* __restrict__ offset, const float* __restrict__ w9, float* __restrict__ grad_init,
@@ -67,8 +71,10 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
     const T* wgt_b = weight + (size_t)c.b * 9 * cs;
     const T* off_b = offset + (size_t)c.b * 18 * cs;
     const TI* init_b = init + (size_t)c.b * g.init_rows * g.W;
-    T* gwgt_b = grad_weight + (size_t)c.b * 9 * cs;
-    T* goff_b = grad_offset + (size_t)c.b * 18 * cs;
+    T* gwgt_b = grad_weight + (size_t)c.b * (GZ ? 25 : 9) * cs;
+    T* goff_b = GZ ? gwgt_b + 9 * cs : grad_offset + (size_t)c.b * 18 * cs;
+    // channel of tap k's row-offset gradient inside goff_b (GZ: the centre pair k = 4 has no source and is skipped)
+    auto och = [](int k) { return GZ ? 2 * (k - (k > 4 ? 1 : 0)) : 2 * k; };
     float* gi_b = GRAD_INIT ? grad_init + (size_t)c.b * g.init_rows * g.W : nullptr;
     const TI* tile_lo = tile + c.r_lo * SW;
     int* gtile_lo = gtile + (GRAD_INIT ? c.r_lo * SW : 0);
@@ -198,14 +204,16 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
             const float gkm = ga * s_w[k];       // dL/d(sample_k)
             acc_w[k] = fmaf(ga, val, acc_w[k]);
             gm[k] = (go * s_w[k]) * val;
-            if (CS) {
-                store(po + (2 * k) * cs, gkm * dh);
-                store(po + (2 * k + 1) * cs, gkm * dw);
-            } else {
-                store(pos, gkm * dh);
-                pos = step_ptr(pos, csb);
-                store(pos, gkm * dw);
-                pos = step_ptr(pos, csb);
+            if (!(GZ && k == 4)) {
+                if (CS) {
+                    store(po + och(k) * cs, gkm * dh);
+                    store(po + (och(k) + 1) * cs, gkm * dw);
+                } else {
+                    store(pos, gkm * dh);
+                    pos = step_ptr(pos, csb);
+                    store(pos, gkm * dw);
+                    pos = step_ptr(pos, csb);
+                }
             }
             if (GRAD_INIT) {
                 if (t.ok) {
@@ -232,8 +240,10 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
                     const float ga = go * a[k], gkm = ga * s_w[k];
                     acc_w[k] = fmaf(ga, val, acc_w[k]);
                     gm[k] += (go * s_w[k]) * val;
-                    store(po + (2 * k) * cs, gkm * dh);      // the fast pass stored 0 here (ACC: added 0)
-                    store(po + (2 * k + 1) * cs, gkm * dw);
+                    if (!(GZ && k == 4)) {
+                        store(po + och(k) * cs, gkm * dh);      // the fast pass stored 0 here (ACC: added 0)
+                        store(po + (och(k) + 1) * cs, gkm * dw);
+                    }
                     if (GRAD_INIT && t.finite) {
                         const float ch = gkm * t.lh, cl = gkm - ch, c2 = cl * t.lw, c4 = ch * t.lw;
                         scatter_corner_global<T>(gi_b, g, t.h0, t.w0, cl - c2);
@@ -260,6 +270,14 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
             const float inv = __fdiv_rn(1.f, s);
 #pragma unroll
             for (int k = 0; k < 9; ++k) gm[k] = (gm[k] - dot) * inv;
+        }
+        if (GZ) {  // sigmoid' at the RAW affinity: a[] holds the normalised m_k, the raw value is m_k + mean / m_k * s
+            const float mean = __fdiv_rn(s, 9.f);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float raw = mode == NORM_RESIDUAL ? a[k] + mean : (mode == NORM_SUM ? a[k] * s : a[k]);
+                gm[k] *= raw * (1.f - raw);
+            }
         }
         T* pw = gwgt_b + p;
 #pragma unroll
@@ -337,27 +355,32 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
     }
 }
 
-template <typename T, typename TI, bool TMA, bool GI, bool ACC, int CS, int TH>
+template <typename T, typename TI, bool TMA, bool GI, bool ACC, int CS, int TH, bool GZ = false>
 static void launch_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_backward_kernel<T, TI, TMA, GI, ACC, CS, TH><<<grid, THREADS, 0, la.stream>>>(
+    spn_backward_kernel<T, TI, TMA, GI, ACC, CS, TH, GZ><<<grid, THREADS, 0, la.stream>>>(
         (const TI*)la.grad_out, (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.grad_init,
         (T*)la.grad_weight, (T*)la.grad_offset, la.grad_w9, la.grad_b1, (ReduceWs*)la.workspace, la.g, la.mode,
         la.scale, la.tmap);
 }
 
 // (TMA, CS) variants: the compile-time stride only exists for 128x128-pixel planes, which always qualify for TMA
-template <typename T, typename TI, bool GI, bool ACC, int TH>
+template <typename T, typename TI, bool GI, bool ACC, int TH, bool GZ = false>
 static void launch_variant(const LaunchArgs& la) {
     const size_t cs = (size_t)la.g.H * la.g.W;
-    if (la.use_tma && cs == 16384) launch_one<T, TI, true, GI, ACC, 16384, TH>(la);
-    else if (la.use_tma) launch_one<T, TI, true, GI, ACC, 0, TH>(la);
-    else launch_one<T, TI, false, GI, ACC, 0, TH>(la);
+    if (la.use_tma && cs == 16384) launch_one<T, TI, true, GI, ACC, 16384, TH, GZ>(la);
+    else if (la.use_tma) launch_one<T, TI, true, GI, ACC, 0, TH, GZ>(la);
+    else launch_one<T, TI, false, GI, ACC, 0, TH, GZ>(la);
 }
 
 template <typename T, typename TI, int TH>
 static cudaError_t launch_bwd_th(const LaunchArgs& la) {
     const bool gi = la.grad_init != nullptr;
+    if (la.gen_preact) {  // generator-tail training: the DEM is detached there (models/JSPSR.py:372), nothing accumulates
+        if (gi || la.accumulate) return cudaErrorNotSupported;
+        launch_variant<T, TI, false, false, TH, true>(la);
+        return cudaGetLastError();
+    }
     if (la.accumulate) {
         // only the fixed-affinity loop accumulates (NLSPN backward: grad_init always needed)
         if (!gi) return cudaErrorNotSupported;

@@ -41,6 +41,7 @@ struct LaunchArgs {
     float* grad_b1 = nullptr;
     void* workspace = nullptr;
     bool accumulate = false;
+    bool gen_preact = false;  // JSPSR_BWD_GEN_PREACT: grad_weight is [B,25,H,W] pre-activation gradients
     Geom g{};
     int mode = NORM_RESIDUAL;
     float scale = 1.f;

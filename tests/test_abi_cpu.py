@@ -39,7 +39,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_workspace(lib):
     h = lib.lib()
-    assert h.jspsr_version() == 103
+    assert h.jspsr_version() == 104
     assert 64 <= h.jspsr_spn_workspace_bytes() <= 4096
     assert h.jspsr_spn_host_scratch_bytes(2, 128, 128, 0) >= 2 * 2 * 128 * 128 * 4 * 29
 
