@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 104 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 105 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,
@@ -152,6 +152,16 @@ int jspsr_gen_spn_forward(const void *init, const void *feature, const float *co
                           const float *conv_b, const float *w9, const float *b1, void *out,
                           void *weight_out, void *offset_out, int B, int C, int H, int W,
                           int norm_mode, float scale, int dtype, void *stream);
+
+/*
+ * Feature gradient of the Generator tail: grad_feature[b,c,y,x] = sum_j gz[b,j,y,x] * conv_w[j,c] - the backward of
+ * Generator.conv_weight / conv_offset (spn.py:41-52) w.r.t. their input, with gz [B,25,H,W] the pre-activation
+ * gradients jspsr_spn_backward writes under JSPSR_BWD_GEN_PREACT and conv_w the [25,C] matrix of
+ * jspsr_gen_spn_forward.  Tensor-core contraction (tcgen05, tf32 3-product split).  gz and grad_feature [B,C,H,W] share
+ * `dtype` (JSPSR_F32 or JSPSR_BF16); C = 64 or 128.
+ */
+int jspsr_gen_tail_grad_feature(const void *gz, const float *conv_w, void *grad_feature, int B, int C,
+                                int H, int W, int dtype, void *stream);
 
 /* max |row offset| and max |column offset| over a [B,18,H,W] tensor -> out2[2] (device,
  * combined with max so several calls may fold into one pair; zero it first).  Used to

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "jspsr_spn_backward": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p]),
     "jspsr_spn_forward_strip": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_float, c_int, c_void_p, c_void_p]),
     "jspsr_gen_spn_forward": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_float, c_int, c_void_p]),
+    "jspsr_gen_tail_grad_feature": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
     "jspsr_spn_offset_absmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "jspsr_spn_iterate": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "jspsr_nlspn_affinity_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),

@@ -34,6 +34,10 @@ cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const 
 JSPSR_DECLARE_VARIANT(narrow)
 JSPSR_DECLARE_VARIANT(wide)
 #undef JSPSR_DECLARE_VARIANT
+namespace narrow {  // gen_tail_backward.cu stages no DEM tile: compiled once
+cudaError_t launch_gen_grad_feature(const LaunchArgs& la, const CUtensorMap& tmap_gz, const void* gz, int C,
+                                    const float* conv_w, void* grad_feature);
+}
 }  // namespace jspsr
 
 static thread_local char g_err[512] = "";
@@ -295,6 +299,30 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
     cudaError_t ce = (wide ? wide::launch_gen_spn_forward : narrow::launch_gen_spn_forward)(la, tmap_feat, feature, C, conv_w,
                                                                                             conv_b, weight_out, offset_out);
     if (ce != cudaSuccess) return cuda_fail(ce, "gen_spn_forward launch");
+    return JSPSR_OK;
+}
+
+int jspsr_gen_tail_grad_feature(const void* gz, const float* conv_w, void* grad_feature, int B, int C, int H, int W,
+                                int dtype, void* stream) {
+    if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (dtype == JSPSR_MIXED) return fail(JSPSR_ERR_BAD_ARG, "jspsr_gen_tail_grad_feature: dtype is 0 (f32) or 1 (bf16)");
+    if (C != 64 && C != 128)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_tail_grad_feature is instantiated for C = 64 and C = 128, got C = %d", C);
+    if (!gz || !conv_w || !grad_feature) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    const size_t es = dtype == JSPSR_BF16 ? 2 : 4;
+    if (int e = check_align(gz, es, "gz")) return e;
+    if (int e = check_align(grad_feature, es, "grad_feature")) return e;
+    if (int e = check_align(conv_w, 4, "conv_w")) return e;
+    LaunchArgs la;
+    if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 16)) return e;
+    la.tile_h = 16;  // the kernel always walks 16 rows per CTA
+    la.g.tiles_y = (H + 15) / 16;
+    la.bf16 = dtype == JSPSR_BF16;
+    la.stream = (cudaStream_t)stream;
+    CUtensorMap tmap_gz{};
+    la.use_tma = make_feature_tmap(&tmap_gz, gz, B, 25, H, W, la.bf16);
+    cudaError_t ce = narrow::launch_gen_grad_feature(la, tmap_gz, gz, C, conv_w, grad_feature);
+    if (ce != cudaSuccess) return cuda_fail(ce, "gen_grad_feature launch");
     return JSPSR_OK;
 }
 

@@ -202,6 +202,26 @@ def gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: 
     return (out, weight, offset) if want_weight_offset else out
 
 
+def gen_tail_grad_feature(gz, conv_w) -> torch.Tensor:
+    """grad_feature [B,C,H,W] = sum_j gz[:, j] * conv_w[j, :] (gz [B,25,H,W] from spn_backward(gen_preact=True))."""
+    _require_cuda(gz, conv_w)
+    if gz.dim() != 4 or gz.shape[1] != 25:
+        raise RuntimeError(f"gz must be [B,25,H,W], got {tuple(gz.shape)}")
+    B, _, H, W = gz.shape
+    C = conv_w.shape[1]
+    if conv_w.shape[0] != 25:
+        raise RuntimeError(f"conv_w must be [25,C], got {tuple(conv_w.shape)}")
+    gz = gz.contiguous()
+    conv_w = conv_w.detach().to(torch.float32).contiguous()
+    out = torch.empty(B, C, H, W, dtype=gz.dtype, device=gz.device)
+    with torch.cuda.device(gz.device):
+        rc = _lib.lib().jspsr_gen_tail_grad_feature(_ptr(gz), _ptr(conv_w), _ptr(out), B, C, H, W, _dtype_code(gz),
+                                                    _stream_ptr(gz))
+    _lib.check(rc, "jspsr_gen_tail_grad_feature")
+    _count()
+    return out
+
+
 def offset_absmax(offset: torch.Tensor) -> torch.Tensor:
     """[max |row offset|, max |col offset|] as a 2-element fp32 device tensor."""
     _require_cuda(offset)
@@ -358,9 +378,8 @@ class _GenPropagate(torch.autograd.Function):
             g_conv_b = gz.sum(dim=2, dtype=torch.float32).sum(dim=0).to(conv_w.dtype)
         if ctx.needs_input_grad[2]:   # [B,25,HW] x [B,HW,C] -> [B,25,C] -> sum over the batch
             g_conv_w = torch.bmm(gz, fview.transpose(1, 2)).sum(dim=0, dtype=torch.float32).to(conv_w.dtype)
-        if ctx.needs_input_grad[1]:   # [C,25] x [B,25,HW] -> [B,C,HW]; bmm with a stride-0 batch of the weights (matmul
-            # would fold the batch into one GEMM through two full-size permute copies: 11 ms of elementwise kernels)
-            g_feat = torch.bmm(conv_w.to(gz.dtype).t().unsqueeze(0).expand(B, C, 25), gz).view(B, C, H, W)
+        if ctx.needs_input_grad[1]:   # [B,25,HW] x [25,C] -> [B,C,HW]: tensor-core kernel (gen_tail_backward.cu)
+            g_feat = gen_tail_grad_feature(gz.view(B, 25, H, W), conv_w)
         if gw is not None:
             gw, gb = gw.to(w.dtype).reshape(w.shape), gb.to(w.dtype)
         return (gi if need_init else None, g_feat, g_conv_w, g_conv_b, gw if ctx.needs_input_grad[4] else None,

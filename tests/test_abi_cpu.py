@@ -30,7 +30,7 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 13, names
+    assert len(names) == 14, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in include/jspsr_spn.h but not exported"
@@ -39,7 +39,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_workspace(lib):
     h = lib.lib()
-    assert h.jspsr_version() == 104
+    assert h.jspsr_version() == 105
     assert 64 <= h.jspsr_spn_workspace_bytes() <= 4096
     assert h.jspsr_spn_host_scratch_bytes(2, 128, 128, 0) >= 2 * 2 * 128 * 128 * 4 * 29
 

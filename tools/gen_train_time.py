@@ -29,6 +29,7 @@ m, _ = timeit(lambda: gz.sum(dim=2).sum(dim=0), n=5); print(f"  bias grad {m:.2f
 fd = feat.detach().view(B, C, H * W)
 m, _ = timeit(lambda: torch.bmm(gz, fd.transpose(1, 2)).sum(dim=0), n=5); print(f"  conv weight grad (bmm per sample) {m:.2f} ms")
 cwd = cw.detach()
+m, _ = timeit(lambda: F.gen_tail_grad_feature(gz.view(B, 25, H, W), cwd), n=5); print(f"  feature grad (tcgen05 kernel) {m:.2f} ms  ({B*H*W*356/m/1e6/6551.4:.3f} of HBM peak)")
 m, _ = timeit(lambda: torch.matmul(cwd.t(), gz), n=5); print(f"  feature grad (matmul per sample) {m:.2f} ms")
 # the unfused reference sequence, forward + backward, torch convs + our propagation
 cwt = cw.detach()[:9].reshape(9, C, 1, 1).clone().requires_grad_(); cot = cw.detach()[9:].reshape(16, C, 1, 1).clone().requires_grad_()
