@@ -1,8 +1,26 @@
 // Small helper kernels around the propagation: offset range scan (strip halo
 // sizing) and the `preserve_input` blend of NLSPN's loop (nlspn.py:228-229).
+#include <mutex>
+#include <unordered_map>
+
 #include "spn_kernels.cuh"
 
 namespace jspsr {
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, unsigned long long> done;  // kernel -> bit mask of devices already set
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long& mask = done[kernel];
+    if (mask & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) mask |= bit;
+    return e;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) offset_absmax_kernel(const T* __restrict__ offset, size_t cs, int B,

@@ -328,8 +328,7 @@ static cudaError_t launch_gen_one(const LaunchArgs& la, const CUtensorMap& tmap_
                                   const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
     const size_t dyn = (TMA ? (size_t)GEN_STAGES * GEN_THREADS * C * sizeof(FT) : 0) + (size_t)2 * GEN_N * C * 4 +
                        (size_t)staged_rows(TH) * SW * 4;
-    static const cudaError_t attr = cudaFuncSetAttribute(gen_spn_forward_kernel<FT, C, TMA, TH, WO>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    const cudaError_t attr = ensure_dynamic_smem((const void*)gen_spn_forward_kernel<FT, C, TMA, TH, WO>, dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
     int l2_ahead = GEN_L2_AHEAD;

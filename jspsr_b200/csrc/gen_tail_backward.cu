@@ -197,8 +197,7 @@ template <typename FT, int C, bool TMA, int CS>
 static cudaError_t launch_gf_cs(const LaunchArgs& la, const CUtensorMap& tmap_gz, const void* gz, const float* conv_w,
                                 void* grad_feature) {
     const size_t dyn = (TMA ? (size_t)GT_STAGES * GEN_NOUT * GEN_THREADS * sizeof(FT) : 0) + (size_t)2 * C * GT_K * 4;
-    static const cudaError_t attr = cudaFuncSetAttribute(gen_grad_feature_kernel<FT, C, TMA, CS>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    const cudaError_t attr = ensure_dynamic_smem((const void*)gen_grad_feature_kernel<FT, C, TMA, CS>, dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
     gen_grad_feature_kernel<FT, C, TMA, CS><<<grid, GEN_CTA_THREADS, dyn, la.stream>>>((const FT*)gz, conv_w,

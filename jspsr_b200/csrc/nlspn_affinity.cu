@@ -411,9 +411,7 @@ static void aff_bwd_launch_one(const AffArgs& a) {
     dim3 grid((unsigned)((size_t)a.g.tiles_x * a.g.tiles_y * a.g.B));
     const size_t dyn = ITILE ? (size_t)staged_rows(TH) * SW * sizeof(int) : 0;
     if (dyn > 0) {  // static + dynamic shared memory exceed 48 KB with the wide halo: opt in once per instantiation
-        static const cudaError_t attr = cudaFuncSetAttribute(nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE>,
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        (void)attr;
+        (void)ensure_dynamic_smem((const void*)nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE>, dyn);
     }
     nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE><<<grid, THREADS, dyn, a.stream>>>(
         (const T*)a.grad_offset, (const T*)a.grad_aff, (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.grad_conv,

@@ -63,4 +63,8 @@ struct alignas(16) ReduceWs {
 };
 
 
+// Opt a kernel in to more than 48 KB of shared memory, once per (kernel, device): the attribute is per device, and
+// a process may drive several devices.  Host only; not a stream operation (safe while a stream is being captured).
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 }  // namespace jspsr

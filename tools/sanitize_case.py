@@ -38,5 +38,19 @@ feat, lst, off, aff, gam = nl(f0, g, c, fix)
 ti = torch.rand(1, 1, 64, 128, device="cuda"); tw = torch.rand(1, 9, 64, 128, device="cuda"); to = torch.randn(1, 18, 64, 128, device="cuda")
 st = torch.zeros(1, dtype=torch.int32, device="cuda")
 F.spn_forward_strip(ti[:, :, 10:50].contiguous(), tw[:, :, 16:40].contiguous(), to[:, :, 16:40].contiguous(), None, None, 0, 0.0, 64, 16, 10, st)
+# mixed dtype (torch.autocast), generator-tail kernels (tcgen05), feature gradient
+for (B, H, W) in ((2, 40, 128), (1, 21, 200), (1, 5, 7)):
+    init = torch.rand(B, 1, H, W, device="cuda")
+    wb = torch.rand(B, 9, H, W, device="cuda").bfloat16().requires_grad_()
+    ob = torch.randn(B, 18, H, W, device="cuda").bfloat16().requires_grad_()
+    pp = jspsr_b200.PostProcessor(3, True, 1.0).cuda()
+    pp(init, wb, ob).square().mean().backward()
+    for C in (64, 128):
+        for fdt in (torch.float32, torch.bfloat16):
+            feat = torch.randn(B, C, H, W, device="cuda").to(fdt).requires_grad_()
+            cw = (0.15 * torch.randn(25, C, device="cuda")).requires_grad_(); cb = (0.1 * torch.randn(25, device="cuda")).requires_grad_()
+            out = F.gen_propagate(init, feat, cw, cb, pp.w, pp.b, 1, 1.0)
+            out.square().mean().backward()
+            F.gen_spn_forward(init, feat.detach(), cw.detach(), cb.detach(), pp.w, pp.b, 2, 1.0)
 torch.cuda.synchronize()
 print("sanitize case done")
