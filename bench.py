@@ -463,72 +463,85 @@ def side_numbers(torch, F, device, B):
                             "note": "T launches of the forward kernel, all T outputs kept"}
     del aff, gout, weight, offset
     torch.cuda.empty_cache()
-    # the Generator's last two layers (1x1 convolutions 64 -> 9 / 16, sigmoid, zero
-    # centre pair; spn.py:41-52,66-73) fused into the propagation forward; contraction on tcgen05 (3xTF32)
-    C = 64
-    g_ = torch.Generator(device=device).manual_seed(4323)
-    feat = torch.randn(B, C, TILE, TILE, device=device, generator=g_)
-    cw = 0.15 * torch.randn(25, C, device=device, generator=g_)
-    cw[9:] *= 1.3
-    cb = 0.1 * torch.randn(25, device=device, generator=g_)
-    fused = timed(lambda: F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0, False))
-    fused_wo = timed(lambda: F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0, True))
-    cwt, cot = cw[:9].reshape(9, C, 1, 1).contiguous(), cw[9:].reshape(16, C, 1, 1).contiguous()
+    # the Generator's last two layers (1x1 convolutions C -> 9 / 16, sigmoid, zero centre
+    # pair; spn.py:41-52,66-73) fused into the propagation forward; contraction on tcgen05 (3xTF32).  C = 128 is what
+    # models/JSPSR.py builds at every YAML config (cat_only = True -> bc = num_feature = 32 -> bc * 4 channels).
+    def gen_tail(C, Bg):
+        npx = Bg * TILE * TILE
+        g_ = torch.Generator(device=device).manual_seed(4323)
+        ini = init[:Bg]
+        feat = torch.randn(Bg, C, TILE, TILE, device=device, generator=g_)
+        cw = 0.15 * torch.randn(25, C, device=device, generator=g_) * (64.0 / C) ** 0.5
+        cw[9:] *= 1.3
+        cb = 0.1 * torch.randn(25, device=device, generator=g_)
+        fused = timed(lambda: F.gen_spn_forward(ini, feat, cw, cb, w, b, 1, 1.0, False))
+        fused_wo = timed(lambda: F.gen_spn_forward(ini, feat, cw, cb, w, b, 1, 1.0, True))
+        by = (C * 4 + 8) * npx
+        res = {"C": C, "tiles": Bg, "ms": fused, "gpix_per_s": npx / (fused * 1e-3) / 1e9,
+               "algorithmic_bytes_per_pixel": C * 4 + 8, "frac_of_hbm_peak": by / (fused * 1e-3) / 1e9 / peak,
+               "ms_with_weight_offset_written": fused_wo,
+               "frac_of_hbm_peak_with_weight_offset_written": (by + 108 * npx) / (fused_wo * 1e-3) / 1e9 / peak}
+        if C != 128:
+            return res
+        cwt, cot = cw[:9].reshape(9, C, 1, 1).contiguous(), cw[9:].reshape(16, C, 1, 1).contiguous()
 
-    def unfused():  # the reference's sequence (spn.py:66-73 + 99-118) with torch's convolutions and OUR propagation kernel
-        weight = torch.sigmoid(torch.nn.functional.conv2d(feat, cwt, cb[:9]))
-        o = torch.nn.functional.conv2d(feat, cot, cb[9:]).view(B, 8, 2, TILE, TILE)
-        lo = list(torch.chunk(o, 8, dim=1))
-        lo.insert(4, torch.zeros((B, 1, 2, TILE, TILE), device=device))
-        return F.spn_forward(init, weight, torch.cat(lo, dim=1).view(B, -1, TILE, TILE), w, b, 1, 1.0)
+        def unfused():  # the reference's sequence (spn.py:66-73 + 99-118) with torch's convolutions and OUR propagation kernel
+            weight = torch.sigmoid(torch.nn.functional.conv2d(feat, cwt, cb[:9]))
+            o = torch.nn.functional.conv2d(feat, cot, cb[9:]).view(Bg, 8, 2, TILE, TILE)
+            lo = list(torch.chunk(o, 8, dim=1))
+            lo.insert(4, torch.zeros((Bg, 1, 2, TILE, TILE), device=device))
+            return F.spn_forward(ini, weight, torch.cat(lo, dim=1).view(Bg, -1, TILE, TILE), w, b, 1, 1.0)
 
-    un = timed(unfused, n=3)
-    # training step through the fused tail: forward (weight/offset written) + spn_backward_kernel in GEN_PREACT mode
-    # (writes the pre-activation gradients) + the two 1x1-convolution gradients as per-sample library GEMMs
-    featg = feat.clone().requires_grad_()
-    cwg, cbg = cw.clone().requires_grad_(), cb.clone().requires_grad_()
-    wg, bg = w.clone().requires_grad_(), b.clone().requires_grad_()
-    gout = torch.randn(B, 1, TILE, TILE, device=device, generator=g_)
+        un = timed(unfused, n=3)
+        # training step through the fused tail: forward (weight/offset written) + spn_backward_kernel in GEN_PREACT mode
+        # (writes the pre-activation gradients) + gen_grad_feature_kernel + the weight gradient as a library GEMM
+        featg = feat.clone().requires_grad_()
+        cwg, cbg = cw.clone().requires_grad_(), cb.clone().requires_grad_()
+        wg, bg = w.clone().requires_grad_(), b.clone().requires_grad_()
+        gout = torch.randn(Bg, 1, TILE, TILE, device=device, generator=g_)
 
-    def train_fused():
-        for t_ in (featg, cwg, cbg, wg, bg):
-            t_.grad = None
-        F.gen_propagate(init, featg, cwg, cbg, wg, bg, 1, 1.0).backward(gout)
+        def train_fused():
+            for t_ in (featg, cwg, cbg, wg, bg):
+                t_.grad = None
+            F.gen_propagate(ini, featg, cwg, cbg, wg, bg, 1, 1.0).backward(gout)
 
-    cwt_g, cot_g = cwt.clone().requires_grad_(), cot.clone().requires_grad_()
-    cbw_g, cbo_g = cb[:9].clone().requires_grad_(), cb[9:].clone().requires_grad_()
+        cwt_g, cot_g = cwt.clone().requires_grad_(), cot.clone().requires_grad_()
+        cbw_g, cbo_g = cb[:9].clone().requires_grad_(), cb[9:].clone().requires_grad_()
 
-    def train_unfused():
-        for t_ in (featg, cwt_g, cot_g, cbw_g, cbo_g, wg, bg):
-            t_.grad = None
-        weight = torch.sigmoid(torch.nn.functional.conv2d(featg, cwt_g, cbw_g))
-        o = torch.nn.functional.conv2d(featg, cot_g, cbo_g).view(B, 8, 2, TILE, TILE)
-        lo = list(torch.chunk(o, 8, dim=1))
-        lo.insert(4, torch.zeros((B, 1, 2, TILE, TILE), device=device))
-        F.propagate(init, weight, torch.cat(lo, dim=1).view(B, -1, TILE, TILE), wg, bg, 1, 1.0).backward(gout)
+        def train_unfused():
+            for t_ in (featg, cwt_g, cot_g, cbw_g, cbo_g, wg, bg):
+                t_.grad = None
+            weight = torch.sigmoid(torch.nn.functional.conv2d(featg, cwt_g, cbw_g))
+            o = torch.nn.functional.conv2d(featg, cot_g, cbo_g).view(Bg, 8, 2, TILE, TILE)
+            lo = list(torch.chunk(o, 8, dim=1))
+            lo.insert(4, torch.zeros((Bg, 1, 2, TILE, TILE), device=device))
+            F.propagate(ini, weight, torch.cat(lo, dim=1).view(Bg, -1, TILE, TILE), wg, bg, 1, 1.0).backward(gout)
 
-    tr_f = timed(train_fused, n=3)
-    tr_u = timed(train_unfused, n=2)
-    del featg, gout
+        tr_f = timed(train_fused, n=3)
+        tr_u = timed(train_unfused, n=2)
+        gz = torch.randn(Bg, 25, TILE, TILE, device=device, generator=g_)
+        gf = timed(lambda: F.gen_tail_grad_feature(gz, cw))
+        del featg, gout, gz
+        torch.cuda.empty_cache()
+        feat16 = feat.bfloat16()
+        fused16 = timed(lambda: F.gen_spn_forward(ini, feat16, cw, cb, w, b, 1, 1.0, False))
+        fused16_wo = timed(lambda: F.gen_spn_forward(ini, feat16, cw, cb, w, b, 1, 1.0, True))
+        res.update({
+            "unfused_ms": un, "speedup_vs_unfused": un / fused,
+            "training_step_ms": tr_f, "training_step_unfused_ms": tr_u, "training_speedup_vs_unfused": tr_u / tr_f,
+            "grad_feature_kernel_ms": gf, "grad_feature_frac_of_hbm_peak": (100 + 4 * C) * npx / (gf * 1e-3) / 1e9 / peak,
+            "autocast_bf16_features": {"ms": fused16, "frac_of_hbm_peak": (C * 2 + 8) * npx / (fused16 * 1e-3) / 1e9 / peak,
+                                       "ms_with_weight_offset_written": fused16_wo,
+                                       "frac_of_hbm_peak_with_weight_offset_written":
+                                           (C * 2 + 8 + 54) * npx / (fused16_wo * 1e-3) / 1e9 / peak},
+            "note": "gen_spn_forward_kernel: TMA ring -> tf32 hi/lo split into TMEM lanes -> tcgen05.mma (A from TMEM, "
+                    "3-product split, fp32-level accuracy) -> per-pixel epilogue + 9-tap gather; unfused = torch 1x1 "
+                    "convolutions (TF32 allowed, torch's default) + sigmoid + chunk/insert/cat + spn_forward_kernel"})
+        return res
+
+    out["generator_tail_fused"] = gen_tail(128, min(B, 1024))
     torch.cuda.empty_cache()
-    feat16 = feat.bfloat16()
-    fused16 = timed(lambda: F.gen_spn_forward(init, feat16, cw, cb, w, b, 1, 1.0, False))
-    fused16_wo = timed(lambda: F.gen_spn_forward(init, feat16, cw, cb, w, b, 1, 1.0, True))
-    by = (C * 4 + 8) * npix
-    out["generator_tail_fused"] = {
-        "ms": fused, "gpix_per_s": npix / (fused * 1e-3) / 1e9, "algorithmic_bytes_per_pixel": C * 4 + 8,
-        "frac_of_hbm_peak": by / (fused * 1e-3) / 1e9 / peak,
-        "ms_with_weight_offset_written": fused_wo,
-        "frac_of_hbm_peak_with_weight_offset_written": (by + 108 * npix) / (fused_wo * 1e-3) / 1e9 / peak,
-        "unfused_ms": un, "speedup_vs_unfused": un / fused,
-        "training_step_ms": tr_f, "training_step_unfused_ms": tr_u, "training_speedup_vs_unfused": tr_u / tr_f,
-        "autocast_bf16_features": {"ms": fused16, "frac_of_hbm_peak": (C * 2 + 8) * npix / (fused16 * 1e-3) / 1e9 / peak,
-                                   "ms_with_weight_offset_written": fused16_wo,
-                                   "frac_of_hbm_peak_with_weight_offset_written":
-                                       (C * 2 + 8 + 54) * npix / (fused16_wo * 1e-3) / 1e9 / peak},
-        "note": "gen_spn_forward_kernel: TMA ring -> tf32 hi/lo split into TMEM lanes -> tcgen05.mma (A from TMEM, "
-                "3-product split, fp32-level accuracy) -> per-pixel epilogue + 9-tap gather; unfused = torch 1x1 "
-                "convolutions (TF32 allowed, torch's default) + sigmoid + chunk/insert/cat + spn_forward_kernel"}
+    out["generator_tail_fused"]["c64"] = gen_tail(64, min(B, 2048))
     return out
 
 

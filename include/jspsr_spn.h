@@ -143,7 +143,7 @@ int jspsr_spn_forward_strip(const void *init, const void *weight, const void *of
  * conv_b [25] the two biases in the same order (all on device, conv_w 16-byte aligned).
  * The contraction runs on the tensor cores (tcgen05, tf32 with a 3-product split: fp32-level accuracy).
  * weight_out [B,9,H,W] / offset_out [B,18,H,W]: both NULL (inference) or both given - they receive what
- * the Generator would have returned, which is what jspsr_spn_backward needs.  C = 64 or 128.
+ * the Generator would have returned, which is what jspsr_spn_backward needs.  C = 128 (the YAML configs: models/JSPSR.py:28,181) or 64.
  * dtype JSPSR_F32: everything fp32.  dtype JSPSR_MIXED (torch.autocast): feature, weight_out, offset_out are
  * bf16 (init / out fp32); weight and offset are rounded to bf16 before the gather, i.e. `out` is exactly
  * jspsr_spn_forward(JSPSR_MIXED) of the tensors written.

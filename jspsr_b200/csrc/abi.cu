@@ -265,8 +265,8 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
                                            "weight_out / offset_out, fp32 init / out)");
     const size_t esf = dtype == JSPSR_MIXED ? 2 : 4;
     if (C != 64 && C != 128)
-        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is instantiated for C = 64 feature channels (Generator "
-                                           "bc = 16, configs/*.yml num_feature = 32) and C = 128 (cat_only / EDSR), got C = %d", C);
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_spn_forward is instantiated for C = 128 feature channels (Generator "
+                                           "bc = 32: configs/*.yml num_feature = 32 with cat_only) and C = 64 (bc = 16), got C = %d", C);
     if (!init || !feature || !conv_w || !conv_b || !w9 || !b1 || !out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
     if ((weight_out == nullptr) != (offset_out == nullptr))
         return fail(JSPSR_ERR_BAD_ARG, "weight_out and offset_out must be given together");

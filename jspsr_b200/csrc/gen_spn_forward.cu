@@ -35,7 +35,8 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
                  : "memory");
 }
 
-// C: feature channels (bc * 4 of the Generator: 64 for JSPSR's num_feature = 32, 128 for cat_only / EDSR with 64 features).
+// C: feature channels = bc * 4 of the Generator: 128 at every YAML config (models/JSPSR.py:28 hard-codes cat_only = True,
+// so bc = num_feature = 32, JSPSR.py:181); 64 for cat_only = False or models/EDSR.py:104-106 with 32 features.
 // TMA: the DEM box AND the feature rows arrive by TMA (needs 16-byte aligned rows); otherwise bounds-checked loads.
 // TH: rows per CTA.  WRITE_WO: also store weight [B,9,H,W] and offset [B,18,H,W] (what the backward needs).
 //
@@ -60,7 +61,7 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 // exactly representable in tf32, so the lo part and its MMAs vanish (16 MMAs per row), the ring stage halves, and
 // weight / offset are rounded to bf16 BEFORE the gather - what the reference's autocast run propagates, and what
 // makes `out` bit-identical to the propagation kernel applied to the tensors written here.
-// C = 128 (Generator of models/EDSR.py:104-106, `cat_only` JSPSR): the operand needs 2 x 128 TMEM columns, so the
+// C = 128 (the JSPSR configs): the operand needs 2 x 128 TMEM columns, so the
 // CTA allocates all 512 and runs alone on its SM (ring 2 x 64 KB).
 template <typename FT, int C, bool TMA, int TH, bool WRITE_WO>
 __global__ void __launch_bounds__(GEN_CTA_THREADS, C <= 64 ? 2 : 1)

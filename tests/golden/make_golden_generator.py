@@ -4,8 +4,9 @@ Run in the build container only (needs /root/reference):
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_generator.py
 
-Builds the reference's own `Generator` (models/components/spn.py:8-75, block = BasicBlock, bc = 16 as
-models/JSPSR.py:181-190 does for num_feature = 32) and `PostProcessor` (spn.py:79-118) with seeded parameters,
+Builds the reference's own `Generator` (models/components/spn.py:8-75, block = BasicBlock; bc = 32 -> 128 feature
+channels is what models/JSPSR.py:28,181-190 builds for the YAML configs' num_feature = 32, bc = 16 -> 64 channels the
+cat_only = False / EDSR-with-32-features variant) and `PostProcessor` (spn.py:79-118) with seeded parameters,
 runs  weight, offset = generator(dem, context);  out = postprocessor(dem.detach(), weight, offset)  exactly as
 models/JSPSR.py:371-375, and records - through a forward hook on `generator.block` - the tensor the fused kernel
 starts from (`feature`, spn.py:65), the two 1x1 convolutions' parameters, every intermediate and all gradients,
@@ -31,17 +32,23 @@ def main():
     from models.components.spn import Generator, PostProcessor
     meta = f"torch {torch.__version__} torchvision {torchvision.__version__}"
     cases = {
-        # name: (seed, B, H, W, in_channels, residual, scale, offset gain)
-        "gen_residual": (301, 2, 8, 20, 32, True, 1.0, 20.0),
-        "gen_sum": (302, 1, 5, 132, 32, False, 1.0, 10.0),
-        "gen_residual_half": (303, 1, 9, 128, 32, True, 0.5, 40.0),
+        # name: (seed, B, H, W, in_channels, residual, scale, offset gain, bc)
+        "gen_residual": (301, 2, 8, 20, 32, True, 1.0, 20.0, 16),
+        "gen_sum": (302, 1, 5, 132, 32, False, 1.0, 10.0, 16),
+        "gen_residual_half": (303, 1, 9, 128, 32, True, 0.5, 40.0, 16),
+        # bc = 32 -> 128 feature channels: what models/JSPSR.py builds at every YAML config (cat_only = True,
+        # JSPSR.py:28,181: bc = num_feature = 32)
+        "gen_c128_residual": (304, 1, 6, 40, 64, True, 1.0, 20.0, 32),
     }
-    for name, (seed, B, H, W, cin, residual, scale, gain) in cases.items():
+    only = sys.argv[1:]  # optional: names of the cases to (re)generate
+    for name, (seed, B, H, W, cin, residual, scale, gain, bc) in cases.items():
+        if only and name not in only:
+            continue
         res = {}
         for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
             torch.manual_seed(seed)
             with contextlib.redirect_stdout(io.StringIO()):
-                gen = Generator(cin, 3, BasicBlock, bc=16).double()
+                gen = Generator(cin, 3, BasicBlock, bc=bc).double()
                 pp = PostProcessor(3, residual, scale).double()
             g = torch.Generator().manual_seed(seed)
             with torch.no_grad():

@@ -23,7 +23,7 @@ def _close(a, b, rtol, atol, what):
 
 
 def test_fixtures_present():
-    assert len(PP) == 10 and len(NL) == 5 and len(GEN) == 3
+    assert len(PP) == 10 and len(NL) == 5 and len(GEN) == 4
 
 
 @pytest.mark.parametrize("path", GEN, ids=[os.path.basename(p)[:-4] for p in GEN])

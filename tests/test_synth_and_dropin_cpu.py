@@ -74,3 +74,48 @@ def test_installs_into_the_reference_model():
     # the diff_lr optimizer groups pick the layer up by name (utils/common_config.py:250-253)
     names = [n for n, _ in model.named_parameters() if "postprocessor" in n]
     assert names == ["postprocessor.w", "postprocessor.b"]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree only exists in the build container")
+def test_generator_postprocess_matches_the_reference_generators_structure(monkeypatch):
+    """jspsr_b200.generator_postprocess drives the reference's OWN Generator (models/components/spn.py:8-75): every
+    sub-module it touches must exist there with the shapes the fused kernel expects, its body up to `block` must be
+    the reference's forward (same feature tensor), and the operand matrix it hands to the kernel must be the two 1x1
+    convolutions' parameters in the documented order.  The kernel call is intercepted: no GPU here."""
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import contextlib
+    import io
+    from models.JSPSR import Model
+    import jspsr_b200 as jb
+    from jspsr_b200 import functional as F
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Model(in_channels={"lr_dem": 1, "COP30": 1, "image": 3}, num_feature=32, layers=(2, 2, 2, 2), spn=True)
+    gen, pp = model.generator.eval(), model.postprocessor
+    # models/JSPSR.py:28 hard-codes cat_only = True, so bc = num_feature = 32 (JSPSR.py:181) and the Generator's feature
+    # has bc * 4 = 128 channels at every YAML config (num_feature: 32): the kernel's C = 128 instantiation
+    assert gen.kernel_size == 3 and gen.conv_weight[0].weight.shape == (9, 128, 1, 1)
+    assert gen.conv_offset.conv[0].weight.shape == (16, 128, 1, 1) and gen.conv_offset.conv[0].bias is not None
+    captured = {}
+    hook = gen.block.register_forward_hook(lambda _m, _i, o: captured.__setitem__("feature", o.detach()))
+    dem, ctx = torch.rand(1, 1, 16, 24), torch.randn(1, gen.convf1.conv[0].in_channels, 16, 24)
+    with torch.no_grad():
+        weight, offset = gen(dem, ctx)                                   # the reference's own forward
+    hook.remove()
+    seen = {}
+
+    def fake_kernel(init, feature, conv_w, conv_b, w, b, mode, scale):
+        seen.update(init=init, feature=feature, conv_w=conv_w, conv_b=conv_b, mode=mode, scale=scale)
+        return init
+    monkeypatch.setattr(F, "gen_propagate", fake_kernel)
+    with torch.no_grad():
+        jb.generator_postprocess(gen, pp, dem, ctx)
+    assert torch.equal(seen["feature"], captured["feature"]) and torch.equal(seen["init"], dem)
+    assert seen["mode"] == 1 and seen["scale"] == float(pp.scale)
+    # the operand reproduces the reference's weight/offset from that feature (spn.py:66-73)
+    z = torch.einsum("nc,bchw->bnhw", seen["conv_w"], seen["feature"]) + seen["conv_b"].view(1, -1, 1, 1)
+    assert torch.allclose(torch.sigmoid(z[:, :9]), weight, atol=1e-6)
+    assert torch.allclose(z[:, 9:17], offset[:, :8], atol=1e-5) and torch.allclose(z[:, 17:], offset[:, 10:], atol=1e-5)
+    assert torch.all(offset[:, 8:10] == 0)
