@@ -283,9 +283,9 @@ int jspsr_gen_spn_forward(const void* init, const void* feature, const float* co
         la.tile_h = 8;
         la.g.tiles_y = (H + 7) / 8;
     }
-    if (C == 128 && la.tile_h != 16) {  // C = 128 runs one CTA per SM, 16 rows each
-        la.tile_h = 16;
-        la.g.tiles_y = (H + 15) / 16;
+    if (C == 128) {  // fp32: one CTA per SM, 16 rows each; bf16 features: two CTAs per SM, 8 rows each
+        la.tile_h = dtype == JSPSR_MIXED ? 8 : 16;
+        la.g.tiles_y = (H + la.tile_h - 1) / la.tile_h;
     }
     la.init = init; la.w9 = w9; la.b1 = b1; la.out = out;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype == JSPSR_MIXED; la.init_f32 = true;

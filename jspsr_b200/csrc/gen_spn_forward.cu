@@ -64,7 +64,7 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
 // C = 128 (the JSPSR configs): the operand needs 2 x 128 TMEM columns, so the
 // CTA allocates all 512 and runs alone on its SM (ring 2 x 64 KB).
 template <typename FT, int C, bool TMA, int TH, bool WRITE_WO>
-__global__ void __launch_bounds__(GEN_CTA_THREADS, C <= 64 ? 2 : 1)
+__global__ void __launch_bounds__(GEN_CTA_THREADS, (C <= 64 || sizeof(FT) == 2) ? 2 : 1)
 gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ feature,
                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                        const float* __restrict__ w9, const float* __restrict__ b1, float* __restrict__ out,
@@ -77,9 +77,10 @@ gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ fe
     constexpr bool F16 = sizeof(FT) == 2;
     constexpr int STAGE_BYTES = GEN_THREADS * C * (int)sizeof(FT), B_BYTES = GEN_N * C * 4;
     constexpr int RING_BYTES = TMA ? GEN_STAGES * STAGE_BYTES : 0;
-    constexpr uint32_t COL_A_HI = 0, COL_A_LO = C, COL_ACC = 2 * C;  // TMEM column map
-    constexpr uint32_t TMEM_COLS = C <= 64 ? 256 : 512;
-    static_assert(2 * C + 2 * GEN_N <= TMEM_COLS, "TMEM budget");
+    // TMEM column map; bf16 features have no lo part, so C = 128 then fits 256 columns and two CTAs per SM again
+    constexpr uint32_t COL_A_HI = 0, COL_A_LO = C, COL_ACC = F16 ? C : 2 * C;
+    constexpr uint32_t TMEM_COLS = COL_ACC + 2 * GEN_N <= 256 ? 256 : 512;
+    static_assert(COL_ACC + 2 * GEN_N <= TMEM_COLS, "TMEM budget");
     extern __shared__ __align__(1024) unsigned char dsm[];
     unsigned char* ring = dsm;                       // [GEN_STAGES][C][128] fp32 (TMA only)
     unsigned char* b_hi = dsm + RING_BYTES;
@@ -356,8 +357,8 @@ static cudaError_t launch_gen_c(const LaunchArgs& la, const CUtensorMap& tmap_fe
 // la.bf16: feature / weight_out / offset_out are bf16 (init and out stay fp32)
 cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature, int C,
                                    const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
-    if (C == 128) {  // one CTA per SM: always 16 rows per CTA
-        return la.bf16 ? launch_gen_c<__nv_bfloat16, 128, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
+    if (C == 128) {  // fp32: one CTA per SM, 16 rows; bf16: two CTAs per SM, 8 rows (the smaller DEM tile makes room)
+        return la.bf16 ? launch_gen_c<__nv_bfloat16, 128, 8>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out)
                        : launch_gen_c<float, 128, 16>(la, tmap_feat, feature, conv_w, conv_b, weight_out, offset_out);
     }
     if (C != 64) return cudaErrorNotSupported;
