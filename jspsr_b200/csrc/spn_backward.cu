@@ -123,6 +123,12 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
         }
     };
     auto store = [&](T* ptr, float v) {
+        if (ACC && sizeof(T) == 4) {
+            // accumulate at L2 (RED.ADD.F32, no return): no dependent load in front of every store.  Each element has
+            // exactly one owner thread, so the result does not depend on ordering.
+            atomicAdd(reinterpret_cast<float*>(ptr), v);
+            return;
+        }
         if (ACC) v += to_f32(*ptr);
         st_stream(ptr, v);
     };
