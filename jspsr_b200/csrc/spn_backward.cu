@@ -126,7 +126,7 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
         if (ACC && sizeof(T) == 4) {
             // accumulate at L2 (RED.ADD.F32, no return): no dependent load in front of every store.  Each element has
             // exactly one owner thread, so the result does not depend on ordering.
-            atomicAdd(reinterpret_cast<float*>(ptr), v);
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(ptr), "f"(v) : "memory");
             return;
         }
         if (ACC) v += to_f32(*ptr);
