@@ -9,5 +9,7 @@ xandercai/JSPSR (same constructor, forward signature and state_dict keys).
 """
 from .modules import NLSPN, Post_process_deconv, PostProcessor, generator_postprocess  # noqa: F401
 from . import functional  # noqa: F401
+from . import epilogue, tiles  # noqa: F401
+from .epilogue import MeterRMSE, MultiLoss  # noqa: F401
 
 __version__ = "1.0"

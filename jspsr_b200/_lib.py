@@ -1,4 +1,4 @@
-"""ctypes binding of libjspsr_spn.so (the C ABI in include/jspsr_spn.h).
+"""ctypes binding of libjspsr_spn.so (the C ABI in include/jspsr_spn.h and include/jspsr_tiles.h).
 
 There is no fallback: if the library is missing or a call fails, a RuntimeError
 is raised with the library's own message.
@@ -19,7 +19,7 @@ AFFINITY = {"AS": 0, "ASS": 1, "TC": 2, "TGASS": 3}
 BWD_ACCUMULATE = 1
 BWD_GEN_PREACT = 2
 
-# name -> (restype, argtypes); mirrors include/jspsr_spn.h one to one
+# name -> (restype, argtypes); mirrors include/jspsr_spn.h and include/jspsr_tiles.h one to one
 _SIGNATURES = {
     "jspsr_version": (c_int, []),
     "jspsr_last_error": (ctypes.c_char_p, []),
@@ -34,6 +34,12 @@ _SIGNATURES = {
     "jspsr_nlspn_affinity_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "jspsr_nlspn_affinity_backward": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "jspsr_spn_host_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    # include/jspsr_tiles.h
+    "jspsr_tiles_crop": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "jspsr_tiles_merge": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "jspsr_loss_l1_l2_grad": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_void_p]),
+    "jspsr_dem_metrics": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float, c_float, c_int, c_void_p]),
     "jspsr_spn_forward_host": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_int]),
 }
 

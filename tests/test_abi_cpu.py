@@ -11,7 +11,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADER = os.path.join(ROOT, "include", "jspsr_spn.h")
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("jspsr_spn.h", "jspsr_tiles.h")]
 
 
 @pytest.fixture(scope="module")
@@ -23,17 +23,17 @@ def lib():
 
 
 def declared_functions():
-    text = open(HEADER).read()
+    text = "".join(open(h).read() for h in HEADERS)
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(jspsr_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 14, names
+    assert len(names) == 18, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
-        assert hasattr(handle, n), f"{n} is declared in include/jspsr_spn.h but not exported"
+        assert hasattr(handle, n), f"{n} is declared in include/*.h but not exported"
     assert sorted(lib.exported_symbols()) == names, "jspsr_b200/_lib.py binds a different set than the header"
 
 

@@ -1,0 +1,254 @@
+"""GPU parity tests of the components either side of the hot path, through the C ABI:
+
+* tile scheduler + blended merge: BIT-EXACT against the fixtures made by the reference's own TileCrop / add_padding /
+  gen_weight_row / gen_weight_col / copyto_add (tests/golden/tiles_reference.npz) and against the numpy oracle on
+  seeded inputs (index work and float64 arithmetic in the reference's order: the bar is equality);
+* loss + metric epilogue: the four losses within 1e-5 relative of the reference's fp32 MultiLoss and of the fp64
+  oracle; the gradient within 1e-5 of the tensor scale, excluding the rare pixels next to a Sobel difference whose
+  sign is decided by rounding (|difference| < 1e-6: the loss is not differentiable there); RMSE/MAE within 1e-6
+  relative of the reference's MeterRMSE, identical at the 4 decimals the reference prints.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import epilogue_oracle as E  # noqa: E402
+from oracle import tiles_oracle as T  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def jb():
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    import jspsr_b200
+    from jspsr_b200 import _lib
+    _lib.lib()
+    return jspsr_b200
+
+
+@pytest.fixture(scope="module")
+def tiles_ref():
+    return np.load(os.path.join(GOLDEN, "tiles_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def epi_ref():
+    return np.load(os.path.join(GOLDEN, "epilogue_reference.npz"))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ tile scheduler
+@pytest.mark.parametrize("tag,n_tile", [("crop70", None), ("crop56", 4), ("crop129", None)])
+def test_crop_matches_reference_tilecrop(jb, tiles_ref, tag, n_tile):
+    size, k, stride, n = (int(v) for v in tiles_ref[tag + "_meta"])
+    raster = dev(tiles_ref[tag + "_img"].transpose(2, 0, 1))
+    got = jb.tiles.crop_tiles(raster, k, n_tile)
+    assert got.shape == (n, 3, k, k)
+    assert np.array_equal(got.cpu().numpy(), tiles_ref[tag + "_tiles"])
+
+
+@pytest.mark.parametrize("tag", ["pad50", "pad100"])
+def test_mirror_padding_matches_reference(jb, tiles_ref, tag):
+    img, pad = tiles_ref[tag + "_img"], int(tiles_ref[tag + "_pad"][0])
+    assert jb.tiles.cal_pad(*img.shape[:2]) == pad
+    got = jb.tiles.add_padding(dev(img.transpose(2, 0, 1)), pad)
+    assert np.array_equal(got.cpu().numpy(), tiles_ref[tag + "_padded"].transpose(2, 0, 1))
+    assert np.array_equal(jb.tiles.remove_padding(got, pad).cpu().numpy(), img.transpose(2, 0, 1))
+
+
+def test_crop_with_padding_and_explicit_walk_matches_oracle(jb):
+    rng = np.random.default_rng(7)
+    img = rng.random((100, 100, 2), dtype=np.float32)
+    want = T.crop_tiles(img, 32, None, pad=14)                 # 128 -> 5 x 5 tiles of 32, stride 24
+    got = jb.tiles.crop_tiles(dev(img.transpose(2, 0, 1)), 32, pad=14)
+    assert want.shape == (25, 2, 32, 32) and np.array_equal(got.cpu().numpy(), want)
+    # rectangular strip, explicit walk
+    strip = rng.random((40, 200, 1), dtype=np.float32)
+    got = jb.tiles.crop_tiles(dev(strip.transpose(2, 0, 1)), 16, stride=12, grid=(3, 16)).cpu().numpy()
+    for r in range(3):
+        for c in range(16):
+            assert np.array_equal(got[r * 16 + c, 0], strip[12 * r:12 * r + 16, 12 * c:12 * c + 16, 0])
+
+
+# ------------------------------------------------------------------ blended merge
+@pytest.mark.parametrize("tag", ["merge9", "merge4", "merge9_b0"])
+def test_merge_matches_reference_bitwise(jb, tiles_ref, tag):
+    full, k, n, border = tiles_ref[tag + "_meta"]
+    tiles = tiles_ref[tag + "_tiles_q"].astype(np.float32) * np.float32(0.25)
+    got = jb.tiles.merge_tiles(dev(tiles), float(border), int(full))
+    assert got.dtype == torch.float64
+    got = got.cpu().numpy()
+    ref = tiles_ref[tag + "_merged"]
+    assert np.array_equal(got if tag == "merge9" else got[::3, ::2], ref)
+    # model-shaped input [N,1,k,k] and fp32 output (= the float64 result rounded once)
+    got32 = jb.tiles.merge_tiles(dev(tiles[:, None]), float(border), int(full), dtype=torch.float32).cpu().numpy()
+    assert np.array_equal(got32, got.astype(np.float32))
+
+
+@pytest.mark.parametrize("k,border,full,S", [(32, 0.0, 132, 3), (40, 0.1, 100, 2), (128, 0.05, 334, 4), (24, 0.0, 42, 1)])
+def test_merge_matches_oracle_bitwise(jb, k, border, full, S):
+    rng = np.random.default_rng(k + S)
+    b, L, out, stride, n_x, p = T.merge_geometry(k, border, full)
+    tiles = (1000.0 * rng.random((S, n_x * n_x, k, k)) - 100.0).astype(np.float32)
+    got = jb.tiles.merge_tiles(dev(tiles), border, full).cpu().numpy()
+    for s in range(S):
+        assert np.array_equal(got[s], T.merge_tiles(tiles[s], border, full)), (s, n_x, p)
+
+
+def test_merge_properties_at_raster_scale(jb):
+    # 40 x 40 tiles of 128 (crop 6, stride 103): a 4133 x 4133 raster per call
+    k, crop, stride, n = 128, 6, 103, 40
+    L = k - 2 * crop
+    out = stride * (n - 1) + L
+    tiles = torch.full((1, n * n, k, k), 12.5, device="cuda")
+    m = jb.tiles.merge_tiles(tiles, 0.05, stride=stride, grid=(n, n))
+    assert m.shape == (1, out, out) and float((m - 12.5).abs().max()) < 1e-12     # ramps sum to one
+    # crop -> merge round trip: tiles cut from one raster blend back to the raster (away from rounding)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    raster = torch.rand(1, stride * (n - 1) + k, stride * (n - 1) + k, device="cuda", generator=g)
+    t = jb.tiles.crop_tiles(raster, k, stride=stride, grid=(n, n))                # [n*n,1,k,k]
+    back = jb.tiles.merge_tiles(t.reshape(1, n * n, k, k), 0.05, stride=stride, grid=(n, n))
+    assert float((back[0] - raster[0, crop:-crop, crop:-crop].double()).abs().max()) < 1e-7
+    # linearity in the tiles
+    a = torch.rand(1, 9, 128, 128, device="cuda", generator=g)
+    b2 = torch.rand(1, 9, 128, 128, device="cuda", generator=g)
+    lhs = jb.tiles.merge_tiles(a + b2)
+    rhs = jb.tiles.merge_tiles(a) + jb.tiles.merge_tiles(b2)
+    assert float((lhs - rhs).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------ loss
+def kink_mask(pred, gt, eps=1e-6):
+    """Pixels whose gradient depends on a Sobel difference smaller than eps (3x3 neighbourhood, border folds)."""
+    ds = E.spatial_gradient(pred.astype(np.float64)) - E.spatial_gradient(gt.astype(np.float64))
+    small = np.abs(ds) < eps                                   # [B,C,2,H,W]: d/dx, d/dy
+    H, W = pred.shape[-2:]
+    if W == 1:
+        small[:, :, 0] = False                                 # replicate padding: d/dx is identically 0, no kink
+    if H == 1:
+        small[:, :, 1] = False
+    near = small.any(axis=2)                                   # [B,C,H,W]
+    d0 = np.abs(pred.astype(np.float64) - gt.astype(np.float64)) < 1e-9
+    pad = np.pad(near, ((0, 0), (0, 0), (1, 1), (1, 1)), mode="edge")
+    H, W = near.shape[-2:]
+    out = np.zeros_like(near)
+    for i in range(3):
+        for j in range(3):
+            out |= pad[..., i:i + H, j:j + W]
+    return out | d0
+
+
+def check_loss(jb, pred, gt, ref_losses=None, ref_grad=None):
+    from jspsr_b200 import epilogue as EP
+    losses, grad = EP.loss_l1_l2_grad(dev(pred), dev(gt))
+    losses = losses.cpu().numpy().astype(np.float64)
+    o = E.multi_loss(pred.astype(np.float64), gt.astype(np.float64))
+    for i, kname in enumerate(("L1", "L2", "Grad", "Total")):
+        assert abs(losses[i] - float(o[kname])) <= 1e-5 * abs(float(o[kname])), (kname, losses[i], float(o[kname]))
+        if ref_losses is not None:
+            assert abs(losses[i] - ref_losses[kname]) <= 1e-5 * abs(ref_losses[kname]), (kname, losses[i], ref_losses[kname])
+    want = E.multi_loss_grad(pred.astype(np.float64), gt.astype(np.float64))
+    got = grad.cpu().numpy().astype(np.float64)
+    ok = ~kink_mask(pred, gt)
+    assert ok.mean() > 0.99 or pred.size < 64
+    scale = np.abs(want).max()
+    if not ok.any():
+        return
+    assert np.abs(got - want)[ok].max() <= 1e-5 * scale, (np.abs(got - want)[ok].max(), scale)
+    if ref_grad is not None:
+        assert np.abs(got - ref_grad)[ok].max() <= 1e-5 * scale
+    # losses-only call (no gradient requested) gives the same numbers
+    l2, g2 = EP.loss_l1_l2_grad(dev(pred), dev(gt), want_grad=False)
+    assert g2 is None and np.array_equal(l2.cpu().numpy().astype(np.float64), losses)
+
+
+@pytest.mark.parametrize("tag", ["loss_a", "loss_b", "loss_c"])
+def test_loss_matches_reference_multiloss(jb, epi_ref, tag):
+    ref = {k: float(epi_ref[f"{tag}_{k}_f32"]) for k in ("L1", "L2", "Grad", "Total")}
+    check_loss(jb, epi_ref[tag + "_pred"], epi_ref[tag + "_gt"], ref, epi_ref[tag + "_grad_f32"].astype(np.float64))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (2, 1, 2, 3), (1, 1, 1, 200), (1, 1, 70, 1), (3, 2, 17, 129), (2, 1, 130, 257),
+                                     (70, 1, 128, 128), (1, 1, 334, 334)])
+def test_loss_matches_oracle(jb, B, C, H, W):
+    rng = np.random.default_rng(B * 1000 + H + W)
+    gt = rng.random((B, C, H, W)).astype(np.float32)
+    pred = (gt + 0.05 * rng.normal(size=gt.shape)).astype(np.float32)
+    check_loss(jb, pred, gt)
+
+
+def test_multiloss_module_and_autograd(jb, epi_ref):
+    pred = dev(epi_ref["loss_a_pred"]).requires_grad_()
+    gt = dev(epi_ref["loss_a_gt"])
+    crit = jb.MultiLoss(**{"L1": {"loss_fn": None, "weight": 1}, "L2": {"loss_fn": None, "weight": 1},
+                           "Grad": {"loss_fn": None, "weight": 0.1}})
+    out = crit(pred, gt)
+    assert list(out) == ["L1", "L2", "Grad", "Total"]
+    for k in out:
+        ref = float(epi_ref[f"loss_a_{k}_f32"])
+        assert abs(float(out[k]) - ref) <= 1e-5 * ref
+    (3.0 * out["Total"]).backward()
+    ref = 3.0 * epi_ref["loss_a_grad_f32"].astype(np.float64)
+    ok = ~kink_mask(epi_ref["loss_a_pred"], epi_ref["loss_a_gt"])
+    assert np.abs(pred.grad.cpu().numpy() - ref)[ok].max() <= 1e-5 * np.abs(ref).max()
+    # repeated calls reuse the (self-cleaning) workspace
+    again = crit(pred.detach(), gt)
+    assert float(again["Total"]) == float(out["Total"])
+    # zero difference: all losses and the gradient are exactly zero
+    z = crit(gt.clone().requires_grad_(), gt)
+    assert float(z["Total"]) == 0.0
+
+
+def test_loss_in_cuda_graph(jb):
+    from jspsr_b200 import epilogue as EP
+    g = torch.Generator(device="cuda").manual_seed(1)
+    pred, gt = torch.rand(4, 1, 128, 128, device="cuda", generator=g), torch.rand(4, 1, 128, 128, device="cuda", generator=g)
+    eager, eager_grad = EP.loss_l1_l2_grad(pred, gt)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        EP.loss_l1_l2_grad(pred, gt)      # allocates this stream's workspace outside the capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            losses, grad = EP.loss_l1_l2_grad(pred, gt)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(losses, eager, rtol=1e-6, atol=0) and torch.equal(grad, eager_grad)
+
+
+# ------------------------------------------------------------------ metrics
+@pytest.mark.parametrize("tag", ["metric_log", "metric_lin"])
+def test_metrics_match_reference_meter(jb, epi_ref, tag):
+    vmin, vmax, elev_log, border = epi_ref[tag + "_meta"]
+    pred, gt = dev(epi_ref[tag + "_pred"]), dev(epi_ref[tag + "_gt"])
+    m = jb.epilogue.dem_metrics(pred, gt, float(border), float(vmin), float(vmax), bool(elev_log))
+    ref = epi_ref[tag + "_sample_rmse"]
+    assert np.allclose(m["rmse"].cpu().numpy(), ref, rtol=2e-6, atol=0)
+    meter = jb.MeterRMSE("local", border=float(border), value_min=float(vmin), value_max=float(vmax), verbose=False)
+    for i in range(pred.shape[0]):                       # valid_batch_size 1, as the reference's loop
+        meter.update(pred[i:i + 1], gt[i:i + 1], elev_log=bool(elev_log))
+    assert f"{meter.get_score():.4f}" == f"{float(epi_ref[tag + '_score']):.4f}"
+    o = E.dem_metrics(epi_ref[tag + "_pred"], epi_ref[tag + "_gt"], float(border), float(vmin), float(vmax), bool(elev_log))
+    assert np.allclose(m["mae"].cpu().numpy(), o["mae"], rtol=2e-6, atol=0)
+    assert np.allclose(m["sum_sq"].cpu().numpy(), o["sum_sq"], rtol=4e-6, atol=0)
+
+
+@pytest.mark.parametrize("B,H,W,border", [(1, 8, 8, 0.0), (5, 33, 77, 0.1), (70, 128, 128, 0.05), (1, 2048, 2048, 0.05)])
+def test_metrics_match_oracle(jb, B, H, W, border):
+    rng = np.random.default_rng(B + H)
+    gt = rng.random((B, 1, H, W)).astype(np.float32)
+    pred = (gt + 0.02 * rng.normal(size=gt.shape)).astype(np.float32)
+    for elev_log in (True, False):
+        m = jb.epilogue.dem_metrics(dev(pred), dev(gt), border, -80.0, 929.0, elev_log)
+        o = E.dem_metrics(pred, gt, border, -80.0, 929.0, elev_log)
+        assert np.allclose(m["rmse"].cpu().numpy(), o["rmse"], rtol=2e-6, atol=0)
+        assert np.allclose(m["mae"].cpu().numpy(), o["mae"], rtol=2e-6, atol=0)

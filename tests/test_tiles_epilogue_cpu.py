@@ -1,0 +1,163 @@
+"""CPU tests for the tile scheduler / blended merge and the loss + metric epilogue (rank 4):
+the numpy oracles against the fixtures produced by the reference's own functions (tests/golden/tiles_reference.npz,
+epilogue_reference.npz; generators: make_golden_tiles.py, make_golden_epilogue.py), the host-side bookkeeping of
+the Python mirror against the oracle, and argument validation of the new C-ABI entry points (no kernel launch)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import epilogue_oracle as E
+from oracle import tiles_oracle as T
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiles_ref():
+    return np.load(os.path.join(GOLDEN, "tiles_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def epi_ref():
+    return np.load(os.path.join(GOLDEN, "epilogue_reference.npz"))
+
+
+def merge_case(g, tag):
+    full, k, n, border = g[tag + "_meta"]
+    tiles = g[tag + "_tiles_q"].astype(np.float32) * np.float32(0.25)
+    return tiles, int(full), int(k), int(n), float(border)
+
+
+@pytest.mark.parametrize("tag,n_tile", [("crop70", None), ("crop56", 4), ("crop129", None)])
+def test_oracle_tilecrop_matches_reference(tiles_ref, tag, n_tile):
+    size, k, stride, n = (int(v) for v in tiles_ref[tag + "_meta"])
+    assert T.get_tile(size, k, n_tile) == (stride, n)
+    assert np.array_equal(T.crop_tiles(tiles_ref[tag + "_img"], k, n_tile), tiles_ref[tag + "_tiles"])
+    assert tuple(tiles_ref["crop334_meta"]) == (334, 128, *T.get_tile(334, 128)) == (334, 128, 103, 9)
+
+
+@pytest.mark.parametrize("tag", ["pad50", "pad100"])
+def test_oracle_mirror_padding_matches_reference(tiles_ref, tag):
+    img, pad = tiles_ref[tag + "_img"], int(tiles_ref[tag + "_pad"][0])
+    assert T.cal_pad(*img.shape[:2]) == pad and T.cal_pad(334, 334) == 89 and T.cal_pad(128, 128) == 0
+    padded = T.add_padding(img, pad)
+    assert np.array_equal(padded, tiles_ref[tag + "_padded"])
+    assert np.array_equal(T.remove_padding(padded, pad), img)
+    # the quirk that the restatement keeps: the bottom border starts one row early (utils.py:1517)
+    assert np.array_equal(padded[pad + img.shape[0], pad:-pad], img[-2]) and not np.array_equal(padded[pad + img.shape[0], pad:-pad], img[-1])
+
+
+@pytest.mark.parametrize("tag", ["merge9", "merge4", "merge9_b0"])
+def test_oracle_merge_matches_reference_bitwise(tiles_ref, tag):
+    tiles, full, k, n, border = merge_case(tiles_ref, tag)
+    b, L, out, stride, n_x, p = T.merge_geometry(k, border, full)
+    for i in range(n):
+        assert np.array_equal(T.weight_1d(i % n_x, n_x, L, p), tiles_ref[tag + "_wrow"][i])
+    for i in range(n_x):
+        assert np.array_equal(T.weight_1d(i, n_x, L, p), tiles_ref[tag + "_wcol"][i])
+    merged = T.merge_tiles(tiles, border, full)
+    assert merged.dtype == np.float64 and merged.shape == (out, out)
+    ref = tiles_ref[tag + "_merged"]
+    assert np.array_equal(merged if tag == "merge9" else merged[::3, ::2], ref)
+
+
+def test_merge_of_constant_tiles_is_constant():
+    # the ramps of two overlapping tiles sum to one: a constant field survives the merge (to rounding)
+    tiles = np.full((9, 128, 128), 37.25, np.float32)
+    assert np.abs(T.merge_tiles(tiles, 0.05, 334) - 37.25).max() < 1e-12
+
+
+def test_python_mirror_bookkeeping_matches_oracle():
+    from jspsr_b200 import tiles as P
+    for w, k, n in ((334, 128, None), (70, 32, None), (56, 32, 4), (129, 33, None), (128, 128, None)):
+        assert P.get_tile(w, k, n) == T.get_tile(w, k, n)
+    for h in (50, 100, 128, 334, 500):
+        assert P.cal_pad(h, h) == T.cal_pad(h, h)
+    for k, border, full in ((128, 0.05, 334), (256, 0.05, 334), (128, 0.0, 334)):
+        b, L, out, stride, n_x, _ = T.merge_geometry(k, border, full)
+        assert P.merge_geometry(k, border, full) == (b, L, out, stride, n_x)
+    with pytest.raises(AssertionError):
+        P.get_tile(335, 128)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.crop_tiles(torch.rand(1, 70, 70), 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.merge_tiles(torch.rand(9, 128, 128))
+
+
+@pytest.mark.parametrize("tag", ["loss_a", "loss_b", "loss_c"])
+def test_oracle_loss_matches_reference(epi_ref, tag):
+    p32, g32 = epi_ref[tag + "_pred"], epi_ref[tag + "_gt"]
+    o = E.multi_loss(p32.astype(np.float64), g32.astype(np.float64))
+    for k in ("L1", "L2", "Grad", "Total"):
+        ref = float(epi_ref[f"{tag}_{k}_f32"])
+        assert abs(float(o[k]) - ref) <= 2e-6 * abs(ref), (k, float(o[k]), ref)
+    grad = E.multi_loss_grad(p32.astype(np.float64), g32.astype(np.float64))
+    ref = epi_ref[tag + "_grad_f32"].astype(np.float64)
+    # the Sobel-L1 gradient is a sum of signs: it jumps where a Sobel difference crosses zero, which fp32 and fp64
+    # evaluations may place on different sides; such pixels are rare and excluded
+    bad = np.abs(grad - ref) > 1e-5 * np.abs(ref).max()
+    assert bad.mean() < 1e-3, bad.mean()
+    o32 = E.multi_loss(p32, g32)
+    assert abs(float(o32["Total"]) - float(epi_ref[tag + "_Total_f32"])) <= 1e-5 * float(o32["Total"])
+
+
+def test_oracle_loss_gradient_is_the_derivative():
+    # finite differences of Total (fp64) away from the kinks of |.|
+    rng = np.random.default_rng(5)
+    gt = rng.random((1, 1, 6, 7))
+    pred = gt + 0.1 * rng.normal(size=gt.shape)
+    g = E.multi_loss_grad(pred, gt)
+    for (y, x) in ((0, 0), (0, 3), (5, 6), (2, 0), (3, 4), (5, 2)):
+        e = np.zeros_like(pred)
+        e[0, 0, y, x] = 1e-7
+        num = (E.multi_loss(pred + e, gt)["Total"] - E.multi_loss(pred - e, gt)["Total"]) / 2e-7
+        assert abs(num - g[0, 0, y, x]) < 1e-6, (y, x, num, g[0, 0, y, x])
+
+
+@pytest.mark.parametrize("tag", ["metric_log", "metric_lin"])
+def test_oracle_metrics_match_reference_meter(epi_ref, tag):
+    vmin, vmax, elev_log, border = epi_ref[tag + "_meta"]
+    m = E.dem_metrics(epi_ref[tag + "_pred"], epi_ref[tag + "_gt"], float(border), float(vmin), float(vmax), bool(elev_log))
+    assert np.allclose(m["rmse"], epi_ref[tag + "_sample_rmse"], rtol=1e-6, atol=0)
+    assert f"{m['rmse'].mean():.4f}" == f"{float(epi_ref[tag + '_score']):.4f}"   # "identical to printed precision"
+
+
+def test_new_entry_points_validate_before_any_cuda_work():
+    from jspsr_b200 import _lib
+    h = _lib.lib()
+    one = ctypes.c_void_p(16)
+    cases = [
+        (lambda: h.jspsr_tiles_crop(one, one, 1, 8, 8, 0, 4, 2, 0, 3, None), -1, "non-positive"),
+        (lambda: h.jspsr_tiles_crop(one, one, 1, 8, 8, 0, 4, 3, 3, 3, None), -1, "leaves"),
+        (lambda: h.jspsr_tiles_crop(one, one, 1, 8, 8, 9, 4, 2, 3, 3, None), -1, "wider"),
+        (lambda: h.jspsr_tiles_crop(None, one, 1, 8, 8, 0, 4, 2, 3, 3, None), -1, "null"),
+        (lambda: h.jspsr_tiles_merge(one, one, 1, 3, 3, 8, 4, 4, 1, None), -1, "no pixels"),
+        (lambda: h.jspsr_tiles_merge(one, one, 1, 3, 3, 8, 1, 7, 1, None), -1, "touch"),
+        (lambda: h.jspsr_tiles_merge(one, ctypes.c_void_p(20), 1, 3, 3, 8, 1, 5, 1, None), -4, "misaligned"),
+        (lambda: h.jspsr_loss_l1_l2_grad(one, one, 1.0, 1.0, 0.1, one, None, None, 1, 8, 8, None), -1, "null"),
+        (lambda: h.jspsr_loss_l1_l2_grad(one, one, 1.0, 1.0, 0.1, one, None, ctypes.c_void_p(8), 1, 8, 8, None), -4, "workspace"),
+        (lambda: h.jspsr_loss_l1_l2_grad(one, one, 1.0, 1.0, 0.1, one, None, one, 0, 8, 8, None), -1, "non-positive"),
+        (lambda: h.jspsr_dem_metrics(one, one, one, 1, 8, 8, 4, 0, 0.0, 1.0, 0, None), -1, "border"),
+        (lambda: h.jspsr_dem_metrics(one, one, one, 1, 8, 8, 0, 0, 1.0, 1.0, 1, None), -1, "value_max"),
+        (lambda: h.jspsr_dem_metrics(one, one, ctypes.c_void_p(20), 1, 8, 8, 0, 0, 0.0, 1.0, 0, None), -4, "misaligned"),
+    ]
+    for call, want, needle in cases:
+        rc = call()
+        assert rc == want, (rc, want, needle, h.jspsr_last_error())
+        assert needle in h.jspsr_last_error().decode(), (needle, h.jspsr_last_error())
+
+
+def test_multiloss_mirror_keeps_the_reference_contract():
+    import jspsr_b200 as jb
+    crit = jb.MultiLoss(**{"L1": {"loss_fn": None, "weight": 1}, "L2": {"loss_fn": None, "weight": 1},
+                           "Grad": {"loss_fn": None, "weight": 0.1}})
+    assert crit.weights == {"L1": 1.0, "L2": 1.0, "Grad": 0.1}
+    with pytest.raises(NotImplementedError):
+        jb.MultiLoss(SSIM={"loss_fn": None, "weight": 1})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        jb.MeterRMSE("local", border=0.05).update(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
