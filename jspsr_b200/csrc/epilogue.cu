@@ -19,29 +19,40 @@ int jspsr_internal_fail(int code, const char* msg);  // abi.cu: sets the thread'
 
 namespace jspsr {
 
-constexpr int LT_H = 16;    // rows per CTA
-constexpr int LT_W = 128;   // columns per CTA
-constexpr int LD_H = LT_H + 4, LD_W = LT_W + 4;   // staged difference tile (halo 2: Sobel of the halo-1 ring)
-constexpr int LS_H = LT_H + 2, LS_W = LT_W + 2;   // sign tile (halo 1)
+constexpr int LT_H = 32;    // rows per CTA
+constexpr int LT_W = 128;   // columns per CTA (one float4 per lane)
+constexpr int LD_H = LT_H + 4;      // staged difference rows: image row y0 - 2 + r
+constexpr int LD_W = LT_W + 8;      // staged difference columns: image column x0 - 4 + c (columns 2 .. 133 are used)
+constexpr int LS_H = LT_H + 2;      // sign rows: image row y0 - 1 + r
+constexpr int LS_B = LT_W + 8;      // sign row stride in bytes: image column x0 - 4 + c (columns 3 .. 132 are used)
+constexpr int LOSS_SLOTS = 4;       // partial sums are spread over 4 slots of the workspace (fewer same-address atomics)
 
 struct alignas(16) LossWs {
-    double sums[3];  // sum |d|, sum d^2, sum |Sobel(pred) - Sobel(gt)|
+    double sums[LOSS_SLOTS][3];  // sum |d|, sum d^2, sum |Sobel(pred) - Sobel(gt)| * 8
     unsigned int ticket;
-    unsigned int pad;
+    unsigned int pad[3];
 };
 static_assert(sizeof(LossWs) <= sizeof(ReduceWs), "the propagation's reduction workspace is large enough");
 
 __device__ __forceinline__ float sgn(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+// sign + 1 in {0, 1, 2}: the sign tiles hold biased signs so that four of them add up bytewise in one 32-bit integer
+__device__ __forceinline__ unsigned sgn1(float v) { return 1u + (unsigned)(v > 0.f) - (unsigned)(v < 0.f); }
 
-// One CTA: LT_H x LT_W pixels of one plane.
-template <bool WRITE_GRAD>
+// One CTA: LT_H x LT_W pixels of one plane, 8 warps; lane j owns the four columns x0 + 4j .. 4j + 3.
+//
+// d = pred - gt.  With kornia's replicate padding the Sobel pair is separable,
+//     gx = Ay (x) Dx d,  gy = Dy (x) Ax d,  A = (1, 2, 1) with replicate border, D = (-1, 0, 1) with replicate border,
+// and so is the adjoint the gradient needs: A^T s = (1, 2, 1) * s with s REPLICATED one past the border, D^T s =
+// s[i - 1] - s[i + 1] with s NEGATED-and-replicated one past the border.  The sign tiles therefore carry one ring of
+// such extended values around the image and every pixel, border or not, uses the same 12-tap formula (no divergence).
+template <bool WRITE_GRAD, bool VEC>
 __global__ void __launch_bounds__(THREADS)
 loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ grad,
                        float* __restrict__ losses4, LossWs* __restrict__ ws, int H, int W, int tiles_x, int tiles_y,
                        float w_l1, float w_l2, float w_grad, float inv_n) {
-    __shared__ float s_d[LD_H][LD_W];
-    __shared__ signed char s_sx[LS_H][LS_W + 2];
-    __shared__ signed char s_sy[LS_H][LS_W + 2];
+    __shared__ __align__(16) float s_d[LD_H][LD_W];
+    __shared__ __align__(16) unsigned char s_sx[WRITE_GRAD ? LS_H : 1][LS_B];
+    __shared__ __align__(16) unsigned char s_sy[WRITE_GRAD ? LS_H : 1][LS_B];
     __shared__ float s_red[WARPS][3];
     __shared__ bool s_last;
 
@@ -52,92 +63,231 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     const int y0 = ty * LT_H, x0 = tx * LT_W;
     const float* __restrict__ p = pred + plane;
     const float* __restrict__ g = gt + plane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- stage d = pred - gt over the tile + halo 2, replicate-clamped (kornia pads with mode "replicate") ----
-    for (int i = threadIdx.x; i < LD_H * LD_W; i += THREADS) {
-        const int r = i / LD_W, c = i - r * LD_W;
-        const int y = min(max(y0 - 2 + r, 0), H - 1), x = min(max(x0 - 2 + c, 0), W - 1);
-        const size_t o = (size_t)y * W + x;
-        s_d[r][c] = ld_stream(p + o) - ld_stream(g + o);
-    }
-    __syncthreads();
+    float a_l1 = 0.f, a_l2 = 0.f, a_grad = 0.f;
 
-    // ---- signs of the Sobel difference on the tile + halo 1 (zero outside the image); |.| summed inside the tile ----
-    float a_grad = 0.f;
-    for (int i = threadIdx.x; i < LS_H * LS_W; i += THREADS) {
-        const int r = i / LS_W, c = i - r * LS_W;          // output position (y0 - 1 + r, x0 - 1 + c)
-        const int y = y0 - 1 + r, x = x0 - 1 + c;
-        signed char sx = 0, sy = 0;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            // staged index of image (y + a, x + b) is [r + 1 + a][c + 1 + b]
-            const float d00 = s_d[r][c], d01 = s_d[r][c + 1], d02 = s_d[r][c + 2];
-            const float d10 = s_d[r + 1][c], d12 = s_d[r + 1][c + 2];
-            const float d20 = s_d[r + 2][c], d21 = s_d[r + 2][c + 1], d22 = s_d[r + 2][c + 2];
-            const float gx = ((d02 - d00) + 2.f * (d12 - d10) + (d22 - d20)) * 0.125f;
-            const float gy = ((d20 - d00) + 2.f * (d21 - d01) + (d22 - d02)) * 0.125f;
-            sx = (signed char)sgn(gx);
-            sy = (signed char)sgn(gy);
-            if (r >= 1 && r <= LT_H && c >= 1 && c <= LT_W) a_grad += fabsf(gx) + fabsf(gy);
-        }
-        s_sx[r][c] = sx;
-        s_sy[r][c] = sy;
-    }
-    __syncthreads();
-
-    // ---- per pixel: L1, L2 and the gradient of Total ----
-    float a_l1 = 0.f, a_l2 = 0.f;
-    const float c_pix_l1 = w_l1 * inv_n, c_pix_l2 = 2.f * w_l2 * inv_n, c_sob = w_grad * 0.5f * inv_n * 0.125f;
-    // S(oy, ox): sign tile lookups by image position; positions outside the staged ring are outside the image
-    auto SX = [&](int oy, int ox) -> float {
-        return (oy < 0 || oy >= H || ox < 0 || ox >= W) ? 0.f : (float)s_sx[oy - y0 + 1][ox - x0 + 1];
-    };
-    auto SY = [&](int oy, int ox) -> float {
-        return (oy < 0 || oy >= H || ox < 0 || ox >= W) ? 0.f : (float)s_sy[oy - y0 + 1][ox - x0 + 1];
-    };
-    // gradient w.r.t. the PADDED image at padded position (u, v) (image pixel (u - 1, v - 1)), times 8:
-    //   sum_{i,j} kx[i][j] * sx[u - i][v - j] + ky[i][j] * sy[u - i][v - j],  kx[i][j] = r[i] * c[j], ky = kx^T,
-    //   r = (1, 2, 1), c = (-1, 0, 1)
-    auto GP = [&](int u, int v) -> float {
-        float acc = 0.f;
+    // ---- phase 1: d over rows y0 - 2 .. y0 + LT_H + 1, columns x0 - 2 .. x0 + LT_W + 1, replicate-clamped ----
+    if (VEC) {
+        // W % 4 == 0 and 16-byte aligned planes: a lane's float4 is entirely inside or entirely outside the image
+        constexpr int ROWS_PER_WARP = (LD_H + WARPS - 1) / WARPS;   // 5
+        float4 vp[ROWS_PER_WARP], vg[ROWS_PER_WARP];
+        const int xc = x0 + 4 * lane;
+        const bool in_x = xc < W;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float ri = (i == 1) ? 2.f : 1.f;
-            acc += ri * (SX(u - i, v - 2) - SX(u - i, v));        // j = 2 (+1) and j = 0 (-1)
-            acc += ri * (SY(u - 2, v - i) - SY(u, v - i));        // ky[2][.] = +r, ky[0][.] = -r
-        }
-        return acc;
-    };
-    for (int i = threadIdx.x; i < LT_H * LT_W; i += THREADS) {
-        const int r = i / LT_W, c = i - r * LT_W;
-        const int y = y0 + r, x = x0 + c;
-        if (y >= H || x >= W) continue;
-        const float d = s_d[r + 2][c + 2];
-        a_l1 += fabsf(d);
-        a_l2 += d * d;
-        if (WRITE_GRAD) {
-            float gs;
-            if (y > 0 && y < H - 1 && x > 0 && x < W - 1) {
-                // interior: u = y + 1, v = x + 1; sign tile index of output (oy, ox) is [oy - y0 + 1][ox - x0 + 1]
-                const int sr = r + 1, sc = c + 1;   // sign-tile index of (y, x)
-                gs = 0.f;
-#pragma unroll
-                for (int k = -1; k <= 1; ++k) {
-                    const float rk = (k == 0) ? 2.f : 1.f;
-                    gs += rk * ((float)s_sx[sr - k][sc - 1] - (float)s_sx[sr - k][sc + 1]);
-                    gs += rk * ((float)s_sy[sr - 1][sc - k] - (float)s_sy[sr + 1][sc - k]);
+        for (int i = 0; i < ROWS_PER_WARP; ++i) {
+            const int r = warp + WARPS * i;
+            const int y = min(max(y0 - 2 + r, 0), H - 1);
+            if (r < LD_H) {
+                if (in_x) {
+                    vp[i] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)y * W + xc));
+                    vg[i] = __ldcs(reinterpret_cast<const float4*>(g + (size_t)y * W + xc));
+                } else {
+                    const float a = __ldg(p + (size_t)y * W + (W - 1)), b = __ldg(g + (size_t)y * W + (W - 1));
+                    vp[i] = make_float4(a, a, a, a);
+                    vg[i] = make_float4(b, b, b, b);
                 }
-            } else {
-                // border pixels also receive what the replicate padding folds back onto them
-                gs = 0.f;
-                for (int u = (y == 0 ? 0 : y + 1); u <= (y == H - 1 ? H + 1 : y + 1); ++u)
-                    for (int v = (x == 0 ? 0 : x + 1); v <= (x == W - 1 ? W + 1 : x + 1); ++v) gs += GP(u, v);
             }
-            st_stream(grad + plane + (size_t)y * W + x, c_pix_l1 * sgn(d) + c_pix_l2 * d + c_sob * gs);
+        }
+        // the two halo columns on either side: LD_H rows x 4 columns
+        float hp = 0.f, hg = 0.f;
+        const int hr = threadIdx.x >> 2, hq = threadIdx.x & 3;          // row, which of the 4 columns
+        const int hc = (hq < 2) ? (2 + hq) : (LT_W + 2 + hq);            // staged column 2, 3, 132, 133
+        if (hr < LD_H) {
+            const int y = min(max(y0 - 2 + hr, 0), H - 1), x = min(max(x0 - 4 + hc, 0), W - 1);
+            hp = __ldg(p + (size_t)y * W + x);
+            hg = __ldg(g + (size_t)y * W + x);
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_WARP; ++i) {
+            const int r = warp + WARPS * i;
+            if (r < LD_H) {
+                const float4 d = make_float4(vp[i].x - vg[i].x, vp[i].y - vg[i].y, vp[i].z - vg[i].z, vp[i].w - vg[i].w);
+                *reinterpret_cast<float4*>(&s_d[r][4 + 4 * lane]) = d;
+                if (r >= 2 && r < LT_H + 2 && y0 - 2 + r < H && in_x) {       // own pixels: L1 and L2 from registers
+                    a_l1 += (fabsf(d.x) + fabsf(d.y)) + (fabsf(d.z) + fabsf(d.w));
+                    a_l2 += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+                }
+            }
+        }
+        if (hr < LD_H) s_d[hr][hc] = hp - hg;
+    } else {
+        for (int i = threadIdx.x; i < LD_H * (LT_W + 4); i += THREADS) {
+            const int r = i / (LT_W + 4), c = 2 + (i - r * (LT_W + 4));
+            const int yy = y0 - 2 + r, xx = x0 - 4 + c;
+            const int y = min(max(yy, 0), H - 1), x = min(max(xx, 0), W - 1);
+            const size_t o = (size_t)y * W + x;
+            const float d = __ldg(p + o) - __ldg(g + o);
+            s_d[r][c] = d;
+            if (r >= 2 && r < LT_H + 2 && c >= 4 && c < LT_W + 4 && yy < H && xx < W) {
+                a_l1 += fabsf(d);
+                a_l2 += d * d;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: Sobel of d, its |.| sum and (for the gradient) its biased signs ----
+    // A warp marches down a band of sign rows with the horizontal difference / smoothing of three d rows in registers.
+    {
+        const int ra = (warp * LS_H) / WARPS, rb = ((warp + 1) * LS_H) / WARPS;   // sign rows [ra, rb): image y0 - 1 + r
+        float hd[3][4], hs[3][4];
+        auto load_row = [&](int dr, float (&hdo)[4], float (&hso)[4]) {
+            // d at image columns x0 + 4 lane - 1 .. + 4: own float4, one value from each neighbour lane
+            const float4 m = *reinterpret_cast<const float4*>(&s_d[dr][4 + 4 * lane]);
+            float l = __shfl_up_sync(0xffffffffu, m.w, 1);
+            float r = __shfl_down_sync(0xffffffffu, m.x, 1);
+            if (lane == 0) l = s_d[dr][3];
+            if (lane == 31) r = s_d[dr][LT_W + 4];
+            const float e[6] = {l, m.x, m.y, m.z, m.w, r};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                hdo[q] = e[q + 2] - e[q];
+                hso[q] = (e[q] + e[q + 2]) + 2.f * e[q + 1];
+            }
+        };
+        load_row(ra, hd[0], hs[0]);
+        load_row(ra + 1, hd[1], hs[1]);
+#pragma unroll 1
+        for (int r = ra; r < rb; ++r) {
+            load_row(r + 2, hd[2], hs[2]);
+            const int y = y0 - 1 + r;
+            const bool row_in = (y >= 0 && y < H);
+            const bool own = row_in && r >= 1 && r <= LT_H;
+            unsigned px = 0u, py = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float gx = (hd[0][q] + hd[2][q]) + 2.f * hd[1][q];
+                const float gy = hs[2][q] - hs[0][q];
+                const bool in = row_in && (x0 + 4 * lane + q < W);
+                if (own && in) a_grad += fabsf(gx) + fabsf(gy);
+                if (WRITE_GRAD) {
+                    px |= (in ? sgn1(gx) : 1u) << (8 * q);
+                    py |= (in ? sgn1(gy) : 1u) << (8 * q);
+                }
+            }
+            if (WRITE_GRAD) {
+                *reinterpret_cast<unsigned*>(&s_sx[r][4 + 4 * lane]) = px;
+                *reinterpret_cast<unsigned*>(&s_sy[r][4 + 4 * lane]) = py;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                hd[0][q] = hd[1][q]; hd[1][q] = hd[2][q];
+                hs[0][q] = hs[1][q]; hs[1][q] = hs[2][q];
+            }
+        }
+        if (WRITE_GRAD && threadIdx.x < 2 * LS_H) {
+            // the sign columns just left and right of the tile (image columns x0 - 1 and x0 + LT_W)
+            const int side = threadIdx.x / LS_H, r = threadIdx.x - side * LS_H;
+            const int y = y0 - 1 + r, x = side ? x0 + LT_W : x0 - 1;
+            const int c = side ? LT_W + 4 : 3;                          // staged column of x in s_d and in the sign tiles
+            unsigned vx = 1u, vy = 1u;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                const float d00 = s_d[r][c - 1], d01 = s_d[r][c], d02 = s_d[r][c + 1];
+                const float d10 = s_d[r + 1][c - 1], d12 = s_d[r + 1][c + 1];
+                const float d20 = s_d[r + 2][c - 1], d21 = s_d[r + 2][c], d22 = s_d[r + 2][c + 1];
+                vx = sgn1(((d02 - d00) + (d22 - d20)) + 2.f * (d12 - d10));
+                vy = sgn1(((d20 + d22) + 2.f * d21) - ((d00 + d02) + 2.f * d01));
+            }
+            s_sx[r][c] = (unsigned char)vx;
+            s_sy[r][c] = (unsigned char)vy;
+        }
+    }
+
+    if (WRITE_GRAD) {
+        __syncthreads();
+        // ---- the ring one past the image border (only the CTAs that see it): replicate, negated along the
+        //      axis the operator differentiates ----
+        const int sc_r = W - x0 + 4, sr_b = H - y0 + 1;                 // staged column of x = W, staged row of y = H
+        const bool left = (x0 == 0), right = (sc_r <= LT_W + 4), top = (y0 == 0), bottom = (sr_b <= LS_H - 1);
+        if (left || right || top || bottom) {
+            for (int i = threadIdx.x; i < 2 * LS_H + 2 * (LT_W + 2); i += THREADS) {
+                int r, c;
+                bool on;
+                if (i < 2 * LS_H) {                                     // columns x = -1 and x = W, image rows only
+                    const int side = i / LS_H;
+                    r = i - side * LS_H;
+                    c = side ? sc_r : 3;
+                    const int y = y0 - 1 + r;
+                    on = (side ? right : left) && y >= 0 && y < H;
+                } else {                                                // rows y = -1 and y = H, x = -1 .. W
+                    const int k = i - 2 * LS_H;
+                    const int side = k / (LT_W + 2);
+                    c = 3 + (k - side * (LT_W + 2));
+                    r = side ? sr_b : 0;
+                    const int x = x0 - 4 + c;
+                    on = (side ? bottom : top) && x >= -1 && x <= W;
+                }
+                if (on) {
+                    const int y = y0 - 1 + r, x = x0 - 4 + c;
+                    const int yc = min(max(y, 0), H - 1), xc = min(max(x, 0), W - 1);
+                    const unsigned vx = s_sx[yc - y0 + 1][xc - x0 + 4], vy = s_sy[yc - y0 + 1][xc - x0 + 4];
+                    s_sx[r][c] = (unsigned char)((x != xc) ? 2u - vx : vx);
+                    s_sy[r][c] = (unsigned char)((y != yc) ? 2u - vy : vy);
+                }
+            }
+            // (every ring cell is derived from an IMAGE cell, corners included, so one pass needs no ordering)
+        }
+        __syncthreads();
+    }
+
+    if (WRITE_GRAD) {
+        // ---- phase 3: dTotal/dpred; a warp marches down LT_H / WARPS pixel rows, four pixels per lane ----
+        const float c_pix_l1 = w_l1 * inv_n, c_pix_l2 = 2.f * w_l2 * inv_n, c_sob = w_grad * 0.5f * inv_n * 0.125f;
+        constexpr int PR = LT_H / WARPS;
+        const int pr0 = warp * PR;                                    // pixel rows pr0 .. pr0 + PR - 1 (sign rows + 1)
+        // U = (sx[x - 1] - sx[x + 1]) + 2 and V = (sy[x - 1] + 2 sy[x] + sy[x + 1]) + 4 per byte, for one sign row
+        auto row_uv = [&](int sr, unsigned& U, unsigned& V) {
+            const unsigned mx = *reinterpret_cast<const unsigned*>(&s_sx[sr][4 + 4 * lane]);
+            const unsigned my = *reinterpret_cast<const unsigned*>(&s_sy[sr][4 + 4 * lane]);
+            unsigned lx = __shfl_up_sync(0xffffffffu, mx, 1), rx = __shfl_down_sync(0xffffffffu, mx, 1);
+            unsigned ly = __shfl_up_sync(0xffffffffu, my, 1), ry = __shfl_down_sync(0xffffffffu, my, 1);
+            if (lane == 0) {
+                lx = *reinterpret_cast<const unsigned*>(&s_sx[sr][0]);
+                ly = *reinterpret_cast<const unsigned*>(&s_sy[sr][0]);
+            }
+            if (lane == 31) {
+                rx = *reinterpret_cast<const unsigned*>(&s_sx[sr][LT_W + 4]);
+                ry = *reinterpret_cast<const unsigned*>(&s_sy[sr][LT_W + 4]);
+            }
+            const unsigned Lx = __funnelshift_r(lx, mx, 24), Rx = __funnelshift_r(mx, rx, 8);
+            const unsigned Ly = __funnelshift_r(ly, my, 24), Ry = __funnelshift_r(my, ry, 8);
+            U = Lx + (0x02020202u - Rx);
+            V = Ly + 2u * my + Ry;
+        };
+        unsigned U0, V0, U1, V1, U2, V2;
+        row_uv(pr0, U0, V0);
+        row_uv(pr0 + 1, U1, V1);
+#pragma unroll
+        for (int i = 0; i < PR; ++i) {
+            const int pr = pr0 + i, y = y0 + pr;
+            row_uv(pr + 2, U2, V2);
+            // (sum + 16) per byte: U0 + 2 U1 + U2 carries 8, V0 + (8 - V2) carries 8
+            const unsigned G = U0 + 2u * U1 + U2 + V0 + (0x08080808u - V2);
+            const float4 d = *reinterpret_cast<const float4*>(&s_d[pr + 2][4 + 4 * lane]);
+            float4 o;
+            o.x = c_pix_l1 * sgn(d.x) + c_pix_l2 * d.x + c_sob * ((float)(G & 0xffu) - 16.f);
+            o.y = c_pix_l1 * sgn(d.y) + c_pix_l2 * d.y + c_sob * ((float)((G >> 8) & 0xffu) - 16.f);
+            o.z = c_pix_l1 * sgn(d.z) + c_pix_l2 * d.z + c_sob * ((float)((G >> 16) & 0xffu) - 16.f);
+            o.w = c_pix_l1 * sgn(d.w) + c_pix_l2 * d.w + c_sob * ((float)(G >> 24) - 16.f);
+            const int x = x0 + 4 * lane;
+            if (y < H) {
+                float* __restrict__ dst = grad + plane + (size_t)y * W + x;
+                if (VEC) {
+                    if (x < W) __stcs(reinterpret_cast<float4*>(dst), o);
+                } else {
+                    if (x < W) __stcs(dst, o.x);
+                    if (x + 1 < W) __stcs(dst + 1, o.y);
+                    if (x + 2 < W) __stcs(dst + 2, o.z);
+                    if (x + 3 < W) __stcs(dst + 3, o.w);
+                }
+            }
+            U0 = U1; U1 = U2;
+            V0 = V1; V1 = V2;
         }
     }
 
     // ---- thread -> warp -> CTA -> fp64 atomics; the last CTA publishes the four losses ----
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     a_l1 = warp_sum(a_l1);
     a_l2 = warp_sum(a_l2);
     a_grad = warp_sum(a_grad);
@@ -151,7 +301,7 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
         double v = 0.0;
 #pragma unroll
         for (int wi = 0; wi < WARPS; ++wi) v += (double)s_red[wi][threadIdx.x];
-        atomicAdd(&ws->sums[threadIdx.x], v);
+        atomicAdd(&ws->sums[blockIdx.x % LOSS_SLOTS][threadIdx.x], v);
         __threadfence();
     }
     __syncthreads();
@@ -162,20 +312,30 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
+        double tot[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            tot[k] = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < LOSS_SLOTS; ++sl) {
+                tot[k] += atomicAdd(&ws->sums[sl][k], 0.0);
+                ws->sums[sl][k] = 0.0;                         // leave the workspace clean for the next call
+            }
+        }
         const double n_inv = (double)inv_n;
-        const double l1 = atomicAdd(&ws->sums[0], 0.0) * n_inv;
-        const double l2 = atomicAdd(&ws->sums[1], 0.0) * n_inv;
-        const double gr = atomicAdd(&ws->sums[2], 0.0) * n_inv * 0.5;
+        const double l1 = tot[0] * n_inv;
+        const double l2 = tot[1] * n_inv;
+        const double gr = tot[2] * n_inv * 0.5 * 0.125;
         losses4[0] = (float)l1;
         losses4[1] = (float)l2;
         losses4[2] = (float)gr;
         losses4[3] = (float)((double)w_l1 * l1 + (double)w_l2 * l2 + (double)w_grad * gr);
-        ws->sums[0] = ws->sums[1] = ws->sums[2] = 0.0;   // leave the workspace clean for the next call
         ws->ticket = 0u;
     }
 }
 
-// One CTA: a slab of rows of one sample's border-cropped window.  sums[b] = {sum d^2, sum |d|} (fp64 atomics).
+// One CTA: a slab of rows of one sample's border-cropped window; a warp per row, lanes along x, four columns of a
+// row in flight per lane.  sums[b] = {sum d^2, sum |d|} (fp64 atomics).
 __global__ void __launch_bounds__(THREADS)
 dem_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, double* __restrict__ sums, int H, int W,
                    int bh, int bw, float log_range, float range, float vmin, int elev_log, int rows_per_cta) {
@@ -184,36 +344,46 @@ dem_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
     const int hc = H - 2 * bh, wc = W - 2 * bw;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, hc);
     const size_t plane = (size_t)b * H * W;
-    float a_sq = 0.f, a_ab = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double d_sq = 0.0, d_ab = 0.0;
-    for (int r = r0; r < r1; ++r) {
+    for (int r = r0 + warp; r < r1; r += WARPS) {
         const size_t row = plane + (size_t)(bh + r) * W + bw;
-        for (int c = threadIdx.x; c < wc; c += THREADS) {
-            const float pv = fminf(fmaxf(ld_stream(pred + row + c), 0.f), 1.f);   // MeterBase._prepare clamps pred only
-            const float gv = ld_stream(gt + row + c);
-            float pe, ge;
-            if (elev_log) {
-                pe = expf(pv * log_range) + vmin;
-                ge = expf(gv * log_range) + vmin;
-            } else {
-                pe = __fadd_rn(__fmul_rn(pv, range), vmin);
-                ge = __fadd_rn(__fmul_rn(gv, range), vmin);
+        float a_sq = 0.f, a_ab = 0.f;
+        for (int c0 = lane; c0 < wc; c0 += 128) {
+            float pv[4], gv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u;
+                pv[u] = (c < wc) ? __ldcs(pred + row + c) : 0.f;
+                gv[u] = (c < wc) ? __ldcs(gt + row + c) : 0.f;
             }
-            const float d = pe - ge;
-            a_sq += d * d;
-            a_ab += fabsf(d);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (c0 + 32 * u < wc) {
+                    const float pc = fminf(fmaxf(pv[u], 0.f), 1.f);   // MeterBase._prepare clamps pred only
+                    float pe, ge;
+                    if (elev_log) {
+                        pe = expf(pc * log_range) + vmin;
+                        ge = expf(gv[u] * log_range) + vmin;
+                    } else {
+                        pe = __fadd_rn(__fmul_rn(pc, range), vmin);
+                        ge = __fadd_rn(__fmul_rn(gv[u], range), vmin);
+                    }
+                    const float d = pe - ge;
+                    a_sq += d * d;
+                    a_ab += fabsf(d);
+                }
+            }
         }
         // fold the fp32 row partials into fp64 so that long windows do not lose low bits
         d_sq += (double)a_sq;
         d_ab += (double)a_ab;
-        a_sq = a_ab = 0.f;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         d_sq += __shfl_xor_sync(0xffffffffu, d_sq, o);
         d_ab += __shfl_xor_sync(0xffffffffu, d_ab, o);
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_red[warp][0] = d_sq;
         s_red[warp][1] = d_ab;
@@ -244,12 +414,17 @@ extern "C" int jspsr_loss_l1_l2_grad(const float* pred, const float* gt, float w
     const long long ctas = (long long)planes * tiles_x * tiles_y;
     if (ctas > 0x7fffffffLL) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: more than 2^31 tiles");
     const float inv_n = (float)(1.0 / ((double)planes * H * W));
-    if (grad_pred)
-        loss_l1_l2_grad_kernel<true><<<(unsigned)ctas, THREADS, 0, (cudaStream_t)stream>>>(
-            pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, tiles_x, tiles_y, w_l1, w_l2, w_grad, inv_n);
-    else
-        loss_l1_l2_grad_kernel<false><<<(unsigned)ctas, THREADS, 0, (cudaStream_t)stream>>>(
-            pred, gt, nullptr, losses4, (LossWs*)workspace, H, W, tiles_x, tiles_y, w_l1, w_l2, w_grad, inv_n);
+    // float4 path: rows 16-byte aligned (W % 4 == 0 and aligned bases)
+    const bool vec = (W % 4 == 0) && !(((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)grad_pred) & 15);
+#define JSPSR_LAUNCH_LOSS(G, V)                                                                         \
+    loss_l1_l2_grad_kernel<G, V><<<(unsigned)ctas, THREADS, 0, (cudaStream_t)stream>>>(                 \
+        pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, tiles_x, tiles_y, w_l1, w_l2, w_grad, inv_n)
+    if (grad_pred) {
+        if (vec) JSPSR_LAUNCH_LOSS(true, true); else JSPSR_LAUNCH_LOSS(true, false);
+    } else {
+        if (vec) JSPSR_LAUNCH_LOSS(false, true); else JSPSR_LAUNCH_LOSS(false, false);
+    }
+#undef JSPSR_LAUNCH_LOSS
     const cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         char msg[256];
@@ -273,9 +448,9 @@ extern "C" int jspsr_dem_metrics(const float* pred, const float* gt, double* sum
     cudaError_t ce = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B, (cudaStream_t)stream);
     if (ce == cudaSuccess) {
         const int hc = H - 2 * border_h;
-        // enough CTAs to fill the GPU twice over, at least 4 rows each
-        int slabs = (2 * 148 * 4 + B - 1) / B;
-        slabs = max(1, min(slabs, (hc + 3) / 4));
+        // enough CTAs to fill the GPU twice over (8 resident per SM), at least one row per warp each
+        int slabs = (2 * 148 * 8 + B - 1) / B;
+        slabs = max(1, min(slabs, (hc + WARPS - 1) / WARPS));
         const int rows_per_cta = (hc + slabs - 1) / slabs;
         slabs = (hc + rows_per_cta - 1) / rows_per_cta;
         const float range = (float)((double)value_max - (double)value_min);

@@ -29,23 +29,51 @@ __device__ __forceinline__ int pad_source(int i, int n, int size, bool bottom) {
     return bottom ? size - 2 - j : size - 1 - j;
 }
 
+constexpr int CROP_ROWS = 32;   // tile rows per CTA
+
+// One CTA: CROP_ROWS rows of one (tile, channel) plane; a warp per row, lanes along x, up to four columns of a row
+// and two rows in flight per lane.  All index arithmetic is 32-bit and per row / per CTA, not per element.
 __global__ void __launch_bounds__(256)
 tiles_crop_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W, int pad, int k,
-                  int stride, int n_x, size_t total) {
-    const size_t kk = (size_t)k * k;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % k);
-        const int y = (int)((i / k) % k);
-        const size_t pc = i / kk;             // tile * C + channel
-        const int c = (int)(pc % C);
-        const int t = (int)(pc / C);
-        const int ty = t / n_x, tx = t - ty * n_x;
-        int sy = stride * ty + y, sx = stride * tx + x;
+                  int stride, int n_x) {
+    const unsigned pc = blockIdx.x;             // tile * C + channel
+    const int c = (int)(pc % (unsigned)C);
+    const int t = (int)(pc / (unsigned)C);
+    const int ty = t / n_x, tx = t - ty * n_x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y_end = min(k, (int)(blockIdx.y + 1) * CROP_ROWS);
+    const float* __restrict__ plane = src + (size_t)c * H * W;
+    float* __restrict__ out = dst + (size_t)pc * k * k;
+    const int sx0 = stride * tx;
+    for (int y = blockIdx.y * CROP_ROWS + warp; y < y_end; y += 16) {
+        const int y2 = y + 8;
+        const bool two = y2 < y_end;
+        int sy = stride * ty + y, sy2 = stride * ty + (two ? y2 : y);
         if (pad > 0) {
             sy = pad_source(sy, pad, H, true);
-            sx = pad_source(sx, pad, W, false);
+            sy2 = pad_source(sy2, pad, H, true);
         }
-        st_stream(dst + i, ld_stream(src + ((size_t)c * H + sy) * W + sx));
+        const float* __restrict__ r1 = plane + (size_t)sy * W;
+        const float* __restrict__ r2 = plane + (size_t)sy2 * W;
+        for (int x0 = lane; x0 < k; x0 += 128) {
+            float v1[4], v2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                int sx = sx0 + (x < k ? x : 0);
+                if (pad > 0) sx = pad_source(sx, pad, W, false);
+                v1[u] = __ldcs(r1 + sx);
+                v2[u] = __ldcs(r2 + sx);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                if (x < k) {
+                    __stcs(out + (size_t)y * k + x, v1[u]);
+                    if (two) __stcs(out + (size_t)y2 * k + x, v2[u]);
+                }
+            }
+        }
     }
 }
 
@@ -65,6 +93,75 @@ __device__ __forceinline__ double blend_weight(int t, int i, int n, int L, int p
     }
     if (j < 0) return 1.0;
     return __dadd_rn(__dmul_rn((double)(j + 1), step), 1.0);
+}
+
+constexpr int MERGE_ROWS = 4;    // output rows per thread
+constexpr int MERGE_COLS = 128;  // output columns per CTA (one per thread)
+
+// Covering tiles along one axis when at most two overlap (L <= 2 * stride): i_lo, whether a second one exists, and
+// the local coordinate in i_lo.
+__device__ __forceinline__ void cover2(int X, int n, int L, int stride, int& lo, bool& two) {
+    if (n == 1) { lo = 0; two = false; return; }
+    const int hi = min(X / stride, n - 1);
+    lo = (X - L + 1 <= 0) ? 0 : max(0, (X - L + stride) / stride);    // ceil((X - L + 1) / stride)
+    two = hi > lo;
+}
+
+// The common case (L <= 2 * stride: at most 2 x 2 tiles cover a pixel): one thread per output column, MERGE_ROWS
+// rows; the column's tiles, offsets and blend weights are computed once, all gathers of the rows are issued before
+// the float64 arithmetic, which is the generic kernel's, operation for operation (bit-identical results).
+template <typename TO>
+__global__ void __launch_bounds__(MERGE_COLS)
+tiles_merge2_kernel(const float* __restrict__ tiles, TO* __restrict__ out, int n_y, int n_x, int k, int crop, int L,
+                    int stride, int p, double step, int out_h, int out_w) {
+    const int X = blockIdx.x * MERGE_COLS + threadIdx.x;
+    if (X >= out_w) return;
+    const int Y0 = blockIdx.y * MERGE_ROWS;
+    const size_t kk = (size_t)k * k;
+    const float* __restrict__ base = tiles + (size_t)blockIdx.z * n_y * n_x * kk;
+    int c_lo;
+    bool c_two;
+    cover2(X, n_x, L, stride, c_lo, c_two);
+    const int tx0 = X - stride * c_lo, tx1 = tx0 - stride;
+    const double wx0 = blend_weight(tx0, c_lo, n_x, L, p, step);
+    const double wx1 = c_two ? blend_weight(tx1, c_lo + 1, n_x, L, p, step) : 0.0;
+    const unsigned col0 = (unsigned)(tx0 + crop), col1 = (unsigned)(tx1 + crop);
+
+    float v[MERGE_ROWS][2][2];
+    int r_lo[MERGE_ROWS];
+    bool r_two[MERGE_ROWS];
+#pragma unroll
+    for (int j = 0; j < MERGE_ROWS; ++j) {
+        const int Y = min(Y0 + j, out_h - 1);
+        cover2(Y, n_y, L, stride, r_lo[j], r_two[j]);
+        const int ty0 = Y - stride * r_lo[j];
+        const float* __restrict__ t0 = base + (size_t)(r_lo[j] * n_x + c_lo) * kk + (unsigned)(ty0 + crop) * (unsigned)k;
+        v[j][0][0] = __ldcs(t0 + col0);
+        v[j][0][1] = c_two ? __ldcs(t0 + kk + col1) : 0.f;
+        if (r_two[j]) {
+            const float* __restrict__ t1 = t0 + (size_t)n_x * kk - (size_t)stride * k;   // next row of tiles, ty - stride
+            v[j][1][0] = __ldcs(t1 + col0);
+            v[j][1][1] = c_two ? __ldcs(t1 + kk + col1) : 0.f;
+        } else {
+            v[j][1][0] = v[j][1][1] = 0.f;
+        }
+    }
+    TO* __restrict__ o = out + ((size_t)blockIdx.z * out_h + Y0) * out_w + X;
+#pragma unroll
+    for (int j = 0; j < MERGE_ROWS; ++j) {
+        if (Y0 + j < out_h) {
+            const int ty0 = (Y0 + j) - stride * r_lo[j];
+            double row = __dmul_rn((double)v[j][0][0], wx0);                            // copy, then add (copyto_add)
+            if (c_two) row = __dadd_rn(row, __dmul_rn((double)v[j][0][1], wx1));
+            double acc = __dmul_rn(row, blend_weight(ty0, r_lo[j], n_y, L, p, step));
+            if (r_two[j]) {
+                double row1 = __dmul_rn((double)v[j][1][0], wx0);
+                if (c_two) row1 = __dadd_rn(row1, __dmul_rn((double)v[j][1][1], wx1));
+                acc = __dadd_rn(acc, __dmul_rn(row1, blend_weight(ty0 - stride, r_lo[j] + 1, n_y, L, p, step)));
+            }
+            __stcs(o + (size_t)j * out_w, (TO)acc);
+        }
+    }
 }
 
 template <typename TO>
@@ -133,8 +230,11 @@ extern "C" int jspsr_tiles_crop(const float* src, float* dst, int C, int H, int 
         return jspsr_internal_fail(JSPSR_ERR_BAD_ARG, "tiles_crop: the mirrored border is wider than the image");
     if ((long long)stride * (n_y - 1) + k > (long long)H + 2 * pad || (long long)stride * (n_x - 1) + k > (long long)W + 2 * pad)
         return jspsr_internal_fail(JSPSR_ERR_BAD_ARG, "tiles_crop: the tile walk leaves the (padded) image");
-    const size_t total = (size_t)n_y * n_x * C * k * k;
-    tiles_crop_kernel<<<launch_blocks(total), 256, 0, (cudaStream_t)stream>>>(src, dst, C, H, W, pad, k, stride, n_x, total);
+    const long long planes = (long long)n_y * n_x * C;
+    const int chunks = (k + CROP_ROWS - 1) / CROP_ROWS;
+    if (planes > 0x7fffffffLL || chunks > 65535) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "tiles_crop: too many tiles");
+    tiles_crop_kernel<<<dim3((unsigned)planes, (unsigned)chunks), 256, 0, (cudaStream_t)stream>>>(src, dst, C, H, W, pad, k,
+                                                                                              stride, n_x);
     return cuda_check("tiles_crop launch");
 }
 
@@ -153,7 +253,15 @@ extern "C" int jspsr_tiles_merge(const float* tiles, void* out, int S, int n_y, 
     const int out_h = stride * (n_y - 1) + L, out_w = stride * (n_x - 1) + L;
     const double step = -1.0 / (double)(p + 1);   // numpy.linspace(1, 0, p + 2): step = (0 - 1) / (p + 1)
     const size_t total = (size_t)S * out_h * out_w;
-    if (out_f64)
+    const unsigned gx = (unsigned)((out_w + MERGE_COLS - 1) / MERGE_COLS), gy = (unsigned)((out_h + MERGE_ROWS - 1) / MERGE_ROWS);
+    if (L <= 2 * stride && gy <= 65535u && S <= 65535) {   // at most two tiles overlap along an axis: the gather is 2 x 2
+        if (out_f64)
+            tiles_merge2_kernel<double><<<dim3(gx, gy, (unsigned)S), MERGE_COLS, 0, (cudaStream_t)stream>>>(
+                tiles, (double*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w);
+        else
+            tiles_merge2_kernel<float><<<dim3(gx, gy, (unsigned)S), MERGE_COLS, 0, (cudaStream_t)stream>>>(
+                tiles, (float*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w);
+    } else if (out_f64)
         tiles_merge_kernel<double><<<launch_blocks(total), 256, 0, (cudaStream_t)stream>>>(
             tiles, (double*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w, total);
     else
