@@ -34,7 +34,10 @@ struct alignas(16) LossWs {
 };
 static_assert(sizeof(LossWs) <= sizeof(ReduceWs), "the propagation's reduction workspace is large enough");
 
-__device__ __forceinline__ float sgn(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+// c * sign(v) (0 at v = +-0): c with its sign flipped by v's sign bit, or zero
+__device__ __forceinline__ float csgn(float c, float v) {
+    return (v != 0.f) ? __int_as_float(__float_as_int(c) ^ (__float_as_int(v) & 0x80000000)) : 0.f;
+}
 // sign + 1 in {0, 1, 2}: the sign tiles hold biased signs so that four of them add up bytewise in one 32-bit integer
 __device__ __forceinline__ unsigned sgn1(float v) { return 1u + (unsigned)(v > 0.f) - (unsigned)(v < 0.f); }
 
@@ -46,9 +49,9 @@ __device__ __forceinline__ unsigned sgn1(float v) { return 1u + (unsigned)(v > 0
 // s[i - 1] - s[i + 1] with s NEGATED-and-replicated one past the border.  The sign tiles therefore carry one ring of
 // such extended values around the image and every pixel, border or not, uses the same 12-tap formula (no divergence).
 template <bool WRITE_GRAD, bool VEC>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ grad,
-                       float* __restrict__ losses4, LossWs* __restrict__ ws, int H, int W, int tiles_x, int tiles_y,
+                       float* __restrict__ losses4, LossWs* __restrict__ ws, int H, int W,
                        float w_l1, float w_l2, float w_grad, float inv_n) {
     __shared__ __align__(16) float s_d[LD_H][LD_W];
     __shared__ __align__(16) unsigned char s_sx[WRITE_GRAD ? LS_H : 1][LS_B];
@@ -56,11 +59,9 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     __shared__ float s_red[WARPS][3];
     __shared__ bool s_last;
 
-    const int tile = blockIdx.x;
-    const int tx = tile % tiles_x;
-    const int ty = (tile / tiles_x) % tiles_y;
-    const size_t plane = (size_t)(tile / (tiles_x * tiles_y)) * H * W;
-    const int y0 = ty * LT_H, x0 = tx * LT_W;
+    // grid = (planes, tiles_x, tiles_y): no per-thread division to find the tile
+    const size_t plane = (size_t)blockIdx.x * H * W;
+    const int y0 = blockIdx.z * LT_H, x0 = blockIdx.y * LT_W;
     const float* __restrict__ p = pred + plane;
     const float* __restrict__ g = gt + plane;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,20 +75,13 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
         float4 vp[ROWS_PER_WARP], vg[ROWS_PER_WARP];
         const int xc = x0 + 4 * lane;
         const bool in_x = xc < W;
+        const int xl = in_x ? xc : W - 4;                   // past the image: the last float4, its .w replicated below
 #pragma unroll
         for (int i = 0; i < ROWS_PER_WARP; ++i) {
-            const int r = warp + WARPS * i;
+            const int r = min(warp + WARPS * i, LD_H - 1);
             const int y = min(max(y0 - 2 + r, 0), H - 1);
-            if (r < LD_H) {
-                if (in_x) {
-                    vp[i] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)y * W + xc));
-                    vg[i] = __ldcs(reinterpret_cast<const float4*>(g + (size_t)y * W + xc));
-                } else {
-                    const float a = __ldg(p + (size_t)y * W + (W - 1)), b = __ldg(g + (size_t)y * W + (W - 1));
-                    vp[i] = make_float4(a, a, a, a);
-                    vg[i] = make_float4(b, b, b, b);
-                }
-            }
+            vp[i] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)y * W + xl));
+            vg[i] = __ldcs(reinterpret_cast<const float4*>(g + (size_t)y * W + xl));
         }
         // the two halo columns on either side: LD_H rows x 4 columns
         float hp = 0.f, hg = 0.f;
@@ -102,7 +96,8 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
         for (int i = 0; i < ROWS_PER_WARP; ++i) {
             const int r = warp + WARPS * i;
             if (r < LD_H) {
-                const float4 d = make_float4(vp[i].x - vg[i].x, vp[i].y - vg[i].y, vp[i].z - vg[i].z, vp[i].w - vg[i].w);
+                float4 d = make_float4(vp[i].x - vg[i].x, vp[i].y - vg[i].y, vp[i].z - vg[i].z, vp[i].w - vg[i].w);
+                if (!in_x) d.x = d.y = d.z = d.w;
                 *reinterpret_cast<float4*>(&s_d[r][4 + 4 * lane]) = d;
                 if (r >= 2 && r < LT_H + 2 && y0 - 2 + r < H && in_x) {       // own pixels: L1 and L2 from registers
                     a_l1 += (fabsf(d.x) + fabsf(d.y)) + (fabsf(d.z) + fabsf(d.w));
@@ -128,11 +123,18 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     __syncthreads();
 
     // ---- phase 2: Sobel of d, its |.| sum and (for the gradient) its biased signs ----
-    // A warp marches down a band of sign rows with the horizontal difference / smoothing of three d rows in registers.
-    {
-        const int ra = (warp * LS_H) / WARPS, rb = ((warp + 1) * LS_H) / WARPS;   // sign rows [ra, rb): image y0 - 1 + r
-        float hd[3][4], hs[3][4];
-        auto load_row = [&](int dr, float (&hdo)[4], float (&hso)[4]) {
+    // Warps 0 .. 6 march down five sign rows each with the horizontal difference / smoothing of three d rows in
+    // registers (fully unrolled: the rolling window is renamed, not moved); warp 7 takes the two sign columns
+    // beside the tile.  Sign cells outside the image are left as computed from the clamped d: the cells one step
+    // outside are overwritten by the ring pass below and nothing reads the ones further out.
+    constexpr int RPW = (LS_H + WARPS - 2) / (WARPS - 1);   // 5 sign rows per marching warp
+    static_assert(RPW * (WARPS - 1) >= LS_H && RPW * (WARPS - 2) + 2 < LD_H, "phase-2 row split");
+    if (warp < WARPS - 1) {
+        const int ra = warp * RPW;                           // sign rows ra .. ra + RPW - 1: image row y0 - 1 + r
+        float hd[RPW + 2][4], hs[RPW + 2][4];
+#pragma unroll
+        for (int i = 0; i < RPW + 2; ++i) {
+            const int dr = min(ra + i, LD_H - 1);
             // d at image columns x0 + 4 lane - 1 .. + 4: own float4, one value from each neighbour lane
             const float4 m = *reinterpret_cast<const float4*>(&s_d[dr][4 + 4 * lane]);
             float l = __shfl_up_sync(0xffffffffu, m.w, 1);
@@ -142,55 +144,47 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
             const float e[6] = {l, m.x, m.y, m.z, m.w, r};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                hdo[q] = e[q + 2] - e[q];
-                hso[q] = (e[q] + e[q + 2]) + 2.f * e[q + 1];
+                hd[i][q] = e[q + 2] - e[q];
+                hs[i][q] = (e[q] + e[q + 2]) + 2.f * e[q + 1];
             }
-        };
-        load_row(ra, hd[0], hs[0]);
-        load_row(ra + 1, hd[1], hs[1]);
-#pragma unroll 1
-        for (int r = ra; r < rb; ++r) {
-            load_row(r + 2, hd[2], hs[2]);
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int r = ra + i;
             const int y = y0 - 1 + r;
-            const bool row_in = (y >= 0 && y < H);
-            const bool own = row_in && r >= 1 && r <= LT_H;
-            unsigned px = 0u, py = 0u;
+            const bool own = (y >= 0 && y < H) && r >= 1 && r <= LT_H;     // a row of this CTA's own pixels
+            unsigned px = 0x01010101u, py = 0x01010101u;
+            float a_row = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float gx = (hd[0][q] + hd[2][q]) + 2.f * hd[1][q];
-                const float gy = hs[2][q] - hs[0][q];
-                const bool in = row_in && (x0 + 4 * lane + q < W);
-                if (own && in) a_grad += fabsf(gx) + fabsf(gy);
+                const float gx = (hd[i][q] + hd[i + 2][q]) + 2.f * hd[i + 1][q];
+                const float gy = hs[i + 2][q] - hs[i][q];
+                const float ag = fabsf(gx) + fabsf(gy);
+                if (VEC) a_row += ag;
+                else a_row += (x0 + 4 * lane + q < W) ? ag : 0.f;
                 if (WRITE_GRAD) {
-                    px |= (in ? sgn1(gx) : 1u) << (8 * q);
-                    py |= (in ? sgn1(gy) : 1u) << (8 * q);
+                    px += (gx > 0.f) ? (1u << (8 * q)) : 0u;
+                    px -= (gx < 0.f) ? (1u << (8 * q)) : 0u;
+                    py += (gy > 0.f) ? (1u << (8 * q)) : 0u;
+                    py -= (gy < 0.f) ? (1u << (8 * q)) : 0u;
                 }
             }
-            if (WRITE_GRAD) {
+            a_grad += (own && (!VEC || x0 + 4 * lane < W)) ? a_row : 0.f;
+            if (WRITE_GRAD && r < LS_H) {
                 *reinterpret_cast<unsigned*>(&s_sx[r][4 + 4 * lane]) = px;
                 *reinterpret_cast<unsigned*>(&s_sy[r][4 + 4 * lane]) = py;
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                hd[0][q] = hd[1][q]; hd[1][q] = hd[2][q];
-                hs[0][q] = hs[1][q]; hs[1][q] = hs[2][q];
-            }
         }
-        if (WRITE_GRAD && threadIdx.x < 2 * LS_H) {
-            // the sign columns just left and right of the tile (image columns x0 - 1 and x0 + LT_W)
-            const int side = threadIdx.x / LS_H, r = threadIdx.x - side * LS_H;
-            const int y = y0 - 1 + r, x = side ? x0 + LT_W : x0 - 1;
-            const int c = side ? LT_W + 4 : 3;                          // staged column of x in s_d and in the sign tiles
-            unsigned vx = 1u, vy = 1u;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const float d00 = s_d[r][c - 1], d01 = s_d[r][c], d02 = s_d[r][c + 1];
-                const float d10 = s_d[r + 1][c - 1], d12 = s_d[r + 1][c + 1];
-                const float d20 = s_d[r + 2][c - 1], d21 = s_d[r + 2][c], d22 = s_d[r + 2][c + 1];
-                vx = sgn1(((d02 - d00) + (d22 - d20)) + 2.f * (d12 - d10));
-                vy = sgn1(((d20 + d22) + 2.f * d21) - ((d00 + d02) + 2.f * d01));
-            }
-            s_sx[r][c] = (unsigned char)vx;
-            s_sy[r][c] = (unsigned char)vy;
+    } else if (WRITE_GRAD) {
+        // the sign columns just left and right of the tile (image columns x0 - 1 and x0 + LT_W)
+        for (int i = lane; i < 2 * LS_H; i += 32) {
+            const int side = i / LS_H, r = i - side * LS_H;
+            const int c = side ? LT_W + 4 : 3;                          // staged column in s_d and in the sign tiles
+            const float d00 = s_d[r][c - 1], d01 = s_d[r][c], d02 = s_d[r][c + 1];
+            const float d10 = s_d[r + 1][c - 1], d12 = s_d[r + 1][c + 1];
+            const float d20 = s_d[r + 2][c - 1], d21 = s_d[r + 2][c], d22 = s_d[r + 2][c + 1];
+            s_sx[r][c] = (unsigned char)sgn1(((d02 - d00) + (d22 - d20)) + 2.f * (d12 - d10));
+            s_sy[r][c] = (unsigned char)sgn1(((d20 + d22) + 2.f * d21) - ((d00 + d02) + 2.f * d01));
         }
     }
 
@@ -266,10 +260,10 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
             const unsigned G = U0 + 2u * U1 + U2 + V0 + (0x08080808u - V2);
             const float4 d = *reinterpret_cast<const float4*>(&s_d[pr + 2][4 + 4 * lane]);
             float4 o;
-            o.x = c_pix_l1 * sgn(d.x) + c_pix_l2 * d.x + c_sob * ((float)(G & 0xffu) - 16.f);
-            o.y = c_pix_l1 * sgn(d.y) + c_pix_l2 * d.y + c_sob * ((float)((G >> 8) & 0xffu) - 16.f);
-            o.z = c_pix_l1 * sgn(d.z) + c_pix_l2 * d.z + c_sob * ((float)((G >> 16) & 0xffu) - 16.f);
-            o.w = c_pix_l1 * sgn(d.w) + c_pix_l2 * d.w + c_sob * ((float)(G >> 24) - 16.f);
+            o.x = csgn(c_pix_l1, d.x) + c_pix_l2 * d.x + c_sob * ((float)(G & 0xffu) - 16.f);
+            o.y = csgn(c_pix_l1, d.y) + c_pix_l2 * d.y + c_sob * ((float)((G >> 8) & 0xffu) - 16.f);
+            o.z = csgn(c_pix_l1, d.z) + c_pix_l2 * d.z + c_sob * ((float)((G >> 16) & 0xffu) - 16.f);
+            o.w = csgn(c_pix_l1, d.w) + c_pix_l2 * d.w + c_sob * ((float)(G >> 24) - 16.f);
             const int x = x0 + 4 * lane;
             if (y < H) {
                 float* __restrict__ dst = grad + plane + (size_t)y * W + x;
@@ -301,13 +295,13 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
         double v = 0.0;
 #pragma unroll
         for (int wi = 0; wi < WARPS; ++wi) v += (double)s_red[wi][threadIdx.x];
-        atomicAdd(&ws->sums[blockIdx.x % LOSS_SLOTS][threadIdx.x], v);
+        atomicAdd(&ws->sums[(blockIdx.x + blockIdx.z) % LOSS_SLOTS][threadIdx.x], v);
         __threadfence();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(&ws->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        s_last = (t == gridDim.x * gridDim.y * gridDim.z - 1);
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
@@ -411,14 +405,15 @@ extern "C" int jspsr_loss_l1_l2_grad(const float* pred, const float* gt, float w
         return jspsr_internal_fail(JSPSR_ERR_ALIGN, "loss: a float pointer is not 4-byte aligned");
     if ((uintptr_t)workspace & 15) return jspsr_internal_fail(JSPSR_ERR_ALIGN, "loss: workspace is not 16-byte aligned");
     const int tiles_x = (W + LT_W - 1) / LT_W, tiles_y = (H + LT_H - 1) / LT_H;
-    const long long ctas = (long long)planes * tiles_x * tiles_y;
-    if (ctas > 0x7fffffffLL) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: more than 2^31 tiles");
+    if (tiles_x > 65535 || tiles_y > 65535) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: plane too large");
+    if ((long long)planes * tiles_x * tiles_y > 0xffffffffLL) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: more than 2^32 tiles");
+    const dim3 ctas((unsigned)planes, (unsigned)tiles_x, (unsigned)tiles_y);
     const float inv_n = (float)(1.0 / ((double)planes * H * W));
     // float4 path: rows 16-byte aligned (W % 4 == 0 and aligned bases)
     const bool vec = (W % 4 == 0) && !(((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)grad_pred) & 15);
 #define JSPSR_LAUNCH_LOSS(G, V)                                                                         \
-    loss_l1_l2_grad_kernel<G, V><<<(unsigned)ctas, THREADS, 0, (cudaStream_t)stream>>>(                 \
-        pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, tiles_x, tiles_y, w_l1, w_l2, w_grad, inv_n)
+    loss_l1_l2_grad_kernel<G, V><<<ctas, THREADS, 0, (cudaStream_t)stream>>>(                           \
+        pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, w_l1, w_l2, w_grad, inv_n)
     if (grad_pred) {
         if (vec) JSPSR_LAUNCH_LOSS(true, true); else JSPSR_LAUNCH_LOSS(true, false);
     } else {

@@ -95,71 +95,74 @@ __device__ __forceinline__ double blend_weight(int t, int i, int n, int L, int p
     return __dadd_rn(__dmul_rn((double)(j + 1), step), 1.0);
 }
 
-constexpr int MERGE_ROWS = 4;    // output rows per thread
+constexpr int MERGE_ROWS = 8;    // output rows per thread
 constexpr int MERGE_COLS = 128;  // output columns per CTA (one per thread)
 
-// Covering tiles along one axis when at most two overlap (L <= 2 * stride): i_lo, whether a second one exists, and
-// the local coordinate in i_lo.
-__device__ __forceinline__ void cover2(int X, int n, int L, int stride, int& lo, bool& two) {
-    if (n == 1) { lo = 0; two = false; return; }
-    const int hi = min(X / stride, n - 1);
-    lo = (X - L + 1 <= 0) ? 0 : max(0, (X - L + stride) / stride);    // ceil((X - L + 1) / stride)
-    two = hi > lo;
-}
-
-// The common case (L <= 2 * stride: at most 2 x 2 tiles cover a pixel): one thread per output column, MERGE_ROWS
-// rows; the column's tiles, offsets and blend weights are computed once, all gathers of the rows are issued before
-// the float64 arithmetic, which is the generic kernel's, operation for operation (bit-identical results).
-template <typename TO>
+// The common case (L <= 2 * stride: at most 2 x 2 tiles cover a pixel).  The grid walks the output in BANDS of
+// `stride` rows (band r = rows [r * stride, (r + 1) * stride), the last one L rows): inside band r a pixel belongs to
+// tile row r and, in its first p rows, also to tile row r - 1, so no thread divides to find its tile rows and the
+// row blend weights are per CTA (computed once, shared memory).  Two instantiations, one launch each: UP = false
+// covers the rows owned by one tile row (most of the raster: one or two gathers per pixel), UP = true the p
+// overlapped rows of bands 1 .. n_y - 1 (two or four).  A thread owns one output column (one division) and
+// MERGE_ROWS rows; all gathers are issued before the float64 arithmetic, which is the generic kernel's,
+// operation for operation (bit-identical results).
+template <typename TO, bool UP>
 __global__ void __launch_bounds__(MERGE_COLS)
 tiles_merge2_kernel(const float* __restrict__ tiles, TO* __restrict__ out, int n_y, int n_x, int k, int crop, int L,
-                    int stride, int p, double step, int out_h, int out_w) {
+                    int stride, int p, double step, int out_h, int out_w, int chunks) {
+    __shared__ double s_wy[MERGE_ROWS][2];   // blend weight of the row in tile row r - 1 / r
+    const int band = blockIdx.y / chunks;
+    const int r = UP ? band + 1 : band;                             // band = tile row that owns these output rows
+    const int y_lo = UP ? 0 : (r > 0 ? p : 0);                      // local rows [y_lo, y_hi) of the band
+    const int y_hi = UP ? p : ((r == n_y - 1) ? L : stride);
+    const int y0 = y_lo + (blockIdx.y - band * chunks) * MERGE_ROWS;   // first local row (= row in tile r before the crop)
+    if (y0 >= y_hi) return;
+    if (threadIdx.x < MERGE_ROWS) {
+        const int y = y0 + threadIdx.x;
+        s_wy[threadIdx.x][0] = UP ? blend_weight(y + stride, r - 1, n_y, L, p, step) : 0.0;
+        s_wy[threadIdx.x][1] = blend_weight(y, r, n_y, L, p, step);
+    }
+    __syncthreads();
     const int X = blockIdx.x * MERGE_COLS + threadIdx.x;
     if (X >= out_w) return;
-    const int Y0 = blockIdx.y * MERGE_ROWS;
     const size_t kk = (size_t)k * k;
-    const float* __restrict__ base = tiles + (size_t)blockIdx.z * n_y * n_x * kk;
-    int c_lo;
-    bool c_two;
-    cover2(X, n_x, L, stride, c_lo, c_two);
-    const int tx0 = X - stride * c_lo, tx1 = tx0 - stride;
-    const double wx0 = blend_weight(tx0, c_lo, n_x, L, p, step);
-    const double wx1 = c_two ? blend_weight(tx1, c_lo + 1, n_x, L, p, step) : 0.0;
-    const unsigned col0 = (unsigned)(tx0 + crop), col1 = (unsigned)(tx1 + crop);
+    const int c_hi = (n_x == 1) ? 0 : min(X / stride, n_x - 1);
+    const int tx = X - stride * c_hi;
+    const bool c_two = (c_hi > 0) && (tx < p);                      // also inside tile column c_hi - 1, at tx + stride
+    const double wx_hi = blend_weight(tx, c_hi, n_x, L, p, step);
+    const double wx_lo = c_two ? blend_weight(tx + stride, c_hi - 1, n_x, L, p, step) : 0.0;
+    // tile (r, c_hi), local pixel (y0, tx); tile column c_hi - 1 at tx + stride; tile row r - 1 at y + stride
+    const float* __restrict__ t_hi = tiles + ((size_t)blockIdx.z * n_y * n_x + (size_t)r * n_x + c_hi) * kk +
+                                     (size_t)(y0 + crop) * k + (tx + crop);
+    const float* __restrict__ t_lo = t_hi + ((ptrdiff_t)stride - (ptrdiff_t)kk);
+    const ptrdiff_t d_up = (ptrdiff_t)stride * k - (ptrdiff_t)n_x * (ptrdiff_t)kk;
+    const float* __restrict__ u_hi = t_hi + d_up;
+    const float* __restrict__ u_lo = t_lo + d_up;
 
-    float v[MERGE_ROWS][2][2];
-    int r_lo[MERGE_ROWS];
-    bool r_two[MERGE_ROWS];
+    float v[MERGE_ROWS][UP ? 2 : 1][2];   // [row][(tile row r - 1,) tile row r][tile column c_hi - 1 / c_hi]
 #pragma unroll
     for (int j = 0; j < MERGE_ROWS; ++j) {
-        const int Y = min(Y0 + j, out_h - 1);
-        cover2(Y, n_y, L, stride, r_lo[j], r_two[j]);
-        const int ty0 = Y - stride * r_lo[j];
-        const float* __restrict__ t0 = base + (size_t)(r_lo[j] * n_x + c_lo) * kk + (unsigned)(ty0 + crop) * (unsigned)k;
-        v[j][0][0] = __ldcs(t0 + col0);
-        v[j][0][1] = c_two ? __ldcs(t0 + kk + col1) : 0.f;
-        if (r_two[j]) {
-            const float* __restrict__ t1 = t0 + (size_t)n_x * kk - (size_t)stride * k;   // next row of tiles, ty - stride
-            v[j][1][0] = __ldcs(t1 + col0);
-            v[j][1][1] = c_two ? __ldcs(t1 + kk + col1) : 0.f;
-        } else {
-            v[j][1][0] = v[j][1][1] = 0.f;
+        const int o = min(j, y_hi - 1 - y0) * k;
+        v[j][UP ? 1 : 0][1] = __ldcs(t_hi + o);
+        v[j][UP ? 1 : 0][0] = c_two ? __ldcs(t_lo + o) : 0.f;
+        if (UP) {
+            v[j][0][1] = __ldcs(u_hi + o);
+            v[j][0][0] = c_two ? __ldcs(u_lo + o) : 0.f;
         }
     }
-    TO* __restrict__ o = out + ((size_t)blockIdx.z * out_h + Y0) * out_w + X;
+    TO* __restrict__ dst = out + ((size_t)blockIdx.z * out_h + (size_t)r * stride + y0) * out_w + X;
 #pragma unroll
     for (int j = 0; j < MERGE_ROWS; ++j) {
-        if (Y0 + j < out_h) {
-            const int ty0 = (Y0 + j) - stride * r_lo[j];
-            double row = __dmul_rn((double)v[j][0][0], wx0);                            // copy, then add (copyto_add)
-            if (c_two) row = __dadd_rn(row, __dmul_rn((double)v[j][0][1], wx1));
-            double acc = __dmul_rn(row, blend_weight(ty0, r_lo[j], n_y, L, p, step));
-            if (r_two[j]) {
-                double row1 = __dmul_rn((double)v[j][1][0], wx0);
-                if (c_two) row1 = __dadd_rn(row1, __dmul_rn((double)v[j][1][1], wx1));
-                acc = __dadd_rn(acc, __dmul_rn(row1, blend_weight(ty0 - stride, r_lo[j] + 1, n_y, L, p, step)));
+        if (y0 + j < y_hi) {
+            double row = __dmul_rn((double)v[j][UP ? 1 : 0][1], wx_hi);
+            if (c_two) row = __dadd_rn(__dmul_rn((double)v[j][UP ? 1 : 0][0], wx_lo), row);   // left tile first (copyto_add)
+            double acc = __dmul_rn(row, s_wy[j][1]);
+            if (UP) {
+                double row_up = __dmul_rn((double)v[j][0][1], wx_hi);
+                if (c_two) row_up = __dadd_rn(__dmul_rn((double)v[j][0][0], wx_lo), row_up);
+                acc = __dadd_rn(__dmul_rn(row_up, s_wy[j][0]), acc);                            // upper tile row first
             }
-            __stcs(o + (size_t)j * out_w, (TO)acc);
+            __stcs(dst + (size_t)j * out_w, (TO)acc);
         }
     }
 }
@@ -253,14 +256,20 @@ extern "C" int jspsr_tiles_merge(const float* tiles, void* out, int S, int n_y, 
     const int out_h = stride * (n_y - 1) + L, out_w = stride * (n_x - 1) + L;
     const double step = -1.0 / (double)(p + 1);   // numpy.linspace(1, 0, p + 2): step = (0 - 1) / (p + 1)
     const size_t total = (size_t)S * out_h * out_w;
-    const unsigned gx = (unsigned)((out_w + MERGE_COLS - 1) / MERGE_COLS), gy = (unsigned)((out_h + MERGE_ROWS - 1) / MERGE_ROWS);
-    if (L <= 2 * stride && gy <= 65535u && S <= 65535) {   // at most two tiles overlap along an axis: the gather is 2 x 2
-        if (out_f64)
-            tiles_merge2_kernel<double><<<dim3(gx, gy, (unsigned)S), MERGE_COLS, 0, (cudaStream_t)stream>>>(
-                tiles, (double*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w);
-        else
-            tiles_merge2_kernel<float><<<dim3(gx, gy, (unsigned)S), MERGE_COLS, 0, (cudaStream_t)stream>>>(
-                tiles, (float*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w);
+    const unsigned gx = (unsigned)((out_w + MERGE_COLS - 1) / MERGE_COLS);
+    // CTAs per band: rows owned by one tile row (up to L in the last band) / the p overlapped rows of bands >= 1
+    const int chunks = (max(stride, L) + MERGE_ROWS - 1) / MERGE_ROWS, chunks_up = (p + MERGE_ROWS - 1) / MERGE_ROWS;
+    const long long gy = (long long)n_y * chunks, gy_up = (long long)(n_y - 1) * chunks_up;
+    if (L <= 2 * stride && gy <= 65535 && gy_up <= 65535 && S <= 65535) {   // at most two tiles overlap along an axis
+#define JSPSR_LAUNCH_MERGE2(TO, UP, GY, CH)                                                               \
+    tiles_merge2_kernel<TO, UP><<<dim3(gx, (unsigned)(GY), (unsigned)S), MERGE_COLS, 0, (cudaStream_t)stream>>>( \
+        tiles, (TO*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w, CH)
+        if (out_f64) JSPSR_LAUNCH_MERGE2(double, false, gy, chunks); else JSPSR_LAUNCH_MERGE2(float, false, gy, chunks);
+        if (gy_up > 0) {
+            if (out_f64) JSPSR_LAUNCH_MERGE2(double, true, gy_up, chunks_up);
+            else JSPSR_LAUNCH_MERGE2(float, true, gy_up, chunks_up);
+        }
+#undef JSPSR_LAUNCH_MERGE2
     } else if (out_f64)
         tiles_merge_kernel<double><<<launch_blocks(total), 256, 0, (cudaStream_t)stream>>>(
             tiles, (double*)out, n_y, n_x, k, crop, L, stride, p, step, out_h, out_w, total);

@@ -127,5 +127,6 @@ def merge_tiles(tiles: torch.Tensor, border: float = 0.05, full: int = 334, dtyp
     with torch.cuda.device(tiles.device):
         _lib.check(_lib.lib().jspsr_tiles_merge(_ptr(tiles), _ptr(out), S, n_y, n_x, k, crop, stride,
                                                 int(dtype == torch.float64), _stream_ptr(tiles)), "jspsr_tiles_merge")
-    _count()
+    # 2 x 2 gather: one launch for the rows owned by one tile row, one for the overlapped rows; else the generic kernel
+    _count(2 if (n_y > 1 and 0 < L - stride and L <= 2 * stride) else 1)
     return out[0] if single else out

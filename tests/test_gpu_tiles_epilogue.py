@@ -93,7 +93,8 @@ def test_merge_matches_reference_bitwise(jb, tiles_ref, tag):
     assert np.array_equal(got32, got.astype(np.float32))
 
 
-@pytest.mark.parametrize("k,border,full,S", [(32, 0.0, 132, 3), (40, 0.1, 100, 2), (128, 0.05, 334, 4), (24, 0.0, 42, 1)])
+@pytest.mark.parametrize("k,border,full,S", [(32, 0.0, 132, 3), (40, 0.1, 100, 2), (128, 0.05, 334, 4), (24, 0.0, 42, 1),
+                                             (32, 0.0, 40, 2)])   # last: stride < L / 2, the generic kernel
 def test_merge_matches_oracle_bitwise(jb, k, border, full, S):
     rng = np.random.default_rng(k + S)
     b, L, out, stride, n_x, p = T.merge_geometry(k, border, full)

@@ -1,12 +1,21 @@
-"""Summarise an `ncu --page source --csv` export: executed warp-instructions per opcode, hot stall lines."""
+"""Summarise an `ncu --page source --csv` export (first kernel section): executed warp-instructions per opcode,
+hot stall lines.  python tools/ncu_src_summary.py file.csv [n_opcodes]"""
 import csv, sys, collections, re
-path = sys.argv[1]
-rows = list(csv.reader(open(path)))
-hdr = rows[1]
-ia, isrc, iex, ismp = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
+rows = list(csv.reader(open(sys.argv[1])))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+sec, n = [], 0
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        n += 1
+        if n == 2:
+            break
+        continue
+    sec.append(r)
+hdr = sec[0]
+isrc, iex, ismp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 iw = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
 tot = 0; by_op = collections.Counter(); samp_op = collections.Counter(); lines = []
-for r in rows[2:]:
+for r in sec[1:]:
     if len(r) <= iex: continue
     src = r[isrc].strip(); ex = int(r[iex] or 0); sm = int(r[ismp] or 0)
     op = re.sub(r"^@!?U?P\d+\s+", "", src).split()[0] if src else "?"
@@ -16,8 +25,8 @@ print("total warp-instructions executed:", tot)
 launched = lines[0][0]
 print("warps launched (first instr):", launched, " => instr per warp:", tot / max(1, launched))
 print("\n-- by opcode (executed, share, stall samples)")
-for op, ex in by_op.most_common(28):
+for op, ex in by_op.most_common(top):
     print(f"{op:28s} {ex:14d} {ex/tot:6.3f}  samples {samp_op[op]}")
 print("\n-- top stall-sample lines")
-for ex, sm, src, wf in sorted(lines, key=lambda t: -t[1])[:25]:
+for ex, sm, src, wf in sorted(lines, key=lambda t: -t[1])[:15]:
     print(f"samples {sm:7d} exec {ex:12d} smem_wavefronts {wf:12d}  {src}")
