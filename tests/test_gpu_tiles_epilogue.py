@@ -253,3 +253,83 @@ def test_metrics_match_oracle(jb, B, H, W, border):
         o = E.dem_metrics(pred, gt, border, -80.0, 929.0, elev_log)
         assert np.allclose(m["rmse"].cpu().numpy(), o["rmse"], rtol=2e-6, atol=0)
         assert np.allclose(m["mae"].cpu().numpy(), o["mae"], rtol=2e-6, atol=0)
+
+
+# ------------------------------------------------------------------ the rows chained as the reference chains them
+def _prop_inputs(rng, n, k, sigma=1.5):
+    weight = (1.0 / (1.0 + np.exp(-1.5 * rng.normal(size=(n, 9, k, k))))).astype(np.float32)
+    offset = np.clip(sigma * rng.normal(size=(n, 18, k, k)), -8, 8).astype(np.float32)
+    offset[:, 8:10] = 0.0
+    return weight, offset
+
+
+def test_tiled_inference_chain_matches_oracle_chain(jb):
+    """upscale_dem's walk (utils/utils.py:1583-1654): mirror-pad -> TileCrop -> per-tile propagation -> border crop +
+    blended merge -> remove padding, every stage on the GPU, against the same chain of oracles."""
+    from oracle import c_oracle as C
+    rng = np.random.default_rng(11)
+    size, k, pad, border = 100, 32, 14, 0.0                     # 128 padded -> 5 x 5 tiles of 32, stride 24
+    raster = rng.random((size, size, 1), dtype=np.float32)
+    want_tiles = T.crop_tiles(raster, k, None, pad=pad)          # [25,1,32,32]
+    n = want_tiles.shape[0]
+    weight, offset = _prop_inputs(rng, n, k)
+    w9 = (np.ones(9) + rng.uniform(-0.1, 0.1, 9)).astype(np.float32)
+    b1 = np.float32(0.1)
+    want_out = C.forward(want_tiles, weight, offset, w9, b1, 1, 1.0)
+    want = T.merge_tiles(want_out[:, 0].astype(np.float32), border, size + 2 * pad)[pad:-pad, pad:-pad]
+
+    post = jb.PostProcessor(3, True, 1.0).cuda()
+    with torch.no_grad():
+        post.w.copy_(dev(w9).view(1, 1, 3, 3))
+        post.b.fill_(float(b1))
+        tiles = jb.tiles.crop_tiles(dev(raster.transpose(2, 0, 1)), k, pad=pad)
+        assert np.array_equal(tiles.cpu().numpy(), want_tiles)
+        out = post(tiles, dev(weight), dev(offset))
+        merged = jb.tiles.remove_padding(jb.tiles.merge_tiles(out, border, size + 2 * pad), pad)
+    assert merged.shape == (size, size) and merged.dtype == torch.float64
+    err = np.abs(merged.cpu().numpy() - want).max()
+    assert err <= 1e-5 * max(1.0, np.abs(want).max()), err
+    # the merge of the GPU's own tiles is bit-exact: the only difference above is the propagation's fp32 rounding
+    again = T.merge_tiles(out[:, 0].cpu().numpy(), border, size + 2 * pad)[pad:-pad, pad:-pad]
+    assert np.array_equal(merged.cpu().numpy(), again)
+
+
+def test_training_step_through_the_fused_loss_matches_oracle_chain(jb):
+    """models/JSPSR.py:372-375 + train/train_utils.py:205-214: propagation on the detached DEM -> MultiLoss ->
+    backward; the gradients reaching (weight, offset, w, b) against oracle(loss gradient) -> oracle(backward)."""
+    from oracle import c_oracle as C
+    rng = np.random.default_rng(5)
+    B, k = 3, 128
+    init = rng.random((B, 1, k, k), dtype=np.float32)
+    gt = np.clip(init + 0.05 * rng.normal(size=init.shape), 0, 1).astype(np.float32)
+    weight, offset = _prop_inputs(rng, B, k)
+    w9 = (np.ones(9) + rng.uniform(-0.1, 0.1, 9)).astype(np.float32)
+    b1 = np.float32(0.05)
+
+    post = jb.PostProcessor(3, True, 1.0).cuda()
+    with torch.no_grad():
+        post.w.copy_(dev(w9).view(1, 1, 3, 3))
+        post.b.fill_(float(b1))
+    crit = jb.MultiLoss(L1=1.0, L2=1.0, Grad=0.1)
+    tw, to = dev(weight).requires_grad_(), dev(offset).requires_grad_()
+    out = post(dev(init), tw, to)
+    losses = crit(out, dev(gt))
+    losses["Total"].backward()
+
+    ref_out = C.forward(init, weight, offset, w9, b1, 1, 1.0)
+    assert np.abs(out.detach().cpu().numpy() - ref_out).max() <= 1e-5
+    # the loss gradient is evaluated at the GPU's own prediction (sign(d) is discontinuous; see kink_mask)
+    pred = out.detach().cpu().numpy()
+    o = E.multi_loss(pred.astype(np.float64), gt.astype(np.float64))
+    assert abs(float(losses["Total"]) - float(o["Total"])) <= 1e-5 * float(o["Total"])
+    g = E.multi_loss_grad(pred.astype(np.float64), gt.astype(np.float64)).astype(np.float32)
+    _, got_g = jb.epilogue.loss_l1_l2_grad(out.detach(), dev(gt))
+    got_g = got_g.cpu().numpy()
+    ok = ~kink_mask(pred, gt)
+    assert np.abs(got_g - g)[ok].max() <= 1e-5 * np.abs(g).max()
+    # drive the oracle backward with the GPU's loss gradient so that the comparison isolates the propagation backward
+    ref = C.backward(got_g, init, weight, offset, w9, 1, 1.0, need_grad_init=False)
+    for name, got in (("grad_weight", tw.grad), ("grad_offset", to.grad), ("grad_w", post.w.grad.view(-1)),
+                      ("grad_b", post.b.grad)):
+        r = np.asarray(ref[name]).reshape(got.shape)
+        assert np.abs(got.cpu().numpy() - r).max() <= 1e-5 * max(1.0, np.abs(r).max()), name
