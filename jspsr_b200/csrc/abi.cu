@@ -129,8 +129,8 @@ static bool make_feature_tmap(CUtensorMap* map, const void* feature, int B, int 
 
 static int check_common(int B, int H, int W, int norm_mode, int dtype) {
     if (B <= 0 || H <= 0 || W <= 0) return fail(JSPSR_ERR_BAD_ARG, "non-positive dimension B=%d H=%d W=%d", B, H, W);
-    if (H > (1 << 24) || W > (1 << 24))
-        return fail(JSPSR_ERR_UNSUPPORTED, "H and W are limited to 2^24 (fp32 pixel coordinates must be exact)");
+    if (H > (1 << 22) - 256 || W > (1 << 22) - 256)
+        return fail(JSPSR_ERR_UNSUPPORTED, "H and W are limited to 2^22 - 256 (the kernels floor pixel coordinates in the fp32 mantissa)");
     if (norm_mode < 0 || norm_mode > 2) return fail(JSPSR_ERR_BAD_ARG, "norm_mode %d is not 0/1/2", norm_mode);
     if (dtype != JSPSR_F32 && dtype != JSPSR_BF16 && dtype != JSPSR_MIXED)
         return fail(JSPSR_ERR_BAD_ARG, "dtype %d is not 0 (f32) / 1 (bf16) / 2 (mixed)", dtype);
@@ -180,7 +180,7 @@ int jspsr_spn_forward_strip(const void* init, const void* weight, const void* of
     if (int e = check_common(B, Hs, W, norm_mode, dtype)) return e;
     if (!init || !weight || !offset || !out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
     if (H_img < Hs || row0 < 0 || row0 + Hs > H_img || init_row0 < 0 || init_rows <= 0 || init_row0 + init_rows > H_img ||
-        H_img > (1 << 24))
+        H_img > (1 << 22) - 256)
         return fail(JSPSR_ERR_BAD_ARG, "inconsistent strip geometry (Hs=%d H_img=%d row0=%d init_row0=%d init_rows=%d)", Hs,
                     H_img, row0, init_row0, init_rows);
     const size_t es = dtype == JSPSR_F32 ? 4 : 2;      // weight / offset

@@ -255,7 +255,7 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
             af[n] = tanh_type ? th[n] * rgam : af[n];  // af[] now holds t_n
             cval[n] = 1.f;
             if (CONF) {
-                const FastTap t = fast_tap<T>(tile_lo, c, fy + oh[n], fx + ow[n]);
+                const FastTap t = fast_tap<T, true>(tile_lo, c, fy + oh[n], fx + ow[n]);
                 cval[n] = t.ok ? bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw) : 0.f;
                 slow |= t.ok ? 0u : (1u << n);
             }
@@ -306,7 +306,7 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
                         if ((unsigned)(r0 + 1) < (unsigned)g.H_img && (unsigned)(q0 + 1) < (unsigned)g.W) atomicAdd(gcf_b + (size_t)(r0 + 1) * g.W + q0 + 1, c4);
                     }
                 } else {
-                    const FastTap t = fast_tap<T>(tile_lo, c, h, w);  // geometry only (values unused)
+                    const FastTap t = fast_tap<T, true>(tile_lo, c, h, w);  // geometry only (values unused)
                     const float gvs = ITILE ? gv * gscale : gv;       // exact: the scale is a power of two
                     const float ch = gvs * t.lh, cl = gvs - ch, c2 = cl * t.lw, c4 = ch * t.lw;
                     float* gtp = gtile_lo + ((unsigned)t.h0 - c.oy_lo) * SW + ((unsigned)t.w0 - (unsigned)c.ox);

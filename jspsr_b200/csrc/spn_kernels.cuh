@@ -97,13 +97,30 @@ struct FastTap {
     bool ok;
 };
 
-template <typename T>
+// MANTISSA_FLOOR: floor without the conversion pipe (F2I / FRND run at a quarter of the FP32 rate): adding 1.5 * 2^23
+// with round-down leaves floor(x) in the low mantissa bits for |x| < 2^22, and subtracting it back gives floor(x) as a
+// float exactly, so h0 / lh are bit-identical to __float2int_rd / x - floorf(x) there.  Anything further out (or NaN)
+// yields an index far outside the staged rows / columns (host: H, W < 2^22), fails the range test below and goes
+// through slow_tap, which keeps the saturating conversions.  Same-box A/B (tools/ab_hot.py, 2048 tiles): one more
+// instruction per coordinate costs the issue-bound propagation kernels 1-6 % (forward 627 -> 633 us, bf16 forward
+// 592 -> 627 us), while the NLSPN affinity backward - 8 gathers whose conversions sit on its critical path - gains
+// 7.6 % (2880 -> 2662 us); so only that kernel turns it on.
+template <typename T, bool MANTISSA_FLOOR = false>
 __device__ __forceinline__ FastTap fast_tap(const T* __restrict__ tile_lo, const TileCtx& c, float h, float w) {
     FastTap t;
-    t.h0 = __float2int_rd(h);  // saturating; NaN -> 0
-    t.w0 = __float2int_rd(w);
-    t.lh = h - floorf(h);
-    t.lw = w - floorf(w);
+    if (MANTISSA_FLOOR) {
+        constexpr float MAGIC = 12582912.f;
+        const float th = __fadd_rd(h, MAGIC), tw = __fadd_rd(w, MAGIC);
+        t.h0 = __float_as_int(th) - 0x4B400000;
+        t.w0 = __float_as_int(tw) - 0x4B400000;
+        t.lh = h - (th - MAGIC);
+        t.lw = w - (tw - MAGIC);
+    } else {
+        t.h0 = __float2int_rd(h);  // saturating; NaN -> 0
+        t.w0 = __float2int_rd(w);
+        t.lh = h - floorf(h);
+        t.lw = w - floorf(w);
+    }
     const unsigned r = (unsigned)t.h0 - c.oy_lo;
     const unsigned q = (unsigned)t.w0 - (unsigned)c.ox;
     t.ok = (r < c.r_span) && (q < (unsigned)(SW - 1));

@@ -52,7 +52,7 @@ def test_argument_validation_needs_no_gpu(lib):
         (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 8, 8, 7, 1.0, 0, None), -1, "norm_mode"),
         (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 8, 8, 1, 1.0, 5, None), -1, "dtype"),
         (lambda: h.jspsr_spn_forward(None, one, one, one, one, one, 1, 8, 8, 1, 1.0, 0, None), -1, "null"),
-        (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 1 << 25, 8, 1, 1.0, 0, None), -2, "2^24"),
+        (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 1 << 25, 8, 1, 1.0, 0, None), -2, "2^22"),
         (lambda: h.jspsr_spn_forward(ctypes.c_void_p(18), one, one, one, one, one, 1, 8, 8, 1, 1.0, 0, None), -4, "aligned"),
         (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, None, None, 1, 32, 8, 8, 1, 1.0, 0, None), -2, "C = 64"),
         (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 1, None), -2, "fp32"),
