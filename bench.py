@@ -614,6 +614,28 @@ def config_batch_latency(torch, jspsr_b200, F, device, dtype):
         e1.record()
         torch.cuda.synchronize()
         res[f"B{B}"] = {"us_per_fwd_bwd": e0.elapsed_time(e1) / n * 1e3, "l2_resident": True}
+        if dtype == torch.float32:
+            # the training step as train/train_utils.py:205-214 chains it: propagation -> MultiLoss (L1 + L2 + 0.1 Grad,
+            # losses and dTotal/dpred in one kernel) -> propagation backward, three launches in one graph
+            from jspsr_b200 import epilogue as EP
+            gt = (init + 0.05 * torch.randn_like(init)).clamp_(0, 1)
+            with torch.cuda.stream(s):
+                EP.loss_l1_l2_grad(init, gt)       # this stream's workspace is allocated outside the capture
+            torch.cuda.current_stream().wait_stream(s)
+            graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph2, stream=s):
+                o = F.spn_forward(init, weight, offset, w, b, 1, 1.0)
+                _, gl = EP.loss_l1_l2_grad(o, gt)
+                F.spn_backward(gl, init, weight, offset, w, 1, 1.0, need_grad_init=False)
+            for _ in range(5):
+                graph2.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                graph2.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"B{B}"]["us_per_fwd_loss_bwd"] = e0.elapsed_time(e1) / n * 1e3
     out = {"config_batch": res}
     try:  # GPU incumbent: the unmodified call sequence on torchvision's CUDA kernels (a library), same shapes
         from oracle import ref_port

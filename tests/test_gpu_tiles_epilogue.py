@@ -333,3 +333,55 @@ def test_training_step_through_the_fused_loss_matches_oracle_chain(jb):
                       ("grad_b", post.b.grad)):
         r = np.asarray(ref[name]).reshape(got.shape)
         assert np.abs(got.cpu().numpy() - r).max() <= 1e-5 * max(1.0, np.abs(r).max()), name
+
+
+# ------------------------------------------------------------------ full-size properties (4096 tiles: 67 Mpix, beyond L2)
+def test_loss_full_size_properties(jb):
+    """At the bench size the oracle is too slow; size-independent identities instead: each term alone has a closed-form
+    gradient, the Sobel term's gradient sums to zero per plane (a derivative filter annihilates constants, replicate
+    border included), swapping (pred, gt) keeps the losses and negates the gradient, and the sums agree with torch's."""
+    from jspsr_b200 import epilogue as EP
+    B, k = 4096, 128
+    g = torch.Generator(device="cuda").manual_seed(17)
+    gt = torch.rand(B, 1, k, k, device="cuda", generator=g)
+    pred = gt + 0.05 * torch.randn(B, 1, k, k, device="cuda", generator=g)
+    n = pred.numel()
+    d = pred - gt
+    # L2 alone: gradient 2 d / n, loss mean(d^2)
+    l, gr = EP.loss_l1_l2_grad(pred, gt, 0.0, 1.0, 0.0)
+    assert torch.allclose(gr, d * (2.0 / n), rtol=2e-6, atol=0)
+    assert abs(float(l[1]) - float((d.double() ** 2).mean())) <= 1e-6 * float(l[1]) and float(l[3]) == float(l[1])
+    # L1 alone: gradient sign(d) / n
+    l, gr = EP.loss_l1_l2_grad(pred, gt, 1.0, 0.0, 0.0)
+    assert torch.equal(gr, torch.sign(d) * torch.tensor(1.0 / n, device="cuda", dtype=torch.float32))
+    assert abs(float(l[0]) - float(d.double().abs().mean())) <= 1e-6 * float(l[0])
+    # Sobel term alone: integer multiples of w / (16 n), summing to exactly zero in every plane
+    l, gr = EP.loss_l1_l2_grad(pred, gt, 0.0, 0.0, 1.0)
+    units = gr.double() * (16.0 * n)
+    assert float((units - units.round()).abs().max()) < 1e-3 and float(units.abs().max()) <= 16.0
+    assert float(units.round().sum(dim=(1, 2, 3)).abs().max()) == 0.0
+    import torch.nn.functional as TF
+    kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]], device="cuda", dtype=torch.float64) / 8.0
+    sob = TF.conv2d(TF.pad(d[:256].double(), [1, 1, 1, 1], mode="replicate"), torch.stack([kx, kx.t()])[:, None])
+    l256, _ = EP.loss_l1_l2_grad(pred[:256], gt[:256], 0.0, 0.0, 1.0, want_grad=False)
+    assert abs(float(l256[2]) - float(sob.abs().mean())) <= 1e-5 * float(l256[2])
+    # antisymmetry
+    la, ga = EP.loss_l1_l2_grad(pred, gt)
+    lb, gb = EP.loss_l1_l2_grad(gt, pred)
+    assert torch.allclose(la, lb, rtol=1e-6, atol=0) and torch.equal(ga, -gb)
+
+
+def test_metrics_full_size_against_torch(jb):
+    from jspsr_b200 import epilogue as EP
+    B, k = 4096, 128
+    g = torch.Generator(device="cuda").manual_seed(23)
+    gt = torch.rand(B, 1, k, k, device="cuda", generator=g)
+    pred = gt + 0.02 * torch.randn(B, 1, k, k, device="cuda", generator=g)
+    m = EP.dem_metrics(pred, gt, 0.05, -80.0, 929.0, True)
+    c = int(k * 0.05)
+    lr = float(np.log(929.0 + 80.0))
+    pe = torch.exp(pred[:, :, c:-c, c:-c].clamp(0, 1) * lr) - 80.0
+    ge = torch.exp(gt[:, :, c:-c, c:-c] * lr) - 80.0
+    dd = (pe - ge).double()
+    assert torch.allclose(m["rmse"], dd.pow(2).mean(dim=(1, 2, 3)).sqrt(), rtol=2e-6, atol=0)
+    assert torch.allclose(m["mae"], dd.abs().mean(dim=(1, 2, 3)), rtol=2e-6, atol=0)
