@@ -178,7 +178,9 @@ def test_loss_matches_reference_multiloss(jb, epi_ref, tag):
 
 
 @pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (2, 1, 2, 3), (1, 1, 1, 200), (1, 1, 70, 1), (3, 2, 17, 129), (2, 1, 130, 257),
-                                     (70, 1, 128, 128), (1, 1, 334, 334)])
+                                     (70, 1, 128, 128), (1, 1, 334, 334),
+                                     # float4 path (W % 4 == 0) with the image ending inside a tile, in x and in y
+                                     (2, 1, 40, 136), (1, 2, 64, 256), (1, 1, 33, 260), (2, 1, 31, 4), (1, 1, 97, 132)])
 def test_loss_matches_oracle(jb, B, C, H, W):
     rng = np.random.default_rng(B * 1000 + H + W)
     gt = rng.random((B, C, H, W)).astype(np.float32)
