@@ -130,3 +130,37 @@ def merge_tiles(tiles: torch.Tensor, border: float = 0.05, full: int = 334, dtyp
     # 2 x 2 gather: one launch for the rows owned by one tile row, one for the overlapped rows; else the generic kernel
     _count(2 if (n_y > 1 and 0 < L - stride and L <= 2 * stride) else 1)
     return out[0] if single else out
+
+
+def tiled_apply(fn, raster: torch.Tensor, k: int, pad: int = 0, border: float = 0.05, n_tile=None, batch=None,
+                dtype=torch.float64) -> torch.Tensor:
+    """Whole-raster inference as the reference composes it, every stage on the GPU: mirror-pad (`upscale_dem`,
+    utils/utils.py:1563-1578) -> overlapping tiles (`TileCrop`, data/data_utils.py:129-163) -> `fn` on batches of
+    tiles -> border crop + blended merge (`merge_dem`, utils/utils.py:916-965) -> remove the padding (:1641-1642).
+
+    raster [C,H,H]; `fn` maps tiles [n,C,k,k] to predictions [n,1,k,k] (or [n,k,k]); `batch` tiles per call (default:
+    all).  The merge walks the SAME stride / grid the crop used.  Returns [h,h] with h = H - 2*max(0, crop - pad),
+    crop = int(k*border): the part of the image the merged raster covers (all of it when pad >= crop)."""
+    raster = _f32_cuda(raster, "raster")
+    C, H, W = raster.shape
+    assert H == W, "TileCrop's walk supports square rasters only"
+    stride, n = get_tile(W + 2 * pad, k, n_tile)
+    n_x = int(round(n ** 0.5))
+    tiles = crop_tiles(raster, k, n_tile, pad=pad)
+    outs = []
+    step = n if not batch else int(batch)
+    for i in range(0, n, step):
+        o = fn(tiles[i:i + step])
+        if o.dim() == 4:
+            if o.shape[1] != 1:
+                raise RuntimeError(f"jspsr_b200.tiles: fn must return one channel, got {tuple(o.shape)}")
+            o = o[:, 0]
+        if tuple(o.shape[-2:]) != (k, k):
+            raise RuntimeError(f"jspsr_b200.tiles: fn must keep the tile size {k}, got {tuple(o.shape)}")
+        outs.append(o)
+    pred = torch.cat(outs) if len(outs) > 1 else outs[0]
+    merged = merge_tiles(pred.float(), border, dtype=dtype, stride=stride, grid=(n_x, n_x))
+    crop = int(k * border)
+    lo = max(0, pad - crop)                       # merged index of image row max(0, crop - pad)
+    h = H - 2 * max(0, crop - pad)
+    return merged[lo:lo + h, lo:lo + h]

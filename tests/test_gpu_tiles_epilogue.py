@@ -387,3 +387,22 @@ def test_metrics_full_size_against_torch(jb):
     dd = (pe - ge).double()
     assert torch.allclose(m["rmse"], dd.pow(2).mean(dim=(1, 2, 3)).sqrt(), rtol=2e-6, atol=0)
     assert torch.allclose(m["mae"], dd.abs().mean(dim=(1, 2, 3)), rtol=2e-6, atol=0)
+
+
+def test_tiled_apply_is_the_explicit_chain(jb):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    size, k, pad, border = 100, 32, 14, 0.1            # crop 3 per side; 128 padded -> 5 x 5 tiles, stride 24
+    raster = torch.rand(2, size, size, device="cuda", generator=g)
+    fn = lambda t: (t[:, :1] * 2.0 + t[:, 1:2]).contiguous()          # any per-pixel map: blending reproduces it
+    got = jb.tiles.tiled_apply(fn, raster, k, pad=pad, border=border, batch=7)
+    assert got.shape == (size, size) and got.dtype == torch.float64
+    want = (raster[0] * 2.0 + raster[1]).double()
+    assert float((got - want).abs().max()) < 1e-6
+    # the explicit chain, bit for bit
+    tiles = jb.tiles.crop_tiles(raster, k, pad=pad)
+    merged = jb.tiles.merge_tiles(fn(tiles), border, stride=24, grid=(5, 5))
+    assert torch.equal(got, merged[pad - 3:pad - 3 + size, pad - 3:pad - 3 + size])
+    # no padding: the border crop is lost at the image edge, as in the reference's merge_dem (334 -> 322)
+    r2 = torch.rand(1, 334, 334, device="cuda", generator=g)
+    got2 = jb.tiles.tiled_apply(lambda t: t, r2, 128, border=0.05)
+    assert got2.shape == (322, 322) and float((got2 - r2[0, 6:-6, 6:-6].double()).abs().max()) < 1e-6
