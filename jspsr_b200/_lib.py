@@ -46,11 +46,58 @@ _SIGNATURES = {
 _lib = None
 
 
+EXT_PATH = os.path.join(os.path.dirname(_CSRC), "_jspsr_torch.so")
+_EXT_SRC = os.path.join(_CSRC, "torch_binding.cpp")
+_ext = None
+_ext_tried = False
+
+
 def build(verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU), then the thin torch
+    extension over its C ABI (csrc/torch_binding.cpp: C++ autograd wrappers, no kernels of its own)."""
     cmd = ["make", "-C", _CSRC, "-j8"] + ([] if verbose else ["-s"])
     subprocess.check_call(cmd)
+    build_ext(verbose)
     return LIB_PATH
+
+
+def build_ext(verbose: bool = False) -> str:
+    """g++ on torch_binding.cpp against this interpreter's torch; in-tree output (jspsr_b200/_jspsr_torch.so) so that
+    it travels with the repository snapshot.  Rebuilt when the source, the headers or torch changed."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension
+    deps = [_EXT_SRC, LIB_PATH, os.path.join(_CSRC, "..", "..", "include", "jspsr_spn.h"),
+            os.path.join(_CSRC, "..", "..", "include", "jspsr_tiles.h"), torch.__file__]
+    if os.path.exists(EXT_PATH) and all(os.path.getmtime(EXT_PATH) >= os.path.getmtime(d) for d in deps):
+        return EXT_PATH
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_jspsr_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    cmd += ["-I" + d for d in cpp_extension.include_paths()]
+    cmd += ["-I" + sysconfig.get_paths()["include"], "-I/usr/local/cuda/include", _EXT_SRC, "-o", EXT_PATH,
+            "-L" + tlib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
+            "-L" + _CSRC, "-ljspsr_spn", "-Wl,-rpath,$ORIGIN/csrc", "-Wl,-rpath," + tlib]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return EXT_PATH
+
+
+def ext():
+    """The C++ torch extension (None when it has not been built, or JSPSR_NO_TORCH_EXT=1): the same kernels of the
+    same library, with the per-call bookkeeping in C++ instead of Python + ctypes."""
+    global _ext, _ext_tried
+    if not _ext_tried:
+        _ext_tried = True
+        if os.environ.get("JSPSR_NO_TORCH_EXT", "0") != "1" and os.path.exists(EXT_PATH):
+            lib()                                  # libjspsr_spn.so first: the extension links against it
+            import torch  # noqa: F401  (libtorch must be loaded before the extension)
+            from . import _jspsr_torch
+            if _jspsr_torch.abi_version() != lib().jspsr_version():
+                raise RuntimeError("jspsr_b200/_jspsr_torch.so was built against another libjspsr_spn.so: rebuild")
+            _ext = _jspsr_torch
+    return _ext
 
 
 def lib() -> ctypes.CDLL:

@@ -75,8 +75,14 @@ class MultiLoss(nn.Module):
 
     def forward(self, pred, gt):
         w = self.weights
-        total, losses = _Loss.apply(pred, gt, w.get("L1", 0.0), w.get("L2", 0.0), w.get("Grad", 0.0))
-        self.out = {k: losses[i] for i, k in enumerate(self.SUPPORTED) if k in w}
+        e = _lib.ext()
+        if e is not None:
+            _check_pair(pred, gt)
+            total, losses = e.multi_loss(pred, gt, w.get("L1", 0.0), w.get("L2", 0.0), w.get("Grad", 0.0))
+        else:
+            total, losses = _Loss.apply(pred, gt, w.get("L1", 0.0), w.get("L2", 0.0), w.get("Grad", 0.0))
+        parts = losses.unbind(0)
+        self.out = {k: parts[i] for i, k in enumerate(self.SUPPORTED) if k in w}
         self.out["Total"] = total
         return self.out
 

@@ -19,7 +19,9 @@ _launches = 0  # kernels of libjspsr_spn.so enqueued through this module (bench.
 
 
 def launch_count() -> int:
-    return _launches
+    """Kernels of libjspsr_spn.so enqueued so far, through ctypes (this module) and through the C++ extension."""
+    e = _lib.ext()
+    return _launches + (int(e.launch_count()) if e is not None else 0)
 
 
 def _count(n: int = 1) -> None:
@@ -406,6 +408,15 @@ def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) ->
     if init.shape[0] == 0:  # empty batch: nothing to launch (the reference returns an empty tensor too)
         _check_shapes(init, weight, offset)
         return init.new_empty(init.shape) + 0 * (weight.sum() + offset.sum() + w.sum() + b.sum())
+    e = _lib.ext()
+    if e is not None:
+        # same checks, same kernels; allocation / stream / workspace / autograd bookkeeping in C++ (torch_binding.cpp):
+        # ~3x less host time per call, which is what bounds a step at the reference's batch sizes
+        _require_cuda(init, weight, offset, w, b)
+        _check_shapes(init, weight, offset)
+        if w.numel() != 9:
+            raise RuntimeError(f"only kernel_size 3 is supported (w has {w.numel()} elements)")
+        return e.propagate(init, weight, offset, w, b, int(norm_mode), float(scale))
     return _Propagate.apply(init, weight, offset, w, b, norm_mode, scale)
 
 

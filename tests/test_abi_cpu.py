@@ -137,3 +137,18 @@ def test_product_never_imports_the_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("the oracle", ""), f"{fn} mentions the oracle package"
             assert "torchvision" not in [ln.split()[1] if ln.startswith(("import ", "from ")) else "" for ln in src.splitlines()]
+
+
+def test_torch_extension_builds_and_binds_the_same_library(lib):
+    """csrc/torch_binding.cpp: C++ autograd wrappers over the C ABI (no kernels of its own).  Without a GPU it must
+    import, report the library's ABI version and refuse CPU tensors."""
+    import torch
+    lib.build_ext()
+    e = lib.ext()
+    assert e is not None and e.abi_version() == lib.lib().jspsr_version()
+    for name in ("propagate", "spn_forward", "multi_loss", "launch_count"):
+        assert hasattr(e, name)
+    with pytest.raises(RuntimeError):
+        e.spn_forward(torch.zeros(1, 1, 4, 4), torch.zeros(1, 9, 4, 4), torch.zeros(1, 18, 4, 4), torch.ones(1, 1, 3, 3),
+                      torch.zeros(1), 1, 1.0)
+    assert e.launch_count() == 0

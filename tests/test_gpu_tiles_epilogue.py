@@ -406,3 +406,46 @@ def test_tiled_apply_is_the_explicit_chain(jb):
     r2 = torch.rand(1, 334, 334, device="cuda", generator=g)
     got2 = jb.tiles.tiled_apply(lambda t: t, r2, 128, border=0.05)
     assert got2.shape == (322, 322) and float((got2 - r2[0, 6:-6, 6:-6].double()).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------ the C++ torch extension over the same C ABI
+def test_torch_extension_path_equals_ctypes_path_bitwise(jb):
+    """jspsr_b200/_jspsr_torch.so (csrc/torch_binding.cpp) enqueues the same kernels of the same library with the
+    bookkeeping in C++; the ctypes path (functional._Propagate / epilogue._Loss) must give identical bits."""
+    from jspsr_b200 import _lib, functional as F, epilogue as EP
+    e = _lib.ext()
+    assert e is not None, "the torch extension was not built (python -c 'import __graft_entry__ as g; g.build()')"
+    g = torch.Generator(device="cuda").manual_seed(8)
+    B, k = 3, 128
+    for dt_w, need_init in ((torch.float32, False), (torch.float32, True), (torch.bfloat16, False)):
+        init = torch.rand(B, 1, k, k, device="cuda", generator=g)
+        weight = torch.sigmoid(1.5 * torch.randn(B, 9, k, k, device="cuda", generator=g)).to(dt_w)
+        offset = (1.5 * torch.randn(B, 18, k, k, device="cuda", generator=g)).clamp_(-8, 8).to(dt_w)
+        gt = (init + 0.05 * torch.randn(B, 1, k, k, device="cuda", generator=g)).clamp_(0, 1)
+        res = []
+        for use_ext in (True, False):
+            post = jb.PostProcessor(3, True, 0.9).cuda()
+            with torch.no_grad():
+                post.w.add_(0.05)
+                post.b.fill_(0.02)
+            i_, w_, o_ = init.clone().requires_grad_(need_init), weight.clone().requires_grad_(), offset.clone().requires_grad_()
+            n0 = F.launch_count()
+            if use_ext:
+                out = post(i_, w_, o_)                                   # F.propagate -> extension
+                total, losses = e.multi_loss(out, gt, 1.0, 1.0, 0.1)
+            else:
+                out = F._Propagate.apply(i_, w_, o_, post.w, post.b, 1, 0.9)
+                total, losses = EP._Loss.apply(out, gt, 1.0, 1.0, 0.1)
+            (2.0 * total).backward()
+            assert F.launch_count() - n0 == 3                            # forward, loss, backward
+            res.append([out.detach(), losses.detach(), w_.grad, o_.grad, post.w.grad, post.b.grad] +
+                       ([i_.grad] if need_init else []))
+        for a, b2 in zip(*res):
+            assert a.dtype == b2.dtype and a.shape == b2.shape
+            if a.numel() > 16:
+                assert torch.equal(a, b2)
+            else:                                                        # global sums: fp64 atomics, order-dependent
+                assert torch.allclose(a, b2, rtol=1e-5, atol=1e-7)
+    # errors surface as RuntimeError with the library's message; CPU tensors never reach a kernel
+    with pytest.raises(RuntimeError):
+        e.propagate(init.cpu(), weight.cpu(), offset.cpu(), torch.ones(1, 1, 3, 3), torch.zeros(1), 1, 1.0)
