@@ -636,6 +636,26 @@ def config_batch_latency(torch, jspsr_b200, F, device, dtype):
             e1.record()
             torch.cuda.synchronize()
             res[f"B{B}"]["us_per_fwd_loss_bwd"] = e0.elapsed_time(e1) / n * 1e3
+            # the same step eager, through the drop-in modules and autograd (what an unmodified training loop pays):
+            # wall clock per step, host-bound at these sizes (torch's own floor for a 3-node autograd step is ~135 us)
+            post = jspsr_b200.PostProcessor(3, True, 1.0).to(device)
+            crit = jspsr_b200.MultiLoss(L1=1.0, L2=1.0, Grad=0.1)
+            wr, orq = weight.clone().requires_grad_(), offset.clone().requires_grad_()
+
+            def eager_step():
+                crit(post(init, wr, orq), gt)["Total"].backward()
+                wr.grad = None
+                orq.grad = None
+                post.w.grad = None
+                post.b.grad = None
+            for _ in range(30):
+                eager_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                eager_step()
+            torch.cuda.synchronize()
+            res[f"B{B}"]["eager_us_per_fwd_loss_bwd"] = (time.perf_counter() - t0) / n * 1e6
     out = {"config_batch": res}
     try:  # GPU incumbent: the unmodified call sequence on torchvision's CUDA kernels (a library), same shapes
         from oracle import ref_port
