@@ -11,6 +11,7 @@
 // memory with the replicate border the Sobel operator needs, global sums through fp64 atomics + last-CTA publish.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/jspsr_tiles.h"
 #include "spn_common.cuh"
@@ -19,12 +20,17 @@ int jspsr_internal_fail(int code, const char* msg);  // abi.cu: sets the thread'
 
 namespace jspsr {
 
-constexpr int LT_H = 32;    // rows per CTA
+// rows per CTA: template parameter LT_H in {32, 64}.  64 halves the share of halo rows every phase recomputes (staged
+// rows 36/32 -> 68/64, sign rows marched 7 per 5 -> 12 per 10, adjoint rows 6 per 4 -> 10 per 8) at 55 KB of shared
+// memory; 32 is the default (see the launch)
 constexpr int LT_W = 128;   // columns per CTA (one float4 per lane)
-constexpr int LD_H = LT_H + 4;      // staged difference rows: image row y0 - 2 + r
 constexpr int LD_W = LT_W + 8;      // staged difference columns: image column x0 - 4 + c (columns 2 .. 133 are used)
-constexpr int LS_H = LT_H + 2;      // sign rows: image row y0 - 1 + r
 constexpr int LS_B = LT_W + 8;      // sign row stride in bytes: image column x0 - 4 + c (columns 3 .. 132 are used)
+constexpr int loss_ld_h(int lt_h) { return lt_h + 4; }   // staged difference rows: image row y0 - 2 + r
+constexpr int loss_ls_h(int lt_h) { return lt_h + 2; }   // sign rows: image row y0 - 1 + r
+constexpr size_t loss_smem_bytes(int lt_h, bool grad) {
+    return (size_t)loss_ld_h(lt_h) * LD_W * 4 + (grad ? 2 * (size_t)loss_ls_h(lt_h) * LS_B : 0);
+}
 constexpr int LOSS_SLOTS = 4;       // partial sums are spread over 4 slots of the workspace (fewer same-address atomics)
 
 struct alignas(16) LossWs {
@@ -48,14 +54,16 @@ __device__ __forceinline__ unsigned sgn1(float v) { return 1u + (unsigned)(v > 0
 // and so is the adjoint the gradient needs: A^T s = (1, 2, 1) * s with s REPLICATED one past the border, D^T s =
 // s[i - 1] - s[i + 1] with s NEGATED-and-replicated one past the border.  The sign tiles therefore carry one ring of
 // such extended values around the image and every pixel, border or not, uses the same 12-tap formula (no divergence).
-template <bool WRITE_GRAD, bool VEC>
+template <bool WRITE_GRAD, bool VEC, int LT_H>
 __global__ void __launch_bounds__(THREADS, 4)
 loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ grad,
                        float* __restrict__ losses4, LossWs* __restrict__ ws, int H, int W,
                        float w_l1, float w_l2, float w_grad, float inv_n) {
-    __shared__ __align__(16) float s_d[LD_H][LD_W];
-    __shared__ __align__(16) unsigned char s_sx[WRITE_GRAD ? LS_H : 1][LS_B];
-    __shared__ __align__(16) unsigned char s_sy[WRITE_GRAD ? LS_H : 1][LS_B];
+    constexpr int LD_H = loss_ld_h(LT_H), LS_H = loss_ls_h(LT_H);
+    extern __shared__ __align__(16) unsigned char loss_smem[];
+    float (*s_d)[LD_W] = reinterpret_cast<float (*)[LD_W]>(loss_smem);
+    unsigned char (*s_sx)[LS_B] = reinterpret_cast<unsigned char (*)[LS_B]>(loss_smem + (size_t)LD_H * LD_W * 4);
+    unsigned char (*s_sy)[LS_B] = s_sx + LS_H;      // (both only exist with WRITE_GRAD)
     __shared__ float s_red[WARPS][3];
     __shared__ bool s_last;
 
@@ -71,41 +79,55 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     // ---- phase 1: d over rows y0 - 2 .. y0 + LT_H + 1, columns x0 - 2 .. x0 + LT_W + 1, replicate-clamped ----
     if (VEC) {
         // W % 4 == 0 and 16-byte aligned planes: a lane's float4 is entirely inside or entirely outside the image
-        constexpr int ROWS_PER_WARP = (LD_H + WARPS - 1) / WARPS;   // 5
-        float4 vp[ROWS_PER_WARP], vg[ROWS_PER_WARP];
+        constexpr int ROWS_PER_WARP = (LD_H + WARPS - 1) / WARPS;   // 5 (LT_H = 32) or 9 (64)
+        constexpr int CHUNK = 5;                                    // rows in flight per lane: 10 float4 loads
         const int xc = x0 + 4 * lane;
         const bool in_x = xc < W;
         const int xl = in_x ? xc : W - 4;                   // past the image: the last float4, its .w replicated below
+        // the two halo columns on either side: LD_H rows x 4 columns (threads 0 .. 4 * LD_H - 1, two passes at most)
+        float hp[2] = {0.f, 0.f}, hg[2] = {0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_WARP; ++i) {
-            const int r = min(warp + WARPS * i, LD_H - 1);
-            const int y = min(max(y0 - 2 + r, 0), H - 1);
-            vp[i] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)y * W + xl));
-            vg[i] = __ldcs(reinterpret_cast<const float4*>(g + (size_t)y * W + xl));
-        }
-        // the two halo columns on either side: LD_H rows x 4 columns
-        float hp = 0.f, hg = 0.f;
-        const int hr = threadIdx.x >> 2, hq = threadIdx.x & 3;          // row, which of the 4 columns
-        const int hc = (hq < 2) ? (2 + hq) : (LT_W + 2 + hq);            // staged column 2, 3, 132, 133
-        if (hr < LD_H) {
-            const int y = min(max(y0 - 2 + hr, 0), H - 1), x = min(max(x0 - 4 + hc, 0), W - 1);
-            hp = __ldg(p + (size_t)y * W + x);
-            hg = __ldg(g + (size_t)y * W + x);
+        for (int u = 0; u < 2; ++u) {
+            const int hi = threadIdx.x + u * THREADS;
+            const int hr = hi >> 2, hq = hi & 3;                           // row, which of the 4 columns
+            const int hc = (hq < 2) ? (2 + hq) : (LT_W + 2 + hq);          // staged column 2, 3, 132, 133
+            if (hr < LD_H) {
+                const int y = min(max(y0 - 2 + hr, 0), H - 1), x = min(max(x0 - 4 + hc, 0), W - 1);
+                hp[u] = __ldg(p + (size_t)y * W + x);
+                hg[u] = __ldg(g + (size_t)y * W + x);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_WARP; ++i) {
-            const int r = warp + WARPS * i;
-            if (r < LD_H) {
-                float4 d = make_float4(vp[i].x - vg[i].x, vp[i].y - vg[i].y, vp[i].z - vg[i].z, vp[i].w - vg[i].w);
-                if (!in_x) d.x = d.y = d.z = d.w;
-                *reinterpret_cast<float4*>(&s_d[r][4 + 4 * lane]) = d;
-                if (r >= 2 && r < LT_H + 2 && y0 - 2 + r < H && in_x) {       // own pixels: L1 and L2 from registers
-                    a_l1 += (fabsf(d.x) + fabsf(d.y)) + (fabsf(d.z) + fabsf(d.w));
-                    a_l2 += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+        for (int i0 = 0; i0 < ROWS_PER_WARP; i0 += CHUNK) {
+            float4 vp[CHUNK], vg[CHUNK];
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+                const int r = min(warp + WARPS * (i0 + i), LD_H - 1);
+                const int y = min(max(y0 - 2 + r, 0), H - 1);
+                vp[i] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)y * W + xl));
+                vg[i] = __ldcs(reinterpret_cast<const float4*>(g + (size_t)y * W + xl));
+            }
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+                const int r = warp + WARPS * (i0 + i);
+                if (i0 + i < ROWS_PER_WARP && r < LD_H) {
+                    float4 d = make_float4(vp[i].x - vg[i].x, vp[i].y - vg[i].y, vp[i].z - vg[i].z, vp[i].w - vg[i].w);
+                    if (!in_x) d.x = d.y = d.z = d.w;
+                    *reinterpret_cast<float4*>(&s_d[r][4 + 4 * lane]) = d;
+                    if (r >= 2 && r < LT_H + 2 && y0 - 2 + r < H && in_x) {       // own pixels: L1 and L2 from registers
+                        a_l1 += (fabsf(d.x) + fabsf(d.y)) + (fabsf(d.z) + fabsf(d.w));
+                        a_l2 += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+                    }
                 }
             }
         }
-        if (hr < LD_H) s_d[hr][hc] = hp - hg;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int hi = threadIdx.x + u * THREADS;
+            const int hr = hi >> 2, hq = hi & 3;
+            const int hc = (hq < 2) ? (2 + hq) : (LT_W + 2 + hq);
+            if (hr < LD_H) s_d[hr][hc] = hp[u] - hg[u];
+        }
     } else {
         for (int i = threadIdx.x; i < LD_H * (LT_W + 4); i += THREADS) {
             const int r = i / (LT_W + 4), c = 2 + (i - r * (LT_W + 4));
@@ -127,52 +149,54 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     // registers (fully unrolled: the rolling window is renamed, not moved); warp 7 takes the two sign columns
     // beside the tile.  Sign cells outside the image are left as computed from the clamped d: the cells one step
     // outside are overwritten by the ring pass below and nothing reads the ones further out.
-    constexpr int RPW = (LS_H + WARPS - 2) / (WARPS - 1);   // 5 sign rows per marching warp
-    static_assert(RPW * (WARPS - 1) >= LS_H && RPW * (WARPS - 2) + 2 < LD_H, "phase-2 row split");
+    constexpr int RPW = (LS_H + WARPS - 2) / (WARPS - 1);   // sign rows per marching warp: 5 (LT_H = 32) or 10 (64)
+    static_assert(RPW * (WARPS - 1) >= LS_H, "phase-2 row split");
     if (warp < WARPS - 1) {
         const int ra = warp * RPW;                           // sign rows ra .. ra + RPW - 1: image row y0 - 1 + r
-        float hd[RPW + 2][4], hs[RPW + 2][4];
+        float hd[3][4], hs[3][4];                            // d rows i - 2, i - 1, i (slot = row % 3)
 #pragma unroll
         for (int i = 0; i < RPW + 2; ++i) {
-            const int dr = min(ra + i, LD_H - 1);
-            // d at image columns x0 + 4 lane - 1 .. + 4: own float4, one value from each neighbour lane
-            const float4 m = *reinterpret_cast<const float4*>(&s_d[dr][4 + 4 * lane]);
-            float l = __shfl_up_sync(0xffffffffu, m.w, 1);
-            float r = __shfl_down_sync(0xffffffffu, m.x, 1);
-            if (lane == 0) l = s_d[dr][3];
-            if (lane == 31) r = s_d[dr][LT_W + 4];
-            const float e[6] = {l, m.x, m.y, m.z, m.w, r};
+            {
+                const int dr = min(ra + i, LD_H - 1);
+                // d at image columns x0 + 4 lane - 1 .. + 4: own float4, one value from each neighbour lane
+                const float4 m = *reinterpret_cast<const float4*>(&s_d[dr][4 + 4 * lane]);
+                float l = __shfl_up_sync(0xffffffffu, m.w, 1);
+                float r = __shfl_down_sync(0xffffffffu, m.x, 1);
+                if (lane == 0) l = s_d[dr][3];
+                if (lane == 31) r = s_d[dr][LT_W + 4];
+                const float e[6] = {l, m.x, m.y, m.z, m.w, r};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                hd[i][q] = e[q + 2] - e[q];
-                hs[i][q] = (e[q] + e[q + 2]) + 2.f * e[q + 1];
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const int r = ra + i;
-            const int y = y0 - 1 + r;
-            const bool own = (y >= 0 && y < H) && r >= 1 && r <= LT_H;     // a row of this CTA's own pixels
-            unsigned px = 0x01010101u, py = 0x01010101u;
-            float a_row = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float gx = (hd[i][q] + hd[i + 2][q]) + 2.f * hd[i + 1][q];
-                const float gy = hs[i + 2][q] - hs[i][q];
-                const float ag = fabsf(gx) + fabsf(gy);
-                if (VEC) a_row += ag;
-                else a_row += (x0 + 4 * lane + q < W) ? ag : 0.f;
-                if (WRITE_GRAD) {
-                    px += (gx > 0.f) ? (1u << (8 * q)) : 0u;
-                    px -= (gx < 0.f) ? (1u << (8 * q)) : 0u;
-                    py += (gy > 0.f) ? (1u << (8 * q)) : 0u;
-                    py -= (gy < 0.f) ? (1u << (8 * q)) : 0u;
+                for (int q = 0; q < 4; ++q) {
+                    hd[i % 3][q] = e[q + 2] - e[q];
+                    hs[i % 3][q] = (e[q] + e[q + 2]) + 2.f * e[q + 1];
                 }
             }
-            a_grad += (own && (!VEC || x0 + 4 * lane < W)) ? a_row : 0.f;
-            if (WRITE_GRAD && r < LS_H) {
-                *reinterpret_cast<unsigned*>(&s_sx[r][4 + 4 * lane]) = px;
-                *reinterpret_cast<unsigned*>(&s_sy[r][4 + 4 * lane]) = py;
+            if (i >= 2) {
+                const int j = i - 2;                         // sign row ra + j from d rows j, j + 1, j + 2
+                const int r = ra + j;
+                const int y = y0 - 1 + r;
+                const bool own = (y >= 0 && y < H) && r >= 1 && r <= LT_H;     // a row of this CTA's own pixels
+                unsigned px = 0x01010101u, py = 0x01010101u;
+                float a_row = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float gx = (hd[j % 3][q] + hd[(j + 2) % 3][q]) + 2.f * hd[(j + 1) % 3][q];
+                    const float gy = hs[(j + 2) % 3][q] - hs[j % 3][q];
+                    const float ag = fabsf(gx) + fabsf(gy);
+                    if (VEC) a_row += ag;
+                    else a_row += (x0 + 4 * lane + q < W) ? ag : 0.f;
+                    if (WRITE_GRAD) {
+                        px += (gx > 0.f) ? (1u << (8 * q)) : 0u;
+                        px -= (gx < 0.f) ? (1u << (8 * q)) : 0u;
+                        py += (gy > 0.f) ? (1u << (8 * q)) : 0u;
+                        py -= (gy < 0.f) ? (1u << (8 * q)) : 0u;
+                    }
+                }
+                a_grad += (own && (!VEC || x0 + 4 * lane < W)) ? a_row : 0.f;
+                if (WRITE_GRAD && r < LS_H) {
+                    *reinterpret_cast<unsigned*>(&s_sx[r][4 + 4 * lane]) = px;
+                    *reinterpret_cast<unsigned*>(&s_sy[r][4 + 4 * lane]) = py;
+                }
             }
         }
     } else if (WRITE_GRAD) {
@@ -404,22 +428,46 @@ extern "C" int jspsr_loss_l1_l2_grad(const float* pred, const float* gt, float w
     if (((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)losses4 | (uintptr_t)grad_pred) & 3)
         return jspsr_internal_fail(JSPSR_ERR_ALIGN, "loss: a float pointer is not 4-byte aligned");
     if ((uintptr_t)workspace & 15) return jspsr_internal_fail(JSPSR_ERR_ALIGN, "loss: workspace is not 16-byte aligned");
-    const int tiles_x = (W + LT_W - 1) / LT_W, tiles_y = (H + LT_H - 1) / LT_H;
+    const int tiles_x = (W + LT_W - 1) / LT_W;
+    // 32-row tiles.  The 64-row instantiation halves the halo share but measured no better on B200 (4096 tiles: 0.223 ms
+    // vs 0.201 ms with the gradient, 0.119 vs 0.121 ms without: longer phases between the CTA barriers at the same four
+    // resident CTAs); it stays reachable through JSPSR_LOSS_TILE_H=64 (tests hold the two to identical bits)
+    int lt_h = 32;
+    if (const char* ev = getenv("JSPSR_LOSS_TILE_H")) {
+        if (atoi(ev) == 32 || atoi(ev) == 64) lt_h = atoi(ev);
+    }
+    const int tiles_y = (H + lt_h - 1) / lt_h;
     if (tiles_x > 65535 || tiles_y > 65535) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: plane too large");
     if ((long long)planes * tiles_x * tiles_y > 0xffffffffLL) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: more than 2^32 tiles");
     const dim3 ctas((unsigned)planes, (unsigned)tiles_x, (unsigned)tiles_y);
     const float inv_n = (float)(1.0 / ((double)planes * H * W));
     // float4 path: rows 16-byte aligned (W % 4 == 0 and aligned bases)
     const bool vec = (W % 4 == 0) && !(((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)grad_pred) & 15);
-#define JSPSR_LAUNCH_LOSS(G, V)                                                                         \
-    loss_l1_l2_grad_kernel<G, V><<<ctas, THREADS, 0, (cudaStream_t)stream>>>(                           \
-        pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, w_l1, w_l2, w_grad, inv_n)
+    cudaError_t se = cudaSuccess;
+#define JSPSR_LAUNCH_LOSS(G, V, TH)                                                                       \
+    do {                                                                                                  \
+        constexpr size_t smem = loss_smem_bytes(TH, G);                                                   \
+        if (smem > 48 * 1024) se = ensure_dynamic_smem((const void*)loss_l1_l2_grad_kernel<G, V, TH>, smem); \
+        if (se == cudaSuccess)                                                                            \
+            loss_l1_l2_grad_kernel<G, V, TH><<<ctas, THREADS, smem, (cudaStream_t)stream>>>(             \
+                pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, w_l1, w_l2, w_grad, inv_n);       \
+    } while (0)
+#define JSPSR_LAUNCH_LOSS_TH(G, V)                                          \
+    do {                                                                    \
+        if (lt_h == 64) JSPSR_LAUNCH_LOSS(G, V, 64); else JSPSR_LAUNCH_LOSS(G, V, 32); \
+    } while (0)
     if (grad_pred) {
-        if (vec) JSPSR_LAUNCH_LOSS(true, true); else JSPSR_LAUNCH_LOSS(true, false);
+        if (vec) JSPSR_LAUNCH_LOSS_TH(true, true); else JSPSR_LAUNCH_LOSS_TH(true, false);
     } else {
-        if (vec) JSPSR_LAUNCH_LOSS(false, true); else JSPSR_LAUNCH_LOSS(false, false);
+        if (vec) JSPSR_LAUNCH_LOSS_TH(false, true); else JSPSR_LAUNCH_LOSS_TH(false, false);
     }
+#undef JSPSR_LAUNCH_LOSS_TH
 #undef JSPSR_LAUNCH_LOSS
+    if (se != cudaSuccess) {
+        char msg[256];
+        snprintf(msg, sizeof(msg), "loss kernel shared-memory opt-in: %s", cudaGetErrorString(se));
+        return jspsr_internal_fail(JSPSR_ERR_CUDA, msg);
+    }
     const cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         char msg[256];

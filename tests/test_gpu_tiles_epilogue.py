@@ -449,3 +449,45 @@ def test_torch_extension_path_equals_ctypes_path_bitwise(jb):
     # errors surface as RuntimeError with the library's message; CPU tensors never reach a kernel
     with pytest.raises(RuntimeError):
         e.propagate(init.cpu(), weight.cpu(), offset.cpu(), torch.ones(1, 1, 3, 3), torch.zeros(1), 1, 1.0)
+
+
+@pytest.mark.parametrize("n_y,n_x,k,stride,border", [(2, 5, 32, 24, 0.1), (4, 1, 40, 30, 0.0), (1, 6, 24, 20, 0.05), (3, 2, 16, 5, 0.0)])
+def test_rectangular_walks_round_trip(jb, n_y, n_x, k, stride, border):
+    """Strips and rectangular rasters (explicit stride / grid): tiles cut from one raster blend back to it, for the
+    2 x 2 gather kernel (stride >= L / 2) and the generic one (last case: up to four tiles overlap along an axis)."""
+    g = torch.Generator(device="cuda").manual_seed(n_y * 10 + n_x)
+    H, W = stride * (n_y - 1) + k, stride * (n_x - 1) + k
+    raster = torch.rand(2, H, W, device="cuda", generator=g)
+    tiles = jb.tiles.crop_tiles(raster, k, stride=stride, grid=(n_y, n_x))          # [n, 2, k, k]
+    assert tiles.shape == (n_y * n_x, 2, k, k)
+    c = int(k * border)
+    per_channel = tiles.permute(1, 0, 2, 3).contiguous()                             # [S = 2, n, k, k]
+    if k - 2 * c <= 2 * stride:
+        merged = jb.tiles.merge_tiles(per_channel, border, stride=stride, grid=(n_y, n_x))
+        assert merged.shape == (2, H - 2 * c, W - 2 * c)
+        want = raster[:, c:H - c, c:W - c].double()
+        assert float((merged - want).abs().max()) < 1e-6
+    else:
+        # more than two tiles overlap: the reference's ramps no longer sum to one; compare the two kernels' common
+        # ground instead - every pixel covered by a single tile is an exact copy
+        merged = jb.tiles.merge_tiles(per_channel, border, stride=stride, grid=(n_y, n_x))
+        L = k - 2 * c
+        assert merged.shape == (2, stride * (n_y - 1) + L, stride * (n_x - 1) + L)
+        assert torch.equal(merged[:, :stride, :stride], raster[:, c:c + stride, c:c + stride].double())
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (2, 1, 2, 3), (1, 1, 70, 1), (3, 2, 17, 129), (2, 1, 130, 257), (6, 1, 128, 128),
+                                     (1, 1, 334, 334), (2, 1, 40, 136), (1, 2, 64, 256), (1, 1, 65, 260), (1, 1, 97, 132)])
+def test_loss_matches_oracle_with_64_row_tiles(jb, monkeypatch, B, C, H, W):
+    """The 64-row instantiation (picked by itself only for large batches) against the oracle on the ragged shapes."""
+    monkeypatch.setenv("JSPSR_LOSS_TILE_H", "64")
+    rng = np.random.default_rng(B * 999 + H + W)
+    gt = rng.random((B, C, H, W)).astype(np.float32)
+    pred = (gt + 0.05 * rng.normal(size=gt.shape)).astype(np.float32)
+    check_loss(jb, pred, gt)
+    # and it is the 32-row kernel's gradient, bit for bit (the per-pixel arithmetic does not depend on the tiling)
+    from jspsr_b200 import epilogue as EP
+    _, g64 = EP.loss_l1_l2_grad(dev(pred), dev(gt))
+    monkeypatch.setenv("JSPSR_LOSS_TILE_H", "32")
+    _, g32 = EP.loss_l1_l2_grad(dev(pred), dev(gt))
+    assert torch.equal(g64, g32)
