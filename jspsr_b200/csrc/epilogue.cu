@@ -55,7 +55,7 @@ __device__ __forceinline__ unsigned sgn1(float v) { return 1u + (unsigned)(v > 0
 // s[i - 1] - s[i + 1] with s NEGATED-and-replicated one past the border.  The sign tiles therefore carry one ring of
 // such extended values around the image and every pixel, border or not, uses the same 12-tap formula (no divergence).
 template <bool WRITE_GRAD, bool VEC, int LT_H>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, WRITE_GRAD ? 5 : 4)
 loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ grad,
                        float* __restrict__ losses4, LossWs* __restrict__ ws, int H, int W,
                        float w_l1, float w_l2, float w_grad, float inv_n) {
