@@ -444,8 +444,8 @@ def side_numbers(torch, F, device, B):
     peak, _ = peak_hbm()
     out = {}
 
-    def timed(fn, n=5):
-        for _ in range(2):
+    def timed(fn, n=5, warm=2):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -582,28 +582,28 @@ def neighbour_rows(torch, device, timed, peak, B):
     pred = gt + 0.05 * torch.randn(B, 1, TILE, TILE, device=device, generator=g)
     px = B * TILE * TILE
     res = {}
-    t = timed(lambda: EP.loss_l1_l2_grad(pred, gt), n=10)
+    t = timed(lambda: EP.loss_l1_l2_grad(pred, gt), n=20, warm=5)
     res["loss_l1_l2_sobel_with_gradient"] = {"ms": t, "bytes_per_pixel": 12, "frac_of_hbm_peak": 12 * px / (t * 1e-3) / 1e9 / peak,
                                             "tiles": B, "note": "issue-bound (two-level 3x3 stencil: Sobel, then its adjoint)"}
-    t = timed(lambda: EP.loss_l1_l2_grad(pred, gt, want_grad=False), n=10)
+    t = timed(lambda: EP.loss_l1_l2_grad(pred, gt, want_grad=False), n=20, warm=5)
     res["loss_only"] = {"ms": t, "bytes_per_pixel": 8, "frac_of_hbm_peak": 8 * px / (t * 1e-3) / 1e9 / peak, "tiles": B}
     crop = int(TILE * 0.05)
     win = (TILE - 2 * crop) ** 2
-    t = timed(lambda: EP.dem_metrics(pred, gt, 0.05, -80.0, 929.0, True), n=10)
+    t = timed(lambda: EP.dem_metrics(pred, gt, 0.05, -80.0, 929.0, True), n=20, warm=5)
     res["rmse_mae_sums_log"] = {"ms": t, "bytes_per_window_pixel": 8, "frac_of_hbm_peak": 8 * B * win / (t * 1e-3) / 1e9 / peak,
                                 "tiles": B, "note": "two expf per pixel: issue-bound"}
     del pred, gt
     k, stride, n = TILE, 103, 100
     side = stride * (n - 1) + k
     raster = torch.rand(1, side, side, device=device, generator=g)
-    t = timed(lambda: TL.crop_tiles(raster, k, stride=stride, grid=(n, n)), n=10)
+    t = timed(lambda: TL.crop_tiles(raster, k, stride=stride, grid=(n, n)), n=20, warm=5)
     res["tile_crop"] = {"ms": t, "raster": [side, side], "tiles": n * n, "bytes_per_tile_pixel": 8,
                         "frac_of_hbm_peak": 8 * n * n * k * k / (t * 1e-3) / 1e9 / peak}
     tl = TL.crop_tiles(raster, k, stride=stride, grid=(n, n)).reshape(1, n * n, k, k)
     L = k - 2 * crop
     out_side = stride * (n - 1) + L
     for name, dt, ob in (("float64", torch.float64, 8), ("float32", torch.float32, 4)):
-        t = timed(lambda: TL.merge_tiles(tl, 0.05, stride=stride, grid=(n, n), dtype=dt), n=10)
+        t = timed(lambda: TL.merge_tiles(tl, 0.05, stride=stride, grid=(n, n), dtype=dt), n=20, warm=5)
         nbytes = 4 * n * n * L * L + ob * out_side * out_side
         res["blended_merge_" + name] = {"ms": t, "raster": [out_side, out_side], "tiles": n * n, "algorithmic_bytes": nbytes,
                                         "frac_of_hbm_peak": nbytes / (t * 1e-3) / 1e9 / peak}
