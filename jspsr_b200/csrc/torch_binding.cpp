@@ -26,7 +26,9 @@ namespace {
 
 std::atomic<int64_t> g_launches{0};
 std::mutex g_ws_mutex;
-std::map<std::pair<int, void*>, at::Tensor> g_ws;
+// heap-allocated and never destroyed: the tensors must not be released by a static destructor after torch's CUDA
+// allocator has shut down at interpreter exit
+auto& g_ws = *new std::map<std::pair<int, void*>, at::Tensor>();
 
 // zero-initialised reduction scratch, one per (device, stream); the kernels leave it zeroed
 at::Tensor workspace_for(const at::Tensor& like, void* stream) {
