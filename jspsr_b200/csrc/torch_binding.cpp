@@ -82,7 +82,6 @@ class PropagateFn : public torch::autograd::Function<PropagateFn> {
         ctx->save_for_backward({init, weight, offset, w});
         ctx->saved_data["norm_mode"] = norm_mode;
         ctx->saved_data["scale"] = scale;
-        ctx->saved_data["w_dtype"] = (int64_t)w.scalar_type();
         return spn_forward_raw(init, weight, offset, w, b, norm_mode, scale);
     }
 
