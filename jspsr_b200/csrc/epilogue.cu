@@ -54,7 +54,13 @@ __device__ __forceinline__ unsigned sgn1(float v) { return 1u + (unsigned)(v > 0
 // and so is the adjoint the gradient needs: A^T s = (1, 2, 1) * s with s REPLICATED one past the border, D^T s =
 // s[i - 1] - s[i + 1] with s NEGATED-and-replicated one past the border.  The sign tiles therefore carry one ring of
 // such extended values around the image and every pixel, border or not, uses the same 12-tap formula (no divergence).
-template <bool WRITE_GRAD, bool VEC, int LT_H>
+//
+// FUSED (float4 path with the gradient): after d is staged there is no further CTA-wide step.  Each warp marches down
+// its own LT_H / 8 pixel rows with the Sobel rows, the packed signs and the adjoint's row terms U, V all in registers;
+// the signs of neighbouring columns come from the neighbouring lanes by shuffle, the two columns beside the tile from a
+// per-warp pre-pass, and the ring one past the image border is applied in registers (x: lanes at the first / last image
+// column; y: U(-1) = U(0), V(-1) = 8 - V(0) bytewise, same at the bottom).  No sign tile, no ring pass, one barrier.
+template <bool WRITE_GRAD, bool VEC, int LT_H, bool FUSED>
 __global__ void __launch_bounds__(THREADS, WRITE_GRAD ? 5 : 4)
 loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ grad,
                        float* __restrict__ losses4, LossWs* __restrict__ ws, int H, int W,
@@ -144,6 +150,111 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     }
     __syncthreads();
 
+    if constexpr (FUSED) {
+        static_assert(WRITE_GRAD && VEC, "the fused march is the float4 gradient path");
+        constexpr int PR = LT_H / WARPS;          // pixel rows per warp
+        constexpr int NS = PR + 2;                // sign rows per warp: pixel rows pr0 - 1 .. pr0 + PR
+        __shared__ unsigned short s_edge[WARPS][NS][2];
+        const int pr0 = warp * PR;
+        if (lane < 2 * NS) {
+            // signs of the columns just left / right of the tile (image columns x0 - 1, x0 + LT_W) for this warp's rows
+            const int side = lane / NS, jr = lane - side * NS;
+            const int r = pr0 + jr, c = side ? LT_W + 4 : 3;
+            const float d00 = s_d[r][c - 1], d01 = s_d[r][c], d02 = s_d[r][c + 1];
+            const float d10 = s_d[r + 1][c - 1], d12 = s_d[r + 1][c + 1];
+            const float d20 = s_d[r + 2][c - 1], d21 = s_d[r + 2][c], d22 = s_d[r + 2][c + 1];
+            const unsigned vx = sgn1(((d02 - d00) + (d22 - d20)) + 2.f * (d12 - d10));
+            const unsigned vy = sgn1(((d20 + d22) + 2.f * d21) - ((d00 + d02) + 2.f * d01));
+            s_edge[warp][jr][side] = (unsigned short)(vx | (vy << 8));
+        }
+        __syncwarp();
+        const float c_pix_l1 = w_l1 * inv_n, c_pix_l2 = 2.f * w_l2 * inv_n, c_sob = w_grad * 0.5f * inv_n * 0.125f;
+        const int xl = x0 + 4 * lane;
+        const bool in_x = xl < W;
+        float hd[3][4], hs[3][4];
+        unsigned U[3], V[3];
+#pragma unroll
+        for (int i = 0; i < NS + 2; ++i) {
+            {
+                const int dr = pr0 + i;                      // staged d row: image row y0 - 2 + dr  (dr <= LD_H - 1)
+                const float4 m = *reinterpret_cast<const float4*>(&s_d[dr][4 + 4 * lane]);
+                float l = __shfl_up_sync(0xffffffffu, m.w, 1);
+                float r = __shfl_down_sync(0xffffffffu, m.x, 1);
+                if (lane == 0) l = s_d[dr][3];
+                if (lane == 31) r = s_d[dr][LT_W + 4];
+                const float e[6] = {l, m.x, m.y, m.z, m.w, r};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    hd[i % 3][q] = e[q + 2] - e[q];
+                    hs[i % 3][q] = (e[q] + e[q + 2]) + 2.f * e[q + 1];
+                }
+            }
+            if (i >= 2) {
+                const int jr = i - 2;                        // sign row: image row y = y0 - 1 + pr0 + jr
+                const int y = y0 - 1 + pr0 + jr;
+                unsigned px = 0x01010101u, py = 0x01010101u;
+                float a_row = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float gx = (hd[jr % 3][q] + hd[(jr + 2) % 3][q]) + 2.f * hd[(jr + 1) % 3][q];
+                    const float gy = hs[(jr + 2) % 3][q] - hs[jr % 3][q];
+                    a_row += fabsf(gx) + fabsf(gy);
+                    px += (gx > 0.f) ? (1u << (8 * q)) : 0u;
+                    px -= (gx < 0.f) ? (1u << (8 * q)) : 0u;
+                    py += (gy > 0.f) ? (1u << (8 * q)) : 0u;
+                    py -= (gy < 0.f) ? (1u << (8 * q)) : 0u;
+                }
+                if (jr >= 1 && jr <= PR) a_grad += (y >= 0 && y < H && in_x) ? a_row : 0.f;   // this warp's own rows
+                // the neighbouring columns' signs: lanes beside, the tile's side columns, or the ring at the image border
+                unsigned lx = __shfl_up_sync(0xffffffffu, px, 1), rx = __shfl_down_sync(0xffffffffu, px, 1);
+                unsigned ly = __shfl_up_sync(0xffffffffu, py, 1), ry = __shfl_down_sync(0xffffffffu, py, 1);
+                if (lane == 0) {
+                    const unsigned e = s_edge[warp][jr][0];
+                    lx = (e & 0xffu) << 24;
+                    ly = (e >> 8) << 24;
+                }
+                if (lane == 31) {
+                    const unsigned e = s_edge[warp][jr][1];
+                    rx = e & 0xffu;
+                    ry = e >> 8;
+                }
+                if (xl == 0) {                               // x = -1: d/dx sign negated, d/dy sign replicated
+                    lx = (2u - (px & 0xffu)) << 24;
+                    ly = (py & 0xffu) << 24;
+                }
+                if (xl + 4 == W) {                           // x = W
+                    rx = 2u - (px >> 24);
+                    ry = py >> 24;
+                }
+                const unsigned Lx = __funnelshift_r(lx, px, 24), Rx = __funnelshift_r(px, rx, 8);
+                const unsigned Ly = __funnelshift_r(ly, py, 24), Ry = __funnelshift_r(py, ry, 8);
+                unsigned Ur = Lx + (0x02020202u - Rx);       // (sx[x - 1] - sx[x + 1]) + 2 per byte
+                unsigned Vr = Ly + 2u * py + Ry;             // (sy[x - 1] + 2 sy[x] + sy[x + 1]) + 4 per byte
+                if (jr >= 1 && y == H) {                     // the row below the image: sx replicated, sy negated
+                    Ur = U[(jr + 2) % 3];
+                    Vr = 0x08080808u - V[(jr + 2) % 3];
+                }
+                U[jr % 3] = Ur;
+                V[jr % 3] = Vr;
+                if (jr >= 1 && y == 0) {                     // the row above the image, derived from row 0
+                    U[(jr + 2) % 3] = Ur;
+                    V[(jr + 2) % 3] = 0x08080808u - Vr;
+                }
+                if (jr >= 2) {
+                    const int pr = pr0 + jr - 2, yp = y0 + pr;   // pixel row between sign rows jr - 2 and jr
+                    // (sum + 16) per byte: U0 + 2 U1 + U2 carries 8, V0 + (8 - V2) carries 8
+                    const unsigned G = U[(jr + 1) % 3] + 2u * U[(jr + 2) % 3] + U[jr % 3] + V[(jr + 1) % 3] + (0x08080808u - V[jr % 3]);
+                    const float4 d = *reinterpret_cast<const float4*>(&s_d[pr + 2][4 + 4 * lane]);
+                    float4 o;
+                    o.x = csgn(c_pix_l1, d.x) + c_pix_l2 * d.x + c_sob * ((float)(G & 0xffu) - 16.f);
+                    o.y = csgn(c_pix_l1, d.y) + c_pix_l2 * d.y + c_sob * ((float)((G >> 8) & 0xffu) - 16.f);
+                    o.z = csgn(c_pix_l1, d.z) + c_pix_l2 * d.z + c_sob * ((float)((G >> 16) & 0xffu) - 16.f);
+                    o.w = csgn(c_pix_l1, d.w) + c_pix_l2 * d.w + c_sob * ((float)(G >> 24) - 16.f);
+                    if (yp < H && in_x) __stcs(reinterpret_cast<float4*>(grad + plane + (size_t)yp * W + xl), o);
+                }
+            }
+        }
+    } else {
     // ---- phase 2: Sobel of d, its |.| sum and (for the gradient) its biased signs ----
     // Warps 0 .. 6 march down five sign rows each with the horizontal difference / smoothing of three d rows in
     // registers (fully unrolled: the rolling window is renamed, not moved); warp 7 takes the two sign columns
@@ -305,6 +416,8 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
         }
     }
 
+    }  // !FUSED
+
     // ---- thread -> warp -> CTA -> fp64 atomics; the last CTA publishes the four losses ----
     a_l1 = warp_sum(a_l1);
     a_l2 = warp_sum(a_l2);
@@ -433,6 +546,16 @@ extern "C" int jspsr_loss_l1_l2_grad(const float* pred, const float* gt, float w
     // vs 0.201 ms with the gradient, 0.119 vs 0.121 ms without: longer phases between the CTA barriers at the same four
     // resident CTAs); it stays reachable through JSPSR_LOSS_TILE_H=64 (tests hold the two to identical bits)
     int lt_h = 32;
+    // float4 path: rows 16-byte aligned (W % 4 == 0 and aligned bases)
+    const bool vec = (W % 4 == 0) && !(((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)grad_pred) & 15);
+    // With the gradient on the float4 path there are two kernels of identical per-pixel arithmetic (tests: equal bits):
+    // the phased one (sign tiles in shared memory) and the fused per-warp march.  Measured on B200, 4096 tiles, same box:
+    // phased/32 rows 0.188 ms, fused/32 0.197 ms, fused/64 0.183 ms, phased/64 0.223 ms - so large grids take the fused
+    // march on 64-row tiles and everything else the phased kernel on 32-row tiles.  JSPSR_LOSS_FUSED / JSPSR_LOSS_TILE_H
+    // override (tests).
+    bool fused = vec && grad_pred && H > 32 && (long long)planes * tiles_x * ((H + 63) / 64) >= 2LL * 5 * 148;
+    if (const char* ev = getenv("JSPSR_LOSS_FUSED")) fused = vec && grad_pred && atoi(ev) != 0;
+    if (fused) lt_h = 64;
     if (const char* ev = getenv("JSPSR_LOSS_TILE_H")) {
         if (atoi(ev) == 32 || atoi(ev) == 64) lt_h = atoi(ev);
     }
@@ -441,25 +564,25 @@ extern "C" int jspsr_loss_l1_l2_grad(const float* pred, const float* gt, float w
     if ((long long)planes * tiles_x * tiles_y > 0xffffffffLL) return jspsr_internal_fail(JSPSR_ERR_UNSUPPORTED, "loss: more than 2^32 tiles");
     const dim3 ctas((unsigned)planes, (unsigned)tiles_x, (unsigned)tiles_y);
     const float inv_n = (float)(1.0 / ((double)planes * H * W));
-    // float4 path: rows 16-byte aligned (W % 4 == 0 and aligned bases)
-    const bool vec = (W % 4 == 0) && !(((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)grad_pred) & 15);
     cudaError_t se = cudaSuccess;
-#define JSPSR_LAUNCH_LOSS(G, V, TH)                                                                       \
+#define JSPSR_LAUNCH_LOSS(G, V, TH, FU)                                                                   \
     do {                                                                                                  \
-        constexpr size_t smem = loss_smem_bytes(TH, G);                                                   \
-        if (smem > 48 * 1024) se = ensure_dynamic_smem((const void*)loss_l1_l2_grad_kernel<G, V, TH>, smem); \
+        constexpr size_t smem = loss_smem_bytes(TH, (G) && !(FU));                                        \
+        if (smem > 48 * 1024) se = ensure_dynamic_smem((const void*)loss_l1_l2_grad_kernel<G, V, TH, FU>, smem); \
         if (se == cudaSuccess)                                                                            \
-            loss_l1_l2_grad_kernel<G, V, TH><<<ctas, THREADS, smem, (cudaStream_t)stream>>>(             \
+            loss_l1_l2_grad_kernel<G, V, TH, FU><<<ctas, THREADS, smem, (cudaStream_t)stream>>>(         \
                 pred, gt, grad_pred, losses4, (LossWs*)workspace, H, W, w_l1, w_l2, w_grad, inv_n);       \
     } while (0)
-#define JSPSR_LAUNCH_LOSS_TH(G, V)                                          \
+#define JSPSR_LAUNCH_LOSS_TH(G, V, FU)                                      \
     do {                                                                    \
-        if (lt_h == 64) JSPSR_LAUNCH_LOSS(G, V, 64); else JSPSR_LAUNCH_LOSS(G, V, 32); \
+        if (lt_h == 64) JSPSR_LAUNCH_LOSS(G, V, 64, FU); else JSPSR_LAUNCH_LOSS(G, V, 32, FU); \
     } while (0)
     if (grad_pred) {
-        if (vec) JSPSR_LAUNCH_LOSS_TH(true, true); else JSPSR_LAUNCH_LOSS_TH(true, false);
+        if (fused) JSPSR_LAUNCH_LOSS_TH(true, true, true);
+        else if (vec) JSPSR_LAUNCH_LOSS_TH(true, true, false);
+        else JSPSR_LAUNCH_LOSS_TH(true, false, false);
     } else {
-        if (vec) JSPSR_LAUNCH_LOSS_TH(false, true); else JSPSR_LAUNCH_LOSS_TH(false, false);
+        if (vec) JSPSR_LAUNCH_LOSS_TH(false, true, false); else JSPSR_LAUNCH_LOSS_TH(false, false, false);
     }
 #undef JSPSR_LAUNCH_LOSS_TH
 #undef JSPSR_LAUNCH_LOSS

@@ -168,7 +168,9 @@ def check_loss(jb, pred, gt, ref_losses=None, ref_grad=None):
         assert np.abs(got - ref_grad)[ok].max() <= 1e-5 * scale
     # losses-only call (no gradient requested) gives the same numbers
     l2, g2 = EP.loss_l1_l2_grad(dev(pred), dev(gt), want_grad=False)
-    assert g2 is None and np.array_equal(l2.cpu().numpy().astype(np.float64), losses)
+    # (the gradient path may run the fused march, the loss-only path the phased kernel: the fp32 partial sums are
+    #  grouped differently, so the published floats can differ in the last place)
+    assert g2 is None and np.allclose(l2.cpu().numpy().astype(np.float64), losses, rtol=1e-6, atol=0)
 
 
 @pytest.mark.parametrize("tag", ["loss_a", "loss_b", "loss_c"])
@@ -491,3 +493,26 @@ def test_loss_matches_oracle_with_64_row_tiles(jb, monkeypatch, B, C, H, W):
     monkeypatch.setenv("JSPSR_LOSS_TILE_H", "32")
     _, g32 = EP.loss_l1_l2_grad(dev(pred), dev(gt))
     assert torch.equal(g64, g32)
+
+
+@pytest.mark.parametrize("tile_h", ["32", "64"])
+@pytest.mark.parametrize("B,C,H,W", [(2, 1, 1, 4), (1, 1, 2, 8), (3, 1, 31, 4), (2, 1, 40, 136), (1, 2, 64, 256), (1, 1, 65, 260),
+                                     (1, 1, 97, 132), (6, 1, 128, 128), (1, 1, 33, 128), (1, 1, 200, 384)])
+def test_fused_loss_march_equals_phased_kernel_bitwise(jb, monkeypatch, tile_h, B, C, H, W):
+    """The float4 gradient path runs as one per-warp march (signs and adjoint rows in registers, ring applied in
+    registers); the phased kernel (sign tiles in shared memory, ring pass) computes the same per-pixel arithmetic."""
+    from jspsr_b200 import epilogue as EP
+    monkeypatch.setenv("JSPSR_LOSS_TILE_H", tile_h)
+    rng = np.random.default_rng(H * 7 + W)
+    gt = rng.random((B, C, H, W)).astype(np.float32)
+    pred = (gt + 0.05 * rng.normal(size=gt.shape)).astype(np.float32)
+    if W >= 128 and H >= 33:
+        pred[0, 0, :8, :2] = gt[0, 0, :8, :2]                   # exact zeros of d and of the Sobel difference (corner patch)
+    monkeypatch.setenv("JSPSR_LOSS_FUSED", "1")
+    lf, gf = EP.loss_l1_l2_grad(dev(pred), dev(gt))
+    monkeypatch.setenv("JSPSR_LOSS_FUSED", "0")
+    lp, gp = EP.loss_l1_l2_grad(dev(pred), dev(gt))
+    assert torch.equal(gf, gp)
+    assert torch.allclose(lf, lp, rtol=1e-6, atol=0)
+    monkeypatch.setenv("JSPSR_LOSS_FUSED", "1")
+    check_loss(jb, pred, gt)
