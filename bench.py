@@ -265,6 +265,10 @@ def run_ours(args, rank, world, local_rank):
     all_cpus = os.sched_getaffinity(0)
     cpus_bound = bind_to_gpu_cpus(torch, local_rank)
     if world > 1:
+        # The gradient all-reduce is a 40-byte NCCL kernel enqueued behind compute kernels whose grids keep every SM full:
+        # on a normal-priority stream it only gets a CTA slot when a compute grid drains, each rank at a different moment,
+        # and the stream wait two steps later can stall.  High-priority NCCL streams are dispatched ahead of queued CTAs.
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=device)
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     B = args.batch
@@ -293,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:                                  # DDP's job for these two parameters (40 bytes): asynchronous on
             flat = torch.cat([pp.w.grad.reshape(-1), pp.b.grad.reshape(-1)])   # NCCL's stream, like a DDP bucket,
             pending.append((dist.all_reduce(flat, async_op=True), flat))       # so the next step's kernels are not held up
-            while len(pending) > 2:
+            while len(pending) > 4:
                 pending.pop(0)[0].wait()
         return out
 
