@@ -161,3 +161,30 @@ def test_multiloss_mirror_keeps_the_reference_contract():
         crit(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         jb.MeterRMSE("local", border=0.05).update(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
+
+
+def test_oracle_crop_then_merge_reproduces_the_raster_on_random_geometries():
+    """Property of the pair of oracles (and of the reference's pair of functions they restate): tiles cut by TileCrop's
+    walk, blended back by merge_dem's ramps, give the raster back inside the border crop - for every geometry get_tile
+    accepts, with and without the mirrored border."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 12:
+        k = int(rng.integers(8, 40))
+        n_x = int(rng.integers(2, 5))
+        stride = int(rng.integers(k // 2 + 1, k + 1))                 # tiles touch and at most two overlap
+        w = stride * (n_x - 1) + k
+        if (w - w % k) // k + 1 != n_x:                               # get_tile derives n_x from (w, k): keep consistent walks
+            continue
+        pad = int(rng.integers(0, 3)) * 2
+        size = w - 2 * pad
+        if size <= pad + 1:
+            continue
+        img = rng.random((size, size, 1), dtype=np.float32)
+        tiles = T.crop_tiles(img, k, None, pad=pad)                   # [n, 1, k, k]
+        assert tiles.shape == (n_x * n_x, 1, k, k)
+        merged = T.merge_tiles(tiles[:, 0], 0.0, w)                   # border 0: the merged raster is the padded image
+        padded = T.add_padding(img, pad) if pad else img
+        assert merged.shape == (w, w)
+        assert np.abs(merged - padded[:, :, 0].astype(np.float64)).max() < 1e-6
+        done += 1
