@@ -10,7 +10,12 @@ detached exactly as models/JSPSR.py:372 does) on configs/jspsr_r8_img.yml's laye
 The per-GPU batch is 4096 tiles (67 Mpix, 7.8 GB of inputs - far larger than the 126 MB L2, so nothing is
 cache-resident between steps); the YAML batch of 70 tiles is launch-latency bound and is
 reported separately in `config_batch`.  Multi-GPU: one process per GPU, the batch is sharded (weak scaling), the only
-cross-rank state of the path - grad_w[9] and grad_b[1] - is all-reduced over NCCL inside the step.
+cross-rank state of the path - grad_w[9] and grad_b[1] - is all-reduced INSIDE the backward kernel over peer memory
+(NVLink stores + flags, include/jspsr_peer.h): no NCCL kernel, no extra launch and no stream wait in the step.
+Every run also carries `ddp_parity` (N > 1: sharded gradients through that path against the single-process gradients
+of the concatenated batch, checked before timing) and `strips` (BASELINE config 5: row-strip inference of a raster of
+4096 x 32768 pixels per GPU, T = 1 and T = 6, halo exchange fused into the kernel, bit-compared with the unsharded
+result first).
 
 `--impl reference` times the reference's CPU implementation of the same step on the host cores: the restated call
 sites of spn.py:99-118 on torchvision's own CPU operator (oracle/ref_port.py) - literally what the reference executes
@@ -52,6 +57,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-strips", action="store_true")
+    ap.add_argument("--strip-rows", type=int, default=4096, help="rows of the 32768-wide raster per GPU (config 5)")
     return ap.parse_args()
 
 
@@ -60,7 +67,7 @@ def workload_config(args, n):
         "workload": f"configs/jspsr_r8_img.yml PostProcessor(3x3, residual) training step fwd+bwd, "
                     f"{args.batch} tiles of {TILE}x{TILE} per GPU, T=1, DEM detached",
         "tiles_per_gpu": args.batch, "tile": [TILE, TILE], "global_tiles": args.batch * n,
-        "parallelism": f"dp{n} (batch-sharded tiles, NCCL all-reduce of grad_w/grad_b)",
+        "parallelism": f"dp{n} (batch-sharded tiles; grad_w/grad_b all-reduced inside the backward kernel over peer memory)",
         "l2": "inputs (7.8 GB/GPU) exceed the 126 MB L2; no flush needed",
         "offsets": "N(0,1.5^2) clipped to +-8, centre pair zero (SURVEY.md section 8d)",
     }
@@ -264,24 +271,25 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     all_cpus = os.sched_getaffinity(0)
     cpus_bound = bind_to_gpu_cpus(torch, local_rank)
+    reducer = None
+    ddp_parity = None
     if world > 1:
-        # The gradient all-reduce is a 40-byte NCCL kernel enqueued behind compute kernels whose grids keep every SM full:
-        # on a normal-priority stream it only gets a CTA slot when a compute grid drains, each rank at a different moment,
-        # and the stream wait two steps later can stall.  High-priority NCCL streams are dispatched ahead of queued CTAs.
-        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+        # NCCL is plumbing only (barriers, gathering results, carrying the 64-byte IPC handles): the data path's one
+        # exchange - 80 bytes of gradient sums per step - happens inside spn_backward_kernel over peer memory.
         dist.init_process_group("nccl", device_id=device)
+        from jspsr_b200.peer import PeerGradReducer
+        reducer = PeerGradReducer(average=True)
+        ddp_parity = ddp_gradient_parity(torch, dist, jspsr_b200, reducer, device, rank, world)
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     B = args.batch
     init, weight, offset, gout, w, b = make_inputs(torch, B, device, dtype, 1234 + rank)
-    pp = jspsr_b200.PostProcessor(3, True, 1.0).to(device)
+    pp = jspsr_b200.PostProcessor(3, True, 1.0).to(device).set_grad_reducer(reducer)
     with torch.no_grad():
         pp.w.copy_(w)
         pp.b.copy_(b)
     weight.requires_grad_(True)
     offset.requires_grad_(True)
     npix = B * TILE * TILE
-
-    pending = []
 
     def step(ev=None):
         weight.grad = offset.grad = None
@@ -291,25 +299,19 @@ def run_ours(args, rank, world, local_rank):
         out = pp(init, weight, offset)                 # 1 kernel
         if ev:
             ev[1].record()
-        out.backward(gout)                             # 1 kernel
-        if ev:
-            ev[2].record()
-        if world > 1:                                  # DDP's job for these two parameters (40 bytes): asynchronous on
-            flat = torch.cat([pp.w.grad.reshape(-1), pp.b.grad.reshape(-1)])   # NCCL's stream, like a DDP bucket,
-            pending.append((dist.all_reduce(flat, async_op=True), flat))       # so the next step's kernels are not held up
-            while len(pending) > 4:
-                pending.pop(0)[0].wait()
+        out.backward(gout)                             # 1 kernel; N > 1: its last CTA all-reduces grad_w / grad_b with
+        if ev:                                         # the other ranks' last CTAs (DDP's job for these two parameters),
+            ev[2].record()                             # so pp.w.grad / pp.b.grad are the world's averages when it ends
         return out
 
     def barrier():
-        while pending:
-            pending.pop(0)[0].wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    out_keep = None
     for _ in range(max(args.warmup, 3)):
-        step()
+        out_keep = step()
     barrier()
     launches0 = F.launch_count()
     sampler = ClockSampler(local_rank)
@@ -319,8 +321,6 @@ def run_ours(args, rank, world, local_rank):
     t_start.record()
     for i in range(args.steps):
         step(evs[i])
-    while pending:                       # the timed region ends when the last gradient all-reduce has landed
-        pending.pop(0)[0].wait()
     t_end.record()
     barrier()
     clocks = sampler.stop()
@@ -328,10 +328,18 @@ def run_ours(args, rank, world, local_rank):
     ms = t_start.elapsed_time(t_end) / args.steps
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    # per-step device times (start of step i -> start of step i + 1): a single hiccup and a steady gap look different
+    marks = [e[0] for e in evs] + [t_end]
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+    step_stats = {"p50_ms": statistics.median(per_step), "max_ms": max(per_step), "min_ms": min(per_step)}
     if world > 1:
         t = torch.tensor([ms, fwd_ms, bwd_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, fwd_ms, bwd_ms = t.tolist()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, step_stats)
+        step_stats = {"per_rank": gathered, "p50_ms": max(g["p50_ms"] for g in gathered),
+                      "max_ms": max(g["max_ms"] for g in gathered)}
     value = world * npix / (ms * 1e-3) / 1e9
 
     peak, peak_src = peak_hbm()
@@ -391,9 +399,7 @@ def run_ours(args, rank, world, local_rank):
                     s_out.wait_event(done)
                     out.record_stream(s_out)
                     out_h[i * cb_:(i + 1) * cb_].copy_(out.detach(), non_blocking=True)
-            flat = torch.cat([pp.w.grad.reshape(-1), pp.b.grad.reshape(-1)])
-            if world > 1:
-                dist.all_reduce(flat)
+            flat = torch.cat([pp.w.grad.reshape(-1), pp.b.grad.reshape(-1)])   # N > 1: already all-reduced by the kernels
             gw_h.copy_(flat, non_blocking=True)
             cur.wait_stream(s_out)
 
@@ -410,20 +416,50 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([e_ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = t.item()
+        # what the host can deliver: a plain pinned cudaMemcpyAsync of 1 GiB per rank, all ranks at once (PCIe / NUMA
+        # ceiling of this box at this N) - the e2e step is bound by it, not by the kernels
+        probe_src = host[2].view(-1)[: (1 << 30) // host[2].element_size()]
+        probe_dst = torch.empty_like(probe_src, device=device)
+        probe_dst.copy_(probe_src, non_blocking=True)
+        barrier()
+        e0.record()
+        for _ in range(3):
+            probe_dst.copy_(probe_src, non_blocking=True)
+        e1.record()
+        barrier()
+        probe_gbs = 3 * probe_src.numel() * probe_src.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        h2d_gbs = h2d / (e_ms * 1e-3) / 1e9
+        per_rank = [{"rank": rank, "h2d_probe_gbs": probe_gbs, "cpus_bound": cpus_bound}]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, per_rank[0])
+            per_rank = gathered
+            probe_gbs = min(g["h2d_probe_gbs"] for g in gathered)
+        del probe_dst
         e2e = {"value": world * npix / (e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e_ms,
                "host_cpus_bound": cpus_bound,
+               "h2d_gbs_per_rank": h2d_gbs, "h2d_probe_gbs_per_rank_min": probe_gbs,
+               "frac_of_h2d_probe": h2d_gbs / probe_gbs, "per_rank": per_rank,
                "api": "jspsr_b200.PostProcessor.forward + backward on tensors copied from pinned host memory, "
                       f"{n_chunks} chunks (H2D / compute / D2H overlapped)"}
         del host, out_h
 
     extras = {}
+    del init, gout, out_keep
+    weight.grad = offset.grad = None
+    del weight, offset
+    torch.cuda.empty_cache()
+    if not args.no_strips:
+        # BASELINE config 5 (every rank takes part: the exchange is between neighbouring ranks' kernels)
+        extras["strips"] = strip_inference(torch, dist, F, device, rank, world, args)
+        torch.cuda.empty_cache()
+    if ddp_parity is not None:
+        extras["ddp_parity"] = ddp_parity
+    extras["step_times"] = step_stats
     if not args.no_extras and rank == 0:
-        extras = config_batch_latency(torch, jspsr_b200, F, device, dtype)
+        extras.update(config_batch_latency(torch, jspsr_b200, F, device, dtype))
         if world == 1:
-            del init, gout
-            weight.grad = offset.grad = None
-            torch.cuda.empty_cache()
             extras["variants"] = side_numbers(torch, F, device, min(B, 2048))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -439,7 +475,153 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        reducer.close()
         dist.destroy_process_group()
+
+
+def ddp_gradient_parity(torch, dist, jspsr_b200, reducer, device, rank, world):
+    """DistributedDataParallel semantics on hardware, through the fused all-reduce: every rank runs PostProcessor
+    forward + backward on its shard of a seeded batch (local mean loss, gradients of w / b averaged over the ranks inside
+    the backward kernel) and compares with the single-process gradients of the concatenated batch (global mean loss),
+    which every rank computes for itself.  Also checks that the reduced gradients are bit-identical on all ranks."""
+    per, H, W = 6, 64, 128
+    g = torch.Generator(device="cpu").manual_seed(20261018)
+    n = per * world
+    dem = torch.rand(n, 1, H, W, generator=g).to(device)
+    weight = torch.sigmoid(1.5 * torch.randn(n, 9, H, W, generator=g)).to(device)
+    offset = (1.5 * torch.randn(n, 18, H, W, generator=g)).to(device)
+    gt = torch.rand(n, 1, H, W, generator=g).to(device)
+    w0 = (1 + 0.2 * (torch.rand(1, 1, 3, 3, generator=g) - 0.5)).to(device)
+
+    def run(sl, red):
+        pp = jspsr_b200.PostProcessor(3, True, 1.0).to(device).set_grad_reducer(red)
+        with torch.no_grad():
+            pp.w.copy_(w0)
+            pp.b.fill_(0.1)
+        wt, of = weight[sl].clone().requires_grad_(), offset[sl].clone().requires_grad_()
+        (pp(dem[sl], wt, of) - gt[sl]).square().mean().backward()
+        return pp.w.grad.reshape(-1), pp.b.grad.reshape(-1), wt.grad, of.grad
+
+    sl = slice(rank * per, (rank + 1) * per)
+    gw, gb, gwt, gof = run(sl, reducer)                 # sharded, reduced inside the kernel
+    rw, rb, rwt, rof = run(slice(0, n), None)           # single process, whole batch
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    flat = torch.cat([gw, gb])
+    allg = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(allg, flat)
+    res = torch.tensor([rel(gw, rw), rel(gb, rb), rel(gwt / world, rwt[sl]), rel(gof / world, rof[sl])],
+                       device=device, dtype=torch.float64)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    r = res.tolist()
+    return {"max_rel": max(r), "grad_w_rel": r[0], "grad_b_rel": r[1], "grad_weight_rel": r[2], "grad_offset_rel": r[3],
+            "bit_identical_across_ranks": all(torch.equal(a, flat) for a in allg), "tolerance": 2e-5,
+            "ok": max(r) <= 2e-5, "tiles_per_rank": per, "tile": [H, W],
+            "what": "PostProcessor fwd+bwd on rank shards (local mean loss), grad_w/grad_b averaged over ranks inside "
+                    "spn_backward_kernel (peer memory), vs single-process gradients of the concatenated batch"}
+
+
+def strip_rows(torch, device, r0, r1, W, seed, clip=6.0):
+    """Rows [r0, r1) of a seeded synthetic raster (DEM, affinities, offsets): generated in 256-row blocks keyed by the
+    global block index, so every sharding of the raster sees the same values."""
+    blk = 256
+    parts = ([], [], [])
+    g = torch.Generator(device=device)
+    for bi in range(r0 // blk, (r1 + blk - 1) // blk):
+        g.manual_seed(seed * 100003 + bi)
+        init = torch.rand(1, 1, blk, W, device=device, generator=g)
+        aff = torch.sigmoid(1.5 * torch.randn(1, 9, blk, W, device=device, generator=g))
+        off = (1.5 * torch.randn(1, 18, blk, W, device=device, generator=g)).clamp_(-clip, clip)
+        off[:, 8:10] = 0
+        lo, hi = max(r0, bi * blk) - bi * blk, min(r1, (bi + 1) * blk) - bi * blk
+        for dst, t in zip(parts, (init, aff, off)):
+            dst.append(t[:, :, lo:hi])
+    return tuple(torch.cat(pr, dim=2).contiguous() for pr in parts)
+
+
+def strip_inference(torch, dist, F, device, rank, world, args):
+    """BASELINE config 5: a raster of (4096 * N) x 32768 pixels sharded into row strips, one per GPU (weak scaling: 4096 rows
+    per rank).  T = 1 is JSPSR's single application, T = 6 the fixed-affinity loop; the halo exchange runs inside the
+    propagation kernel (peer stores + flags, jspsr_b200/strips.py).  Before timing, a small raster is bit-compared with
+    the unsharded single-GPU result on every rank."""
+    from jspsr_b200.strips import StripPropagator, strip_bounds
+    peak, _ = peak_hbm()
+    w = torch.full((1, 1, 3, 3), 1.05, device=device)
+    b = torch.full((1,), 0.1, device=device)
+    halo = 8   # offsets are clipped to +-6 rows: ceil(6) + 2
+
+    # ---- bit identity with the unsharded call (T = 1 and T = 3, all intermediates) ----
+    Hs, Ws = 256 * world + 64, 512
+    full = strip_rows(torch, device, 0, Hs, Ws, 7)
+    ref1 = F.spn_forward(full[0], full[1], full[2], w, b, 1, 1.0)
+    ref3 = F.spn_iterate(full[0], full[1] * 0.1, full[2], 3)
+    r0, r1, _, _ = strip_bounds(Hs, world, rank, 0)
+    band = [t[:, :, r0:r1].contiguous() for t in full]
+    sp = StripPropagator(Hs, rank, world)
+    ring = sp.peer_ring(r1 - r0, Ws, halo, n_buf=4)
+    ring.load(band[0])
+    out1, st = sp.forward_peer(ring, band[1], band[2], w, b, 1, 1.0)
+    ok = torch.equal(out1, ref1[:, :, r0:r1])
+    feats, st = sp.iterate_peer(ring, band[1] * 0.1, band[2], 3, keep_all=True)
+    ok = ok and all(torch.equal(f, ref3[t][:, :, r0:r1]) for t, f in enumerate(feats))
+    feats, st = sp.iterate_peer(ring, band[1] * 0.1, band[2], 2)       # continues from the ring's current band
+    ref5 = F.spn_iterate(ref3[2], full[1] * 0.1, full[2], 2)
+    ok = ok and torch.equal(feats[-1], ref5[1][:, :, r0:r1]) and int(st.item()) == 0
+    flag = torch.tensor([1 if ok else 0], device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    bitwise_ok = bool(flag.item())
+    ring.close()
+    del full, ref1, ref3, ref5, band, feats, out1, ring
+
+    # ---- timing: 4096 x 32768 pixels per rank ----
+    rows, W = args.strip_rows, 32768
+    H_img = rows * world
+    r0, r1 = rank * rows, (rank + 1) * rows
+    init, aff, off = strip_rows(torch, device, r0, r1, W, 11)
+    sp = StripPropagator(H_img, rank, world)
+    ring = sp.peer_ring(rows, W, halo, n_buf=2)
+    ring.load(init)
+    del init
+    out = torch.empty(1, 1, rows, W, device=device)
+    res = {"raster": [H_img, W], "rows_per_gpu": rows, "halo_rows": halo, "bitwise_ok": bitwise_ok,
+           "exchange": "none (one strip)" if world == 1 else
+                       "fused into spn_forward_kernel: edge CTAs store their rows into the neighbours' next buffer over "
+                       "NVLink and raise a flag; only the next application's edge CTAs wait for it",
+           "halo_bytes_per_exchange_per_rank": 2 * halo * W * 4}
+
+    def run(T, n):
+        def one():
+            if T == 1:
+                sp.forward_peer(ring, aff, off, w, b, 1, 1.0, out=out)
+            else:
+                sp.iterate_peer(ring, aff, off, T)
+        for _ in range(2):
+            one()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        return {"ms": ms, "gpix": H_img * W * T / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak_per_gpu": 116 * rows * W * T / (ms * 1e-3) / 1e9 / peak, "bitwise_ok": bitwise_ok}
+
+    res["T1"] = run(1, 10)
+    res["T6"] = run(6, 4)
+    res["T6_over_6xT1"] = res["T6"]["ms"] / (6 * res["T1"]["ms"])
+    res["status"] = int(ring.status.item())
+    ring.close()
+    return res
 
 
 def side_numbers(torch, F, device, B):

@@ -1,4 +1,4 @@
-"""ctypes binding of libjspsr_spn.so (the C ABI in include/jspsr_spn.h and include/jspsr_tiles.h).
+"""ctypes binding of libjspsr_spn.so (the C ABI in include/jspsr_spn.h, include/jspsr_tiles.h and include/jspsr_peer.h).
 
 There is no fallback: if the library is missing or a call fails, a RuntimeError
 is raised with the library's own message.
@@ -40,6 +40,15 @@ _SIGNATURES = {
     "jspsr_loss_l1_l2_grad": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p]),
     "jspsr_dem_metrics": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float, c_float, c_int, c_void_p]),
+    # include/jspsr_peer.h
+    "jspsr_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "jspsr_peer_open": (c_int, [c_void_p, c_void_p]),
+    "jspsr_peer_close": (c_int, [c_void_p]),
+    "jspsr_peer_free": (c_int, [c_void_p]),
+    "jspsr_spn_backward_reduce": (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_float, c_int, c_uint, c_void_p,
+                                          c_void_p]),
+    "jspsr_spn_forward_strip_peer": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "jspsr_strip_halo_push": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "jspsr_spn_forward_host": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_int]),
 }
 
@@ -68,7 +77,8 @@ def build_ext(verbose: bool = False) -> str:
     import torch
     from torch.utils import cpp_extension
     deps = [_EXT_SRC, LIB_PATH, os.path.join(_CSRC, "..", "..", "include", "jspsr_spn.h"),
-            os.path.join(_CSRC, "..", "..", "include", "jspsr_tiles.h"), torch.__file__]
+            os.path.join(_CSRC, "..", "..", "include", "jspsr_tiles.h"),
+            os.path.join(_CSRC, "..", "..", "include", "jspsr_peer.h"), torch.__file__]
     if os.path.exists(EXT_PATH) and all(os.path.getmtime(EXT_PATH) >= os.path.getmtime(d) for d in deps):
         return EXT_PATH
     tlib = os.path.join(os.path.dirname(torch.__file__), "lib")

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../include/jspsr_spn.h"
+#include "../../include/jspsr_peer.h"
 #include "spn_types.cuh"
 
 using namespace jspsr;
@@ -13,6 +14,7 @@ using namespace jspsr;
 namespace jspsr {
 cudaError_t launch_offset_absmax(const void* offset, size_t n_pairs_block, size_t cs, int B, bool bf16, float* out2,
                                  cudaStream_t stream);
+cudaError_t launch_halo_push(const void* band, int Hs, int W, bool bf16, const StripPeerDev& sp, cudaStream_t stream);
 cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const float* mask_fix, void* dst, size_t n,
                                   bool bf16, cudaStream_t stream);
 // The tile kernels exist twice (spn_common.cuh): `wide` stages a 14/15-row, 16-column halo, `narrow` 6/7 rows and
@@ -174,9 +176,26 @@ int jspsr_version(void) { return JSPSR_SPN_VERSION; }
 const char* jspsr_last_error(void) { return g_err; }
 size_t jspsr_spn_workspace_bytes(void) { return sizeof(ReduceWs); }
 
-int jspsr_spn_forward_strip(const void* init, const void* weight, const void* offset, const float* w9, const float* b1,
+// host struct (include/jspsr_peer.h) -> the kernel's view; validates the neighbour topology
+static int strip_peer_dev(const jspsr_strip_peer* sp, int Hs, StripPeerDev* d) {
+    if (!sp->my_flags) return fail(JSPSR_ERR_BAD_ARG, "jspsr_strip_peer: my_flags is null");
+    if (sp->halo <= 0 || sp->halo > Hs)
+        return fail(JSPSR_ERR_BAD_ARG, "jspsr_strip_peer: halo %d must be in [1, Hs = %d] (use fewer ranks)", sp->halo, Hs);
+    if ((sp->up_dst && !sp->up_flags) || (sp->dn_dst && !sp->dn_flags))
+        return fail(JSPSR_ERR_BAD_ARG, "jspsr_strip_peer: a destination without its neighbour's flag block");
+    d->up_dst = sp->up_dst; d->dn_dst = sp->dn_dst;
+    d->up_flag = sp->up_flags ? sp->up_flags + 1 : nullptr;   // I am the upper neighbour's LOWER neighbour
+    d->dn_flag = sp->dn_flags ? sp->dn_flags + 0 : nullptr;   // and the lower neighbour's UPPER one
+    d->wait_up = sp->up_flags ? sp->my_flags + 0 : nullptr;
+    d->wait_dn = sp->dn_flags ? sp->my_flags + 1 : nullptr;
+    d->tickets = sp->my_flags + 2;
+    d->stamp = sp->stamp; d->halo = sp->halo;
+    return 0;
+}
+
+static int spn_forward_strip_impl(const void* init, const void* weight, const void* offset, const float* w9, const float* b1,
                             void* out, int B, int Hs, int W, int H_img, int row0, int init_row0, int init_rows,
-                            int norm_mode, float scale, int dtype, int* status, void* stream) {
+                            int norm_mode, float scale, int dtype, int* status, const jspsr_strip_peer* sp, void* stream) {
     if (int e = check_common(B, Hs, W, norm_mode, dtype)) return e;
     if (!init || !weight || !offset || !out) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
     if (H_img < Hs || row0 < 0 || row0 + Hs > H_img || init_row0 < 0 || init_rows <= 0 || init_row0 + init_rows > H_img ||
@@ -193,6 +212,15 @@ int jspsr_spn_forward_strip(const void* init, const void* weight, const void* of
     if (int e = check_align(b1, 4, "b1")) return e;
     LaunchArgs la;
     if (int e = fill_geom(&la, B, Hs, W, H_img, row0, init_row0, init_rows, 16)) return e;
+    StripPeerDev spd;
+    if (sp != nullptr) {  // fused halo exchange: rasters (B = 1), instantiated for 16 rows per CTA
+        if (B != 1 || dtype == JSPSR_MIXED)
+            return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_spn_forward_strip_peer: B = 1 and dtype f32 / bf16 only");
+        if (int e = strip_peer_dev(sp, Hs, &spd)) return e;
+        la.tile_h = 16;
+        la.g.tiles_y = (Hs + 15) / 16;
+        la.strip_peer = &spd;
+    }
     la.init = init; la.weight = weight; la.offset = offset; la.w9 = w9; la.b1 = b1; la.out = out;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
     la.status = status;
@@ -201,6 +229,81 @@ int jspsr_spn_forward_strip(const void* init, const void* weight, const void* of
     la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, dtype == JSPSR_BF16, la.tile_h, wide);
     cudaError_t ce = wide ? wide::launch_spn_forward(la) : narrow::launch_spn_forward(la);
     if (ce != cudaSuccess) return cuda_fail(ce, "spn_forward launch");
+    return JSPSR_OK;
+}
+
+int jspsr_spn_forward_strip(const void* init, const void* weight, const void* offset, const float* w9, const float* b1,
+                            void* out, int B, int Hs, int W, int H_img, int row0, int init_row0, int init_rows,
+                            int norm_mode, float scale, int dtype, int* status, void* stream) {
+    return spn_forward_strip_impl(init, weight, offset, w9, b1, out, B, Hs, W, H_img, row0, init_row0, init_rows, norm_mode,
+                                  scale, dtype, status, nullptr, stream);
+}
+
+int jspsr_spn_forward_strip_peer(const void* init, const void* weight, const void* offset, const float* w9, const float* b1,
+                                 void* out, int Hs, int W, int H_img, int row0, int init_row0, int init_rows, int norm_mode,
+                                 float scale, int dtype, int* status, const jspsr_strip_peer* sp, void* stream) {
+    if (!sp) return fail(JSPSR_ERR_BAD_ARG, "jspsr_spn_forward_strip_peer: sp is null (use jspsr_spn_forward_strip)");
+    return spn_forward_strip_impl(init, weight, offset, w9, b1, out, 1, Hs, W, H_img, row0, init_row0, init_rows, norm_mode,
+                                  scale, dtype, status, sp, stream);
+}
+
+int jspsr_strip_halo_push(const void* band, int Hs, int W, int dtype, const jspsr_strip_peer* sp, void* stream) {
+    if (!band || !sp) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
+    if (Hs <= 0 || W <= 0) return fail(JSPSR_ERR_BAD_ARG, "non-positive dimension Hs=%d W=%d", Hs, W);
+    if (dtype != JSPSR_F32 && dtype != JSPSR_BF16) return fail(JSPSR_ERR_BAD_ARG, "dtype %d is not 0 (f32) / 1 (bf16)", dtype);
+    StripPeerDev spd;
+    if (int e = strip_peer_dev(sp, Hs, &spd)) return e;
+    if ((sp->up_flags && !sp->up_dst) || (sp->dn_flags && !sp->dn_dst))
+        return fail(JSPSR_ERR_BAD_ARG, "jspsr_strip_halo_push needs a destination for every neighbour");
+    if (!sp->up_flags && !sp->dn_flags) return JSPSR_OK;  // a single strip has nobody to push to
+    cudaError_t ce = launch_halo_push(band, Hs, W, dtype == JSPSR_BF16, spd, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "halo push launch");
+    return JSPSR_OK;
+}
+
+// ---- peer-mapped device memory (CUDA IPC) ----
+static_assert(sizeof(cudaIpcMemHandle_t) == JSPSR_PEER_HANDLE_BYTES, "handle size");
+
+int jspsr_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out) {
+    if (!dev_ptr || !handle_out || bytes == 0) return fail(JSPSR_ERR_BAD_ARG, "jspsr_peer_alloc: bad argument");
+    void* p = nullptr;
+    cudaError_t ce = cudaMalloc(&p, bytes);
+    if (ce != cudaSuccess) return cuda_fail(ce, "jspsr_peer_alloc: cudaMalloc");
+    ce = cudaMemset(p, 0, bytes);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (ce == cudaSuccess) ce = cudaIpcGetMemHandle(&h, p);
+    if (ce != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(ce, "jspsr_peer_alloc: memset / cudaIpcGetMemHandle");
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return JSPSR_OK;
+}
+
+int jspsr_peer_open(const void* handle, void** dev_ptr) {
+    if (!handle || !dev_ptr) return fail(JSPSR_ERR_BAD_ARG, "jspsr_peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess) return cuda_fail(ce, "jspsr_peer_open: cudaIpcOpenMemHandle (is peer access between the GPUs available?)");
+    *dev_ptr = p;
+    return JSPSR_OK;
+}
+
+int jspsr_peer_close(void* dev_ptr) {
+    if (!dev_ptr) return JSPSR_OK;
+    cudaError_t ce = cudaIpcCloseMemHandle(dev_ptr);
+    if (ce != cudaSuccess) return cuda_fail(ce, "jspsr_peer_close");
+    return JSPSR_OK;
+}
+
+int jspsr_peer_free(void* dev_ptr) {
+    if (!dev_ptr) return JSPSR_OK;
+    cudaError_t ce = cudaFree(dev_ptr);
+    if (ce != cudaSuccess) return cuda_fail(ce, "jspsr_peer_free");
     return JSPSR_OK;
 }
 
@@ -215,7 +318,29 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
                        float* grad_init, void* grad_weight, void* grad_offset, float* grad_w9, float* grad_b1,
                        void* workspace, int B, int H, int W, int norm_mode, float scale, int dtype, unsigned flags,
                        void* stream) {
+    return jspsr_spn_backward_reduce(grad_out, init, weight, offset, w9, grad_init, grad_weight, grad_offset, grad_w9, grad_b1,
+                                     workspace, B, H, W, norm_mode, scale, dtype, flags, nullptr, stream);
+}
+
+int jspsr_spn_backward_reduce(const void* grad_out, const void* init, const void* weight, const void* offset,
+                              const float* w9, float* grad_init, void* grad_weight, void* grad_offset, float* grad_w9,
+                              float* grad_b1, void* workspace, int B, int H, int W, int norm_mode, float scale, int dtype,
+                              unsigned flags, const jspsr_peer_reduce* pr, void* stream) {
     if (int e = check_common(B, H, W, norm_mode, dtype)) return e;
+    PeerReduceDev prd;
+    if (pr != nullptr && pr->world > 1) {
+        if (pr->world > JSPSR_PEER_MAX_RANKS || pr->rank < 0 || pr->rank >= pr->world)
+            return fail(JSPSR_ERR_BAD_ARG, "jspsr_peer_reduce: rank %d / world %d (at most %d ranks)", pr->rank, pr->world,
+                        JSPSR_PEER_MAX_RANKS);
+        if (!grad_w9) return fail(JSPSR_ERR_BAD_ARG, "jspsr_spn_backward_reduce: nothing to reduce without grad_w9");
+        for (int r = 0; r < pr->world; ++r) {
+            if (!pr->slots[r] || ((uintptr_t)pr->slots[r] & 15) != 0)
+                return fail(JSPSR_ERR_BAD_ARG, "jspsr_peer_reduce: slots[%d] is null or unaligned", r);
+            prd.slots[r] = static_cast<double*>(pr->slots[r]);
+        }
+        prd.rank = pr->rank; prd.world = pr->world;
+        prd.mul = pr->average ? 1.f / (float)pr->world : 1.f;
+    }
     const bool preact = (flags & JSPSR_BWD_GEN_PREACT) != 0;
     if (!grad_out || !init || !weight || !offset || !grad_weight || (!grad_offset && !preact))
         return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
@@ -243,6 +368,7 @@ int jspsr_spn_backward(const void* grad_out, const void* init, const void* weigh
     la.grad_w9 = grad_w9; la.grad_b1 = grad_b1; la.workspace = workspace;
     la.accumulate = (flags & JSPSR_BWD_ACCUMULATE) != 0;
     la.gen_preact = preact;
+    if (prd.world > 1) la.peer_reduce = &prd;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
     la.stream = (cudaStream_t)stream;
     const bool wide = choose_wide(W);

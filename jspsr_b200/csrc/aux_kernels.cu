@@ -57,6 +57,42 @@ cudaError_t launch_offset_absmax(const void* offset, size_t, size_t cs, int B, b
     return cudaGetLastError();
 }
 
+// First generation of a row-strip sequence (include/jspsr_peer.h, jspsr_strip_halo_push): copy the band's own first /
+// last `halo` rows into the neighbours' halo rows and raise their flags to `stamp`.  Thread 0 of every CTA first waits
+// for this rank's flags >= stamp - 1: the neighbours have finished reading the buffer that is being overwritten.
+template <typename T>
+__global__ void __launch_bounds__(256) halo_push_kernel(const T* __restrict__ band, int Hs, int W, const StripPeerDev sp) {
+    if (threadIdx.x == 0) {
+        if (sp.wait_up) wait_stamp(sp.wait_up, sp.stamp - 1u);
+        if (sp.wait_dn) wait_stamp(sp.wait_dn, sp.stamp - 1u);
+    }
+    __syncthreads();
+    const size_t n = (size_t)sp.halo * W;  // elements per direction
+    T* up = static_cast<T*>(sp.up_dst);
+    T* dn = static_cast<T*>(sp.dn_dst);
+    const T* last = band + (size_t)(Hs - sp.halo) * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (up) up[i] = band[i];
+        if (dn) dn[i] = last[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(sp.tickets, 1u) == gridDim.x - 1) {
+        sp.tickets[0] = 0u;
+        __threadfence_system();
+        if (sp.up_flag) st_release_sys(sp.up_flag, sp.stamp);
+        if (sp.dn_flag) st_release_sys(sp.dn_flag, sp.stamp);
+    }
+}
+
+cudaError_t launch_halo_push(const void* band, int Hs, int W, bool bf16, const StripPeerDev& sp, cudaStream_t stream) {
+    const size_t n = (size_t)sp.halo * W;
+    const int blocks = (int)min((size_t)148, (n + 255) / 256);
+    if (bf16) halo_push_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)band, Hs, W, sp);
+    else halo_push_kernel<float><<<blocks, 256, 0, stream>>>((const float*)band, Hs, W, sp);
+    return cudaGetLastError();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) preserve_blend_kernel(const T* __restrict__ feat, const T* __restrict__ fix,
                                                              const float* __restrict__ mask, T* __restrict__ dst,

@@ -45,7 +45,8 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
                     const T* __restrict__ offset, const float* __restrict__ w9, float* __restrict__ grad_init,
                     T* __restrict__ grad_weight, T* __restrict__ grad_offset, float* __restrict__ grad_w9,
                     float* __restrict__ grad_b1, ReduceWs* __restrict__ ws, const Geom g, const int mode,
-                    const float scale, const __grid_constant__ CUtensorMap tmap) {
+                    const float scale, const __grid_constant__ CUtensorMap tmap,
+                    const __grid_constant__ PeerReduceDev pr) {
     constexpr int SH = staged_rows(TH);
     constexpr int PPT = pixels_per_thread(TH);
     __shared__ __align__(128) TI tile[SH * SW];
@@ -350,13 +351,56 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
         __syncthreads();
         if (s_last) {
             __threadfence();
+            __shared__ double s_sum[10];
             if (threadIdx.x < 10) {
-                const double v = atomicAdd(&ws->sums[threadIdx.x], 0.0);  // coherent read
-                if (threadIdx.x < 9) grad_w9[threadIdx.x] = (float)v;
-                else if (grad_b1 != nullptr) grad_b1[0] = (float)v;
+                s_sum[threadIdx.x] = atomicAdd(&ws->sums[threadIdx.x], 0.0);  // coherent read
                 ws->sums[threadIdx.x] = 0.0;  // leave the workspace clean for the next call
             }
             if (threadIdx.x == 0) ws->ticket = 0u;
+            if (pr.world > 1) {
+                // All-reduce over the ranks, fused here (include/jspsr_peer.h): thread p stores this rank's ten fp64 sums
+                // into its slot of rank p's buffer (peer memory over NVLink) and releases the step stamp behind them, then
+                // waits for rank p's stamp in the local buffer.  Every rank adds the world's slots in rank order, so the
+                // result is bit-identical everywhere.  Slots alternate with the stamp's parity: a rank can be at most one
+                // step ahead of the slowest reader (it cannot finish step s + 1 before everyone has published step s + 1,
+                // which they do after reading step s).
+                __shared__ double s_all[8][10];
+                __shared__ unsigned s_stamp;
+                double* mine = pr.slots[pr.rank];
+                if (threadIdx.x == 0) {
+                    unsigned* counter = reinterpret_cast<unsigned*>(mine + REDUCE_COUNTER_OFFSET);
+                    s_stamp = *counter + 1u;
+                    *counter = s_stamp;
+                }
+                __syncthreads();
+                const unsigned stamp = s_stamp;
+                const int par = (int)(stamp & 1u);
+                if ((int)threadIdx.x < pr.world) {
+                    const int peer = (int)threadIdx.x;
+                    double* dst = pr.slots[peer] + (size_t)(par * 8 + pr.rank) * REDUCE_SLOT;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) dst[k] = s_sum[k];
+                    __threadfence_system();
+                    st_release_sys(reinterpret_cast<unsigned*>(dst + REDUCE_SLOT - 1), stamp);
+                    const double* src = mine + (size_t)(par * 8 + peer) * REDUCE_SLOT;
+                    wait_stamp(reinterpret_cast<const unsigned*>(src + REDUCE_SLOT - 1), stamp);
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+                        double v;
+                        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src + k) : "memory");
+                        s_all[peer][k] = v;
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x < 10) {
+                    double v = 0.0;
+                    for (int r = 0; r < pr.world; ++r) v += s_all[r][threadIdx.x];
+                    s_sum[threadIdx.x] = v * (double)pr.mul;
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x < 9) grad_w9[threadIdx.x] = (float)s_sum[threadIdx.x];
+            else if (threadIdx.x == 9 && grad_b1 != nullptr) grad_b1[0] = (float)s_sum[9];
         }
     }
 }
@@ -367,7 +411,7 @@ static void launch_one(const LaunchArgs& la) {
     spn_backward_kernel<T, TI, TMA, GI, ACC, CS, TH, GZ><<<grid, THREADS, 0, la.stream>>>(
         (const TI*)la.grad_out, (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.grad_init,
         (T*)la.grad_weight, (T*)la.grad_offset, la.grad_w9, la.grad_b1, (ReduceWs*)la.workspace, la.g, la.mode,
-        la.scale, la.tmap);
+        la.scale, la.tmap, la.peer_reduce ? *la.peer_reduce : PeerReduceDev{});
 }
 
 // (TMA, CS) variants: the compile-time stride only exists for 128x128-pixel planes, which always qualify for TMA

@@ -176,6 +176,39 @@ __device__ __forceinline__ T* step_ptr(T* p, size_t bytes) {
     return reinterpret_cast<T*>(r);
 }
 
+// ---------------------------------------------------------------------------
+// System-scope flags in peer memory (another GPU's HBM mapped through CUDA IPC, reached over NVLink).
+// A producer makes its data stores visible with a system fence and then release-stores a generation stamp;
+// a consumer spins on an acquire load (with back-off) until the stamp has been reached.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// A peer that never arrives (a rank died, or the ranks' call sequences diverged) must not hang the GPU: after
+// PEER_WAIT_LIMIT_NS the kernel traps, which surfaces as a launch failure on the host (the fused counterpart of a
+// collective's watchdog timeout).
+constexpr unsigned long long PEER_WAIT_LIMIT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void wait_stamp(const unsigned* flag, unsigned stamp) {
+    if ((int)(ld_acquire_sys(flag) - stamp) >= 0) return;
+    const unsigned long long t0 = global_ns();
+    unsigned ns = 32;
+    while ((int)(ld_acquire_sys(flag) - stamp) < 0) {
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+        else if (global_ns() - t0 > PEER_WAIT_LIMIT_NS) __trap();
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -21,12 +21,17 @@ inline namespace JSPSR_VARIANT {
 // merge them (measured at W = 2004: 11.1 GB read from DRAM for 7.5 GB of data with the row mapping).
 // T: element type of weight / offset; TI: element type of init / out (TI = float with T = bf16 is what
 // torch.autocast produces: bf16 Generator outputs, fp32 DEM; torchvision's operator promotes to fp32 there).
-template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR>
+// PEER: row strip of a raster sharded over GPUs with the halo exchange fused in (include/jspsr_peer.h): the CTAs
+// whose rows lie within `halo` of a strip edge - the only ones whose taps can reach a neighbour's rows - wait for
+// that neighbour's flag before they stage their DEM tile, store their edge rows a second time into the neighbour's
+// next DEM buffer (peer memory over NVLink), and the last of them to finish raises the neighbour's flag.  All other
+// CTAs run exactly the non-PEER code, so the bulk of the band is computed while the boundary rows travel.
+template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, FWD_MIN_BLOCKS)
 spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, const T* __restrict__ offset,
                    const float* __restrict__ w9, const float* __restrict__ b1, TI* __restrict__ out, const Geom g,
                    const int mode, const float scale, int* __restrict__ status,
-                   const __grid_constant__ CUtensorMap tmap) {
+                   const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StripPeerDev sp) {
     constexpr int SH = staged_rows(TH);
     constexpr int PPT = pixels_per_thread(TH);
     __shared__ __align__(128) TI tile[SH * SW];
@@ -34,6 +39,17 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
     __shared__ float s_w[10];
 
     const TileCtx c = make_tile_ctx<TH>(g);
+    // edge membership is CTA-uniform; rows [0, halo) go up, rows [H - halo, H) go down
+    const bool top_edge = PEER && sp.wait_up != nullptr && c.y0 < sp.halo;
+    const bool bot_edge = PEER && sp.wait_dn != nullptr && c.y0 + TH > g.H - sp.halo;
+    if (PEER && (top_edge || bot_edge)) {
+        if (threadIdx.x == 0) {
+            if (top_edge) wait_stamp(sp.wait_up, sp.stamp);
+            if (bot_edge) wait_stamp(sp.wait_dn, sp.stamp);
+            asm volatile("fence.proxy.async;" ::: "memory");  // the TMA box copy below reads what the peers wrote
+        }
+        if (!TMA) __syncthreads();  // the cooperative loader reads the halo rows from every thread
+    }
     stage_tile_begin<TI, TMA, TH>(tile, &bar, &tmap, init, g, c.b, c.ox, c.oy - g.init_row0);
     // w9 == nullptr: frozen unit weight / zero bias (NLSPN, nlspn.py:61-65)
     if (threadIdx.x < 9) s_w[threadIdx.x] = w9 ? w9[threadIdx.x] : 1.f;
@@ -138,6 +154,13 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         acc += s_w[9];
         if (mode == NORM_RESIDUAL) acc = fmaf(scale, to_f32(tile[(ry + HALO_T) * SW + (cx + HALO_L)]), acc);
         st_stream(out_b + in.p, acc);
+        if (PEER) {  // B = 1: second copy of the edge rows, straight into the neighbours' next DEM buffer
+            const int y = c.y0 + ry;
+            if (top_edge && sp.up_dst != nullptr && y < sp.halo)
+                st_stream(static_cast<TI*>(sp.up_dst) + (size_t)y * g.W + (c.x0 + cx), acc);
+            if (bot_edge && sp.dn_dst != nullptr && y >= g.H - sp.halo)
+                st_stream(static_cast<TI*>(sp.dn_dst) + (size_t)(y - (g.H - sp.halo)) * g.W + (c.x0 + cx), acc);
+        }
     };
 
     // the first pixel's 27 streamed loads are in flight while the tile lands
@@ -153,14 +176,51 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         if (it > 0) load_inputs(it, cur);
         compute(it, cur);
     }
+
+    if (PEER && (top_edge || bot_edge)) {
+        // every edge CTA has (a) finished reading this generation's halo rows and (b) pushed its rows of the next one:
+        // the last CTA of each edge tells the neighbour both things with one stamp
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned per_row = (unsigned)g.tiles_x;
+            if (top_edge) {
+                const unsigned n = per_row * (unsigned)((sp.halo + TH - 1) / TH);
+                if (atomicAdd(sp.tickets, 1u) == n - 1) {
+                    sp.tickets[0] = 0u;
+                    __threadfence_system();
+                    st_release_sys(sp.up_flag, sp.stamp + 1u);
+                }
+            }
+            if (bot_edge) {
+                const unsigned n = per_row * (unsigned)(g.tiles_y - max(0, g.H - sp.halo) / TH);
+                if (atomicAdd(sp.tickets + 1, 1u) == n - 1) {
+                    sp.tickets[1] = 0u;
+                    __threadfence_system();
+                    st_release_sys(sp.dn_flag, sp.stamp + 1u);
+                }
+            }
+        }
+    }
 }
 
-template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR>
+template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR, bool PEER = false>
 static void launch_fwd_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_forward_kernel<T, TI, TMA, CS, TH, LINEAR><<<grid, THREADS, 0, la.stream>>>(
+    spn_forward_kernel<T, TI, TMA, CS, TH, LINEAR, PEER><<<grid, THREADS, 0, la.stream>>>(
         (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (TI*)la.out, la.g, la.mode, la.scale,
-        la.status, la.tmap);
+        la.status, la.tmap, PEER ? *la.strip_peer : StripPeerDev{});
+}
+
+// fused halo exchange: rasters only (B = 1, runtime channel stride), 16 rows per CTA, fp32 or bf16 throughout
+template <typename T>
+static cudaError_t launch_fwd_peer(const LaunchArgs& la) {
+    if (la.tile_h != 16 || la.g.B != 1) return cudaErrorInvalidValue;
+    const bool aligned = ((size_t)la.g.W * sizeof(T)) % 128 == 0;
+    if (la.use_tma && aligned) launch_fwd_one<T, T, true, 0, 16, false, true>(la);
+    else if (la.use_tma) launch_fwd_one<T, T, true, 0, 16, true, true>(la);
+    else launch_fwd_one<T, T, false, 0, 16, true, true>(la);
+    return cudaGetLastError();
 }
 
 // (TMA, CS, LINEAR) variants: the compile-time stride only exists for 128x128-pixel planes (always
@@ -191,6 +251,10 @@ int stage_box_cols() { return SW; }
 int stage_box_rows(int th) { return staged_rows(th); }
 
 cudaError_t launch_spn_forward(const LaunchArgs& la) {
+    if (la.strip_peer != nullptr) {
+        if (la.bf16 && la.init_f32) return cudaErrorNotSupported;
+        return la.bf16 ? launch_fwd_peer<__nv_bfloat16>(la) : launch_fwd_peer<float>(la);
+    }
     if (la.bf16 && la.init_f32) return launch_fwd_dtype<__nv_bfloat16, float>(la);
     return la.bf16 ? launch_fwd_dtype<__nv_bfloat16, __nv_bfloat16>(la) : launch_fwd_dtype<float, float>(la);
 }

@@ -24,6 +24,31 @@ struct Geom {
     int tiles_x, tiles_y;
 };
 
+// Row-strip halo exchange fused into the forward (include/jspsr_peer.h, jspsr_strip_peer): device-side view.
+// Flags are monotonically increasing generation stamps; `wait_*` are this rank's own flag words (raised by the
+// neighbours), `*_flag` / `*_dst` live in the neighbours' memory (CUDA IPC mappings reached over NVLink).
+struct StripPeerDev {
+    void* up_dst = nullptr;             // upper neighbour's bottom halo rows of its next DEM buffer (or null: signal only)
+    void* dn_dst = nullptr;             // lower neighbour's top halo rows
+    unsigned* up_flag = nullptr;        // raised to stamp + 1 when this strip's top edge CTAs are done (null: first strip)
+    unsigned* dn_flag = nullptr;
+    const unsigned* wait_up = nullptr;  // raised by the upper neighbour when its rows of generation `stamp` have landed here
+    const unsigned* wait_dn = nullptr;
+    unsigned* tickets = nullptr;        // [2] local counters of finished edge CTAs (zero between launches)
+    unsigned stamp = 0;
+    int halo = 0;
+};
+
+// Gradient all-reduce fused into the backward (jspsr_peer_reduce): slots[p] = rank p's buffer as mapped here,
+// laid out [2 parities][8 source ranks][16 doubles] followed by the device-side step counter.
+struct PeerReduceDev {
+    double* slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int rank = 0, world = 1;
+    float mul = 1.f;  // 1 / world when averaging
+};
+constexpr int REDUCE_SLOT = 16;                       // doubles per (parity, source) slot; [15] holds the stamp
+constexpr int REDUCE_COUNTER_OFFSET = 2 * 8 * REDUCE_SLOT;  // in doubles: the step counter follows the slots
+
 // Host-side launch descriptor (filled by abi.cu)
 struct LaunchArgs {
     const void* init = nullptr;
@@ -52,6 +77,8 @@ struct LaunchArgs {
     int tile_h = 16;  // rows per CTA (16 / 8 / 4 / 2), chosen by abi.cu; the TMA box is encoded to match
     cudaStream_t stream = nullptr;
     CUtensorMap tmap{};
+    const StripPeerDev* strip_peer = nullptr;    // forward: fused halo exchange (B = 1, 16 rows per CTA)
+    const PeerReduceDev* peer_reduce = nullptr;  // backward: fused all-reduce of grad_w9 / grad_b1
 };
 
 

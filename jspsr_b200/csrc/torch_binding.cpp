@@ -20,6 +20,7 @@
 #include <string>
 #include <utility>
 
+#include "../../include/jspsr_peer.h"
 #include "../../include/jspsr_tiles.h"
 
 namespace {
@@ -78,10 +79,11 @@ class PropagateFn : public torch::autograd::Function<PropagateFn> {
    public:
     static at::Tensor forward(torch::autograd::AutogradContext* ctx, const at::Tensor& init, const at::Tensor& weight,
                               const at::Tensor& offset, const at::Tensor& w, const at::Tensor& b, int64_t norm_mode,
-                              double scale) {
+                              double scale, int64_t reduce_ptr) {
         ctx->save_for_backward({init, weight, offset, w});
         ctx->saved_data["norm_mode"] = norm_mode;
         ctx->saved_data["scale"] = scale;
+        ctx->saved_data["reduce_ptr"] = reduce_ptr;  // host address of a jspsr_peer_reduce kept alive by the caller, or 0
         return spn_forward_raw(init, weight, offset, w, b, norm_mode, scale);
     }
 
@@ -92,6 +94,7 @@ class PropagateFn : public torch::autograd::Function<PropagateFn> {
         const at::Tensor& w = saved[3];
         const int64_t norm_mode = ctx->saved_data["norm_mode"].toInt();
         const double scale = ctx->saved_data["scale"].toDouble();
+        const auto* reduce = reinterpret_cast<const jspsr_peer_reduce*>(ctx->saved_data["reduce_ptr"].toInt());
         const bool need_init = ctx->needs_input_grad(0);
         const bool need_w = ctx->needs_input_grad(3) || ctx->needs_input_grad(4);
 
@@ -107,12 +110,12 @@ class PropagateFn : public torch::autograd::Function<PropagateFn> {
         if (need_w) grad_wb = at::empty({10}, f32);   // grad_w[9] then grad_b[1]
         void* stream = at::cuda::getCurrentCUDAStream(init.get_device()).stream();
         if (need_w) ws = workspace_for(init, stream);
-        check(jspsr_spn_backward(gout.data_ptr(), init.data_ptr(), weight.data_ptr(), offset.data_ptr(), w9.data_ptr<float>(),
+        check(jspsr_spn_backward_reduce(gout.data_ptr(), init.data_ptr(), weight.data_ptr(), offset.data_ptr(), w9.data_ptr<float>(),
                                  need_init ? grad_init.data_ptr<float>() : nullptr, grad_weight.data_ptr(),
                                  grad_offset.data_ptr(), need_w ? grad_wb.data_ptr<float>() : nullptr,
                                  need_w ? grad_wb.data_ptr<float>() + 9 : nullptr, need_w ? ws.data_ptr() : nullptr,
                                  (int)init.size(0), (int)init.size(2), (int)init.size(3), (int)norm_mode, (float)scale,
-                                 io_code(init, weight), 0u, stream),
+                                 io_code(init, weight), 0u, need_w ? reduce : nullptr, stream),
               "jspsr_spn_backward");
         ++g_launches;
 
@@ -132,13 +135,14 @@ class PropagateFn : public torch::autograd::Function<PropagateFn> {
                 ctx->needs_input_grad(3) ? gw : at::Tensor(),
                 ctx->needs_input_grad(4) ? gb : at::Tensor(),
                 at::Tensor(),
+                at::Tensor(),
                 at::Tensor()};
     }
 };
 
 at::Tensor propagate(const at::Tensor& init, const at::Tensor& weight, const at::Tensor& offset, const at::Tensor& w,
-                     const at::Tensor& b, int64_t norm_mode, double scale) {
-    return PropagateFn::apply(init, weight, offset, w, b, norm_mode, scale);
+                     const at::Tensor& b, int64_t norm_mode, double scale, int64_t reduce_ptr) {
+    return PropagateFn::apply(init, weight, offset, w, b, norm_mode, scale, reduce_ptr);
 }
 
 // -> (losses [4] = L1, L2, Grad, Total; dTotal/dpred or an undefined tensor)
@@ -188,7 +192,10 @@ int64_t launch_count() { return g_launches.load(); }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "C++ autograd wrappers over libjspsr_spn.so's C ABI (propagation forward/backward, fused loss)";
-    m.def("propagate", &propagate, "normalise -> deformable 3x3 gather -> (+ scale*init), differentiable");
+    m.def("propagate", &propagate, "normalise -> deformable 3x3 gather -> (+ scale*init), differentiable; reduce_ptr: host "
+          "address of a jspsr_peer_reduce (gradients of w / b all-reduced inside the backward kernel) or 0",
+          py::arg("init"), py::arg("weight"), py::arg("offset"), py::arg("w"), py::arg("b"), py::arg("norm_mode"),
+          py::arg("scale"), py::arg("reduce_ptr") = 0);
     m.def("spn_forward", &spn_forward_raw, "forward only, no autograd");
     m.def("multi_loss", &multi_loss, "(Total, losses[4]) of L1 + L2 + Sobel-L1; Total is differentiable w.r.t. pred");
     m.def("launch_count", &launch_count, "kernels enqueued through this extension");

@@ -112,8 +112,9 @@ def spn_forward(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) 
 
 
 def spn_backward(grad_out, init, weight, offset, w, norm_mode: int, scale: float = 1.0, need_grad_init=True,
-                 need_grad_w=True, accumulate_into=None, gen_preact=False):
+                 need_grad_w=True, accumulate_into=None, gen_preact=False, reducer=None):
     """Returns (grad_init fp32 | None, grad_weight, grad_offset, grad_w [1,1,3,3] | None, grad_b [1] | None).
+    `reducer` (peer.PeerGradReducer): grad_w / grad_b are all-reduced over its ranks inside the kernel.
     `accumulate_into=(grad_weight, grad_offset)` adds into existing buffers (fixed-affinity loops).
     `gen_preact`: generator-tail training - grad_weight is [B,25,H,W] (gradients w.r.t. the pre-activations of the
     Generator's two 1x1 convolutions: sigmoid' applied, centre offset pair dropped) and grad_offset is None."""
@@ -139,35 +140,76 @@ def spn_backward(grad_out, init, weight, offset, w, norm_mode: int, scale: float
     grad_b = torch.empty(1, dtype=torch.float32, device=dev) if need_grad_w else None
     ws = _workspace(init) if need_grad_w else None
     with torch.cuda.device(dev):
-        rc = _lib.lib().jspsr_spn_backward(_ptr(grad_out), _ptr(init), _ptr(weight), _ptr(offset), _ptr(w9),
-                                           _ptr(grad_init), _ptr(grad_weight), _ptr(grad_offset), _ptr(grad_w),
-                                           _ptr(grad_b), _ptr(ws), B, H, W, norm_mode, float(scale),
-                                           _io_code(init, weight), flags, _stream_ptr(init))
+        rc = _lib.lib().jspsr_spn_backward_reduce(_ptr(grad_out), _ptr(init), _ptr(weight), _ptr(offset), _ptr(w9),
+                                                  _ptr(grad_init), _ptr(grad_weight), _ptr(grad_offset), _ptr(grad_w),
+                                                  _ptr(grad_b), _ptr(ws), B, H, W, norm_mode, float(scale),
+                                                  _io_code(init, weight), flags,
+                                                  reducer.address if (reducer is not None and need_grad_w) else None,
+                                                  _stream_ptr(init))
     _lib.check(rc, "jspsr_spn_backward")
     _count()
     return grad_init, grad_weight, grad_offset, grad_w, grad_b
 
 
-def spn_forward_strip(init_buf, weight, offset, w, b, norm_mode, scale, H_img, row0, init_row0, status=None, out=None):
+def _check_strip(init_buf, weight, offset, out):
+    """Shapes / dtypes of a row-strip call: weight [B,9,Hs,W], offset [B,18,Hs,W], init_buf [B,1,rows >= 1,W]; one dtype,
+    or the torch.autocast mix (fp32 DEM buffer and output, bf16 weight / offset).  Returns (B, Hs, W, dtype code)."""
+    if weight.dim() != 4 or weight.shape[1] != 9:
+        raise RuntimeError(f"weight must be [B,9,Hs,W], got {tuple(weight.shape)}")
+    B, _, Hs, W = weight.shape
+    if tuple(offset.shape) != (B, 18, Hs, W):
+        raise RuntimeError(f"offset must be [B,18,Hs,W] = {(B, 18, Hs, W)}, got {tuple(offset.shape)}")
+    if init_buf.dim() != 4 or init_buf.shape[0] != B or init_buf.shape[1] != 1 or init_buf.shape[3] != W or init_buf.shape[2] < 1:
+        raise RuntimeError(f"init_buf must be [B,1,rows,W] with B = {B}, W = {W}, got {tuple(init_buf.shape)}")
+    if weight.dtype != offset.dtype or not (init_buf.dtype == weight.dtype or _is_mixed(init_buf, weight)):
+        raise RuntimeError("init_buf, weight and offset must share one dtype (or: float32 init_buf with bfloat16 weight/offset)")
+    if out is not None and (tuple(out.shape) != (B, 1, Hs, W) or not out.is_contiguous() or out.dtype != init_buf.dtype):
+        raise RuntimeError("out must be a contiguous [B,1,Hs,W] tensor of init_buf's dtype")
+    return B, Hs, W, _io_code(init_buf, weight)
+
+
+def spn_forward_strip(init_buf, weight, offset, w, b, norm_mode, scale, H_img, row0, init_row0, status=None, out=None,
+                      strip_peer=None):
     """Row-strip forward: `init_buf` holds rows [init_row0, init_row0+init_buf.shape[2]) of the image.
-    `out` (optional, contiguous [B,1,Hs,W], e.g. the interior of the next halo buffer) receives the result."""
-    _require_cuda(init_buf, weight, offset)
-    B, _, Hs, W = weight.shape[0], None, weight.shape[2], weight.shape[3]
+    `out` (optional, contiguous [B,1,Hs,W], e.g. the interior of the next halo buffer) receives the result.
+    `strip_peer` (peer.StripPeerStruct, B = 1): the halo exchange with the neighbouring ranks runs inside the kernel."""
+    _require_cuda(init_buf, weight, offset, out, status)
+    B, Hs, W, code = _check_strip(init_buf, weight, offset, out)
     init_buf, weight, offset = init_buf.contiguous(), weight.contiguous(), offset.contiguous()
     w9 = _w9(w, weight)
     b1 = None if b is None else b.detach().to(device=weight.device, dtype=torch.float32).contiguous()
     if out is None:
-        out = torch.empty(B, 1, Hs, W, dtype=weight.dtype, device=weight.device)
-    elif tuple(out.shape) != (B, 1, Hs, W) or not out.is_contiguous() or out.dtype != weight.dtype:
-        raise RuntimeError("out must be a contiguous [B,1,Hs,W] tensor of the input dtype")
+        out = torch.empty(B, 1, Hs, W, dtype=init_buf.dtype, device=weight.device)
     with torch.cuda.device(weight.device):
-        rc = _lib.lib().jspsr_spn_forward_strip(_ptr(init_buf), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1),
-                                                _ptr(out), B, Hs, W, H_img, row0, init_row0, init_buf.shape[2],
-                                                norm_mode, float(scale), _dtype_code(weight), _ptr(status),
-                                                _stream_ptr(weight))
+        if strip_peer is None:
+            rc = _lib.lib().jspsr_spn_forward_strip(_ptr(init_buf), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1),
+                                                    _ptr(out), B, Hs, W, H_img, row0, init_row0, init_buf.shape[2],
+                                                    norm_mode, float(scale), code, _ptr(status), _stream_ptr(weight))
+        else:
+            import ctypes
+            if B != 1:
+                raise RuntimeError("the fused halo exchange handles one raster per call (B = 1)")
+            rc = _lib.lib().jspsr_spn_forward_strip_peer(_ptr(init_buf), _ptr(weight), _ptr(offset), _ptr(w9), _ptr(b1),
+                                                         _ptr(out), Hs, W, H_img, row0, init_row0, init_buf.shape[2],
+                                                         norm_mode, float(scale), code, _ptr(status),
+                                                         ctypes.addressof(strip_peer), _stream_ptr(weight))
     _lib.check(rc, "jspsr_spn_forward_strip")
     _count()
     return out
+
+
+def strip_halo_push(band, strip_peer) -> None:
+    """First generation of a row-strip sequence: this band's own first / last `halo` rows go to the neighbours' halo rows
+    (jspsr_strip_halo_push).  band: contiguous [1,1,Hs,W] view of the buffer that will be read with `strip_peer.stamp`."""
+    import ctypes
+    _require_cuda(band)
+    if band.dim() != 4 or band.shape[0] != 1 or band.shape[1] != 1 or not band.is_contiguous():
+        raise RuntimeError(f"band must be a contiguous [1,1,Hs,W] tensor, got {tuple(band.shape)}")
+    with torch.cuda.device(band.device):
+        rc = _lib.lib().jspsr_strip_halo_push(_ptr(band), band.shape[2], band.shape[3], _dtype_code(band),
+                                              ctypes.addressof(strip_peer), _stream_ptr(band))
+    _lib.check(rc, "jspsr_strip_halo_push")
+    _count()
 
 
 def gen_spn_forward(init, feature, conv_w, conv_b, w, b, norm_mode: int, scale: float = 1.0, want_weight_offset=False):
@@ -316,9 +358,9 @@ class _Propagate(torch.autograd.Function):
     """normalise -> deformable 3x3 gather -> (+ scale*init): one kernel each way."""
 
     @staticmethod
-    def forward(ctx, init, weight, offset, w, b, norm_mode, scale):
+    def forward(ctx, init, weight, offset, w, b, norm_mode, scale, reducer=None):
         ctx.save_for_backward(init, weight, offset, w)
-        ctx.norm_mode, ctx.scale = norm_mode, scale
+        ctx.norm_mode, ctx.scale, ctx.reducer = norm_mode, scale, reducer
         return spn_forward(init, weight, offset, w, b, norm_mode, scale)
 
     @staticmethod
@@ -328,13 +370,13 @@ class _Propagate(torch.autograd.Function):
         need_init = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
         gi, gwt, goff, gw, gb = spn_backward(grad_out, init, weight, offset, w, ctx.norm_mode, ctx.scale,
-                                             need_grad_init=need_init, need_grad_w=need_w)
+                                             need_grad_init=need_init, need_grad_w=need_w, reducer=ctx.reducer)
         if gi is not None:
             gi = gi.to(init.dtype)
         if gw is not None:
             gw, gb = gw.to(w.dtype).reshape(w.shape), gb.to(w.dtype)
         return (gi, gwt if ctx.needs_input_grad[1] else None, goff if ctx.needs_input_grad[2] else None,
-                gw if ctx.needs_input_grad[3] else None, gb if ctx.needs_input_grad[4] else None, None, None)
+                gw if ctx.needs_input_grad[3] else None, gb if ctx.needs_input_grad[4] else None, None, None, None)
 
 
 class _GenPropagate(torch.autograd.Function):
@@ -403,7 +445,8 @@ def _common_dtype(init, weight, offset):
     return init.float(), weight.float(), offset.float()
 
 
-def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) -> torch.Tensor:
+def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0, reducer=None) -> torch.Tensor:
+    """`reducer` (peer.PeerGradReducer, batch-sharded training): the gradients of w / b come back all-reduced."""
     init, weight, offset = _common_dtype(init, weight, offset)
     if init.shape[0] == 0:  # empty batch: nothing to launch (the reference returns an empty tensor too)
         _check_shapes(init, weight, offset)
@@ -416,8 +459,9 @@ def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0) ->
         _check_shapes(init, weight, offset)
         if w.numel() != 9:
             raise RuntimeError(f"only kernel_size 3 is supported (w has {w.numel()} elements)")
-        return e.propagate(init, weight, offset, w, b, int(norm_mode), float(scale))
-    return _Propagate.apply(init, weight, offset, w, b, norm_mode, scale)
+        return e.propagate(init, weight, offset, w, b, int(norm_mode), float(scale),
+                           0 if reducer is None else reducer.address)
+    return _Propagate.apply(init, weight, offset, w, b, norm_mode, scale, reducer)
 
 
 class _Iterate(torch.autograd.Function):

@@ -45,9 +45,17 @@ class PostProcessor(nn.Module):
         if self.scale != 1:
             print("Warning: The scale factor is not 1. This may lead to unexpected results.")
 
+    def set_grad_reducer(self, reducer):
+        """Batch-sharded training (one process per GPU): all-reduce the gradients of `w` / `b` inside the backward kernel
+        over `reducer`'s ranks (jspsr_b200.peer.PeerGradReducer) instead of through a NCCL bucket.  None switches it off.
+        Not a parameter or buffer: state_dict and checkpoints are unchanged."""
+        object.__setattr__(self, "_grad_reducer", reducer)
+        return self
+
     def forward(self, init_dem, weight, offset):
         mode = NORM_RESIDUAL if self.residual else NORM_SUM
-        return F.propagate(init_dem, weight, offset, self.w, self.b, mode, float(self.scale))
+        return F.propagate(init_dem, weight, offset, self.w, self.b, mode, float(self.scale),
+                           getattr(self, "_grad_reducer", None))
 
 
 def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, context, init_dem=None):

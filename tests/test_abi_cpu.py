@@ -11,7 +11,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADERS = [os.path.join(ROOT, "include", h) for h in ("jspsr_spn.h", "jspsr_tiles.h")]
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("jspsr_spn.h", "jspsr_tiles.h", "jspsr_peer.h")]
 
 
 @pytest.fixture(scope="module")
@@ -30,11 +30,48 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 18, names
+    assert len(names) == 25, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in include/*.h but not exported"
     assert sorted(lib.exported_symbols()) == names, "jspsr_b200/_lib.py binds a different set than the header"
+
+
+def test_peer_argument_validation_needs_no_gpu(lib):
+    """include/jspsr_peer.h: the structs are validated on the host before any CUDA work."""
+    from jspsr_b200 import peer
+    h = lib.lib()
+    one = ctypes.c_void_p(16)
+    pr = peer.PeerReduceStruct()
+    pr.rank, pr.world, pr.average = 0, 9, 1
+    bwd = lambda pr_, gw=one: h.jspsr_spn_backward_reduce(one, one, one, one, one, None, one, one, gw, one, one, 1, 8, 8, 1, 1.0,
+                                                          0, 0, ctypes.addressof(pr_), None)
+    assert bwd(pr) == -1 and b"at most 8" in h.jspsr_last_error()
+    pr.world, pr.rank = 2, 2
+    assert bwd(pr) == -1 and b"rank 2 / world 2" in h.jspsr_last_error()
+    pr.rank = 1
+    assert bwd(pr) == -1 and b"slots[0]" in h.jspsr_last_error()
+    pr.slots[0], pr.slots[1] = 256, 512
+    assert bwd(pr, None) == -1 and b"nothing to reduce" in h.jspsr_last_error()
+
+    sp = peer.StripPeerStruct()
+    fwd = lambda: h.jspsr_spn_forward_strip_peer(one, one, one, one, one, one, 64, 128, 256, 0, 0, 72, 0, 1.0, 0, None,
+                                                 ctypes.addressof(sp), None)
+    assert fwd() == -1 and b"my_flags" in h.jspsr_last_error()
+    sp.my_flags, sp.halo = 256, 65
+    assert fwd() == -1 and b"halo 65" in h.jspsr_last_error()
+    sp.halo, sp.up_dst = 8, 1024
+    assert fwd() == -1 and b"without its neighbour" in h.jspsr_last_error()
+    assert h.jspsr_spn_forward_strip_peer(one, one, one, one, one, one, 64, 128, 256, 0, 0, 72, 0, 1.0, 2, None,
+                                          ctypes.addressof(sp), None) == -2          # mixed dtype
+    assert h.jspsr_spn_forward_strip_peer(one, one, one, one, one, one, 64, 128, 256, 0, 0, 72, 0, 1.0, 0, None,
+                                          None, None) == -1
+    sp.up_dst, sp.up_flags = None, 2048
+    assert h.jspsr_strip_halo_push(one, 64, 128, 0, ctypes.addressof(sp), None) == -1
+    assert b"destination for every neighbour" in h.jspsr_last_error()
+    sp.up_flags = None
+    assert h.jspsr_strip_halo_push(one, 64, 128, 0, ctypes.addressof(sp), None) == 0   # a single strip: nothing to do
+    assert h.jspsr_peer_open(None, None) == -1 and h.jspsr_peer_close(None) == 0 and h.jspsr_peer_free(None) == 0
 
 
 def test_version_and_workspace(lib):
