@@ -328,8 +328,15 @@ gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ fe
 template <typename FT, int C, bool TMA, int TH, bool WO>
 static cudaError_t launch_gen_one(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature,
                                   const float* conv_w, const float* conv_b, void* weight_out, void* offset_out) {
-    const size_t dyn = (TMA ? (size_t)GEN_STAGES * GEN_THREADS * C * sizeof(FT) : 0) + (size_t)2 * GEN_N * C * 4 +
-                       (size_t)staged_rows(TH) * SW * 4;
+    size_t dyn = (TMA ? (size_t)GEN_STAGES * GEN_THREADS * C * sizeof(FT) : 0) + (size_t)2 * GEN_N * C * 4 +
+                 (size_t)staged_rows(TH) * SW * 4;
+    // The kernel allocates 256 or 512 TMEM columns per CTA, so at most 2 or 1 CTAs fit an SM's 512 columns.  With the TMA
+    // ring the shared-memory footprint enforces that by itself; the bounds-checked fallback (no ring) is small enough for
+    // more CTAs to become resident, and the extra ones would spin inside tcgen05.alloc holding registers and shared memory.
+    // Pad the request so that residency never exceeds what TMEM can serve.
+    constexpr size_t tmem_cols = ((sizeof(FT) == 2 ? C : 2 * C) + 2 * GEN_N <= 256) ? 256 : 512;
+    constexpr size_t min_dyn = tmem_cols == 512 ? (size_t)116 * 1024 : (size_t)76 * 1024;   // > 227 KB / 2, > 227 KB / 3
+    if (dyn < min_dyn) dyn = min_dyn;
     const cudaError_t attr = ensure_dynamic_smem((const void*)gen_spn_forward_kernel<FT, C, TMA, TH, WO>, dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));

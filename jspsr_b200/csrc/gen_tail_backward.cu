@@ -196,7 +196,11 @@ gen_grad_feature_kernel(const FT* __restrict__ gz, const float* __restrict__ con
 template <typename FT, int C, bool TMA, int CS>
 static cudaError_t launch_gf_cs(const LaunchArgs& la, const CUtensorMap& tmap_gz, const void* gz, const float* conv_w,
                                 void* grad_feature) {
-    const size_t dyn = (TMA ? (size_t)GT_STAGES * GEN_NOUT * GEN_THREADS * sizeof(FT) : 0) + (size_t)2 * C * GT_K * 4;
+    size_t dyn = (TMA ? (size_t)GT_STAGES * GEN_NOUT * GEN_THREADS * sizeof(FT) : 0) + (size_t)2 * C * GT_K * 4;
+    // residency must not exceed what the SM's 512 TMEM columns can serve (256 per CTA at C <= 64, else 512): see
+    // gen_spn_forward.cu - pad the shared-memory request of the small (no TMA ring) instantiations accordingly
+    constexpr size_t min_dyn = C <= 64 ? (size_t)76 * 1024 : (size_t)116 * 1024;
+    if (dyn < min_dyn) dyn = min_dyn;
     const cudaError_t attr = ensure_dynamic_smem((const void*)gen_grad_feature_kernel<FT, C, TMA, CS>, dyn);
     if (attr != cudaSuccess) return attr;
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));

@@ -406,12 +406,18 @@ static void aff_fwd_launch(const AffArgs& a) {
     nlspn_affinity_fwd_kernel<T, CONF, TMA, TH><<<grid, THREADS, 0, a.stream>>>(
         (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.offset_out, (T*)a.aff_out, a.g, a.affinity, a.legacy, a.tmap);
 }
+static thread_local cudaError_t g_aff_attr_error = cudaSuccess;  // set by a launcher of this call, read by aff_dispatch
+
 template <typename T, bool CONF, bool TMA, int TH, int CS, bool ITILE>
 static void aff_bwd_launch_one(const AffArgs& a) {
     dim3 grid((unsigned)((size_t)a.g.tiles_x * a.g.tiles_y * a.g.B));
     const size_t dyn = ITILE ? (size_t)staged_rows(TH) * SW * sizeof(int) : 0;
     if (dyn > 0) {  // static + dynamic shared memory exceed 48 KB with the wide halo: opt in once per instantiation
-        (void)ensure_dynamic_smem((const void*)nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE>, dyn);
+        const cudaError_t e = ensure_dynamic_smem((const void*)nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE>, dyn);
+        if (e != cudaSuccess) {  // do not launch a kernel that cannot get its shared memory: report the attribute error
+            g_aff_attr_error = e;
+            return;
+        }
     }
     nlspn_affinity_bwd_kernel<T, CONF, TMA, TH, CS, ITILE><<<grid, THREADS, dyn, a.stream>>>(
         (const T*)a.grad_offset, (const T*)a.grad_aff, (const T*)a.conv_out, (const T*)a.conf, a.gamma, (T*)a.grad_conv,
@@ -445,8 +451,10 @@ static void aff_dispatch_th(const AffArgs& a) {
 
 template <typename T, bool FWD>
 static cudaError_t aff_dispatch(const AffArgs& a) {
+    g_aff_attr_error = cudaSuccess;
     if (a.tile_h == 8) aff_dispatch_th<T, FWD, 8>(a);
     else aff_dispatch_th<T, FWD, 2>(a);
+    if (g_aff_attr_error != cudaSuccess) return g_aff_attr_error;
     return cudaGetLastError();
 }
 

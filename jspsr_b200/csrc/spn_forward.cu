@@ -38,7 +38,10 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_w[10];
 
-    const TileCtx c = make_tile_ctx<TH>(g);
+    // tile rows inside `halo` of a strip edge that has a neighbour (0 without PEER: plain row-major tile order)
+    const int n_top = (PEER && sp.wait_up != nullptr) ? (sp.halo + TH - 1) / TH : 0;
+    const int n_bot = (PEER && sp.wait_dn != nullptr) ? g.tiles_y - max(0, g.H - sp.halo) / TH : 0;
+    const TileCtx c = make_tile_ctx<TH>(g, n_top, n_bot);
     // edge membership is CTA-uniform; rows [0, halo) go up, rows [H - halo, H) go down
     const bool top_edge = PEER && sp.wait_up != nullptr && c.y0 < sp.halo;
     const bool bot_edge = PEER && sp.wait_dn != nullptr && c.y0 + TH > g.H - sp.halo;
@@ -185,7 +188,7 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         if (threadIdx.x == 0) {
             const unsigned per_row = (unsigned)g.tiles_x;
             if (top_edge) {
-                const unsigned n = per_row * (unsigned)((sp.halo + TH - 1) / TH);
+                const unsigned n = per_row * (unsigned)n_top;
                 if (atomicAdd(sp.tickets, 1u) == n - 1) {
                     sp.tickets[0] = 0u;
                     __threadfence_system();
@@ -193,7 +196,7 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
                 }
             }
             if (bot_edge) {
-                const unsigned n = per_row * (unsigned)(g.tiles_y - max(0, g.H - sp.halo) / TH);
+                const unsigned n = per_row * (unsigned)n_bot;
                 if (atomicAdd(sp.tickets + 1, 1u) == n - 1) {
                     sp.tickets[1] = 0u;
                     __threadfence_system();

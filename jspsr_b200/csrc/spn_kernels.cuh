@@ -38,14 +38,21 @@ struct TileCtx {
     unsigned oy_lo;  // (unsigned)(oy + r_lo): global row of the first trusted staged row
 };
 
+// edge_top / edge_bot (fused halo exchange, B = 1): that many tile rows at the top / bottom of the strip are scheduled
+// FIRST (CTAs are dispatched in blockIdx order).  They are the CTAs that feed the neighbouring ranks and that wait for
+// them: run first, their rows reach the neighbours a whole kernel before the neighbours' next application needs them,
+// and what they wait for was produced at the start of the neighbours' previous kernel.
 template <int TH>
-__device__ __forceinline__ TileCtx make_tile_ctx(const Geom& g) {
+__device__ __forceinline__ TileCtx make_tile_ctx(const Geom& g, int edge_top = 0, int edge_bot = 0) {
     constexpr int SH = staged_rows(TH);
     TileCtx c;
     unsigned t = blockIdx.x;
     const int tx = t % g.tiles_x;
     t /= g.tiles_x;
-    const int ty = t % g.tiles_y;
+    int ty = t % g.tiles_y;
+    if (edge_bot > 0 && edge_top + edge_bot <= g.tiles_y) {
+        if (ty >= edge_top) ty = ty < edge_top + edge_bot ? g.tiles_y - edge_bot + (ty - edge_top) : ty - edge_bot;
+    }
     c.b = t / g.tiles_y;
     c.x0 = tx * TILE_W;
     c.y0 = ty * TH;

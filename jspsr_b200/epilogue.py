@@ -122,11 +122,13 @@ class MeterRMSE:
         self.reset()
 
     def update(self, pred, gt, meta=None, base_elev=0, elev_log=False):
+        # the reference pools the whole batch tensor into ONE rmse per update (metrics.py:382-396: sum / numel, then
+        # total_n += 1); its evaluation loop runs at batch size 1, where that is the per-sample rmse
         m = dem_metrics(pred, gt, self.border, self.value_min, self.value_max, elev_log)
-        for v in m["rmse"].tolist():           # the reference reads .item() per sample as well
-            self.total_rmse += v
-            self.sample_rmse.append(v)
-            self.total_n += 1
+        v = float(torch.sqrt(m["sum_sq"].sum() / (m["count"] * pred.shape[0])).item())
+        self.total_rmse += v
+        self.sample_rmse.append(v)
+        self.total_n += 1
 
     def reset(self):
         self.total_rmse, self.total_n, self.sample_rmse, self.sample_id = 0.0, 0, [], []

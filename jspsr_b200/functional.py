@@ -283,9 +283,15 @@ def offset_absmax(offset: torch.Tensor) -> torch.Tensor:
 
 
 def spn_iterate(feat_init, aff, offset, T: int, feat_fix=None, mask_fix=None) -> torch.Tensor:
-    """T fixed-affinity applications; returns all intermediates [T,B,1,H,W]."""
+    """T fixed-affinity applications; returns all intermediates [T,B,1,H,W].  One dtype for all three tensors
+    (jspsr_spn_iterate has no mixed mode; `iterate` promotes autocast's mix first)."""
     _require_cuda(feat_init, aff, offset, feat_fix, mask_fix)
     B, H, W = _check_shapes(feat_init, aff, offset)
+    if not (feat_init.dtype == aff.dtype == offset.dtype):
+        raise RuntimeError("spn_iterate needs feat_init, aff and offset in one dtype (float32 or bfloat16); "
+                           f"got {feat_init.dtype}, {aff.dtype}, {offset.dtype}")
+    if T < 1:
+        raise RuntimeError(f"spn_iterate: T = {T} must be positive (NLSPN.forward handles prop_time = 0 itself)")
     feat_init, aff, offset = feat_init.contiguous(), aff.contiguous(), offset.contiguous()
     out = torch.empty((T, B, 1, H, W), dtype=feat_init.dtype, device=feat_init.device)
     scratch = None
@@ -496,6 +502,11 @@ class _Iterate(torch.autograd.Function):
 
 
 def iterate(feat_init, aff, offset, T: int, feat_fix=None, mask_fix=None) -> torch.Tensor:
+    """The loop of NLSPN.forward (nlspn.py:222-235).  Mixed dtypes - e.g. the fp32 feature with bf16 affinities / offsets
+    that torch.autocast(bfloat16) produces - are promoted to float32 first, which is what torchvision's operator does with
+    them in the reference; a uniform bf16 set runs in bf16 I/O."""
+    if not (feat_init.dtype == aff.dtype == offset.dtype):
+        feat_init, aff, offset = feat_init.float(), aff.float(), offset.float()
     return _Iterate.apply(feat_init, aff, offset, feat_fix, mask_fix, T)
 
 

@@ -58,7 +58,8 @@ class PostProcessor(nn.Module):
                            getattr(self, "_grad_reducer", None))
 
 
-def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, context, init_dem=None):
+def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, context, init_dem=None,
+                          detach_dem: bool = True):
     """The two lines `weight, offset = self.generator(dem, context)` and
     `out = self.postprocessor(dem.detach(), weight, offset)` of models/JSPSR.py:371-375 (models/EDSR.py:133-134)
     with the Generator's last two layers fused into the propagation kernel.
@@ -68,7 +69,16 @@ def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, c
     (spn.py:57-65: cuDNN convolutions, not on the hot path) runs as is, its parameters stay where they are, so
     checkpoints and optimizer groups are unchanged.  `postprocessor` is a PostProcessor (either implementation).
     The weight/offset tensors never exist in inference; with autograd they are written once by the fused kernel
-    and consumed by the fused backward."""
+    and consumed by the fused backward.
+
+    `detach_dem` selects the call site being replaced:
+      True  (default) models/JSPSR.py:372-375 - `dem = dem.detach()` BEFORE the Generator: no gradient reaches `dem`,
+            neither through the Generator's convd1 nor through the propagation;
+      False models/EDSR.py:133-134 - `dem` is not detached at all: it receives the gradient through the Generator body
+            AND the propagation's grad_init.
+    `init_dem` overrides the DEM the propagation starts from (used as given, with its own autograd history)."""
+    if detach_dem:
+        dem = dem.detach()
     d2 = generator.convd2(generator.convd1(dem))
     f2 = generator.convf2(generator.convf1(context))
     feature = generator.block(generator.conv(torch.cat((d2, f2), dim=1)))
@@ -78,7 +88,7 @@ def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, c
     conv_w = torch.cat((cw.weight.flatten(1), co.weight.flatten(1)), dim=0)
     conv_b = torch.cat((cw.bias, co.bias))
     mode = NORM_RESIDUAL if postprocessor.residual else NORM_SUM
-    init = dem.detach() if init_dem is None else init_dem
+    init = dem if init_dem is None else init_dem
     return F.gen_propagate(init, feature, conv_w, conv_b, postprocessor.w, postprocessor.b, mode,
                            float(postprocessor.scale))
 
@@ -180,6 +190,8 @@ class NLSPN(nn.Module):
             mask_fix = (mask_fix > 0.0).type_as(feat_fix)
             fix = feat_fix
 
+        if self.prop_time < 1:   # nlspn.py:222-235 with an empty loop: the input comes back, list_feat is empty
+            return feat_init, [], offset, aff, self.aff_scale_const.data
         feats = F.iterate(feat_init, aff, offset, self.prop_time, fix, mask_fix)
         list_feat = list(feats.unbind(0))
         feat_result = list_feat[-1]

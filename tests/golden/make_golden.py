@@ -35,7 +35,7 @@ def _import_reference():
     return PostProcessor, Post_process_deconv, NLSPN
 
 
-def _inputs(seed, B, H, W, off_sigma, dtype, mode="normal"):
+def _inputs(seed, B, H, W, off_sigma, dtype, mode="normal", gout_scale=1.0):
     g = torch.Generator().manual_seed(seed)
     init = torch.rand(B, 1, H, W, generator=g, dtype=torch.float64)
     weight = torch.sigmoid(1.5 * torch.randn(B, 9, H, W, generator=g, dtype=torch.float64))
@@ -47,7 +47,7 @@ def _inputs(seed, B, H, W, off_sigma, dtype, mode="normal"):
     elif mode == "half":
         offset = torch.round(offset * 2) / 2
     offset[:, 8:10] = 0          # Generator inserts a zero centre pair (spn.py:69-73)
-    grad_out = torch.randn(B, 1, H, W, generator=g, dtype=torch.float64)
+    grad_out = gout_scale * torch.randn(B, 1, H, W, generator=g, dtype=torch.float64)
     w = 1 + 0.2 * (torch.rand(1, 1, 3, 3, generator=g, dtype=torch.float64) - 0.5)
     b = torch.tensor([0.1], dtype=torch.float64)
     # inputs are rounded to fp32 first so fp32 and fp64 runs see identical values
@@ -55,8 +55,8 @@ def _inputs(seed, B, H, W, off_sigma, dtype, mode="normal"):
     return [cast(t) for t in (init, weight, offset, grad_out, w, b)]
 
 
-def run_postprocessor(make_module, seed, B, H, W, off_sigma, mode, dtype):
-    init, weight, offset, grad_out, w, b = _inputs(seed, B, H, W, off_sigma, dtype, mode)
+def run_postprocessor(make_module, seed, B, H, W, off_sigma, mode, dtype, gout_scale=1.0):
+    init, weight, offset, grad_out, w, b = _inputs(seed, B, H, W, off_sigma, dtype, mode, gout_scale)
     mod = make_module().to(dtype)
     with torch.no_grad():
         mod.w.copy_(w)
@@ -88,17 +88,23 @@ def main():
         "pp_integer_offsets": (lambda: PostProcessor(3, False, 1.0), 16, 1, 9, 11, 2.0, "integer", 2, 1.0),
         "pp_half_offsets": (lambda: PostProcessor(3, True, 1.0), 17, 1, 9, 11, 2.0, "half", 1, 1.0),
         "pp_w32_multirow": (lambda: PostProcessor(3, True, 1.0), 18, 1, 40, 32, 2.5, "normal", 1, 1.0),
+        # the gradient a mean-reduced loss hands back (train/train_utils.py:214-217: losses are means over ~1e6 pixels):
+        # grad_out ~ 1e-6, so every gradient tensor is ~1e-6 and only a tolerance relative to the tensor's own scale tests it
+        "pp_small_grad": (lambda: PostProcessor(3, True, 1.0), 19, 2, 24, 32, 1.5, "normal", 1, 1.0, 1e-6),
+        "pp_small_grad_sum": (lambda: PostProcessor(3, False, 1.0), 20, 2, 24, 32, 1.5, "normal", 2, 1.0, 1e-6),
         "lrru_residual": (lambda: Post_process_deconv(types.SimpleNamespace(kernel_size=3, dkn_residual=True)),
                           21, 2, 12, 16, 1.5, "normal", 1, 1.0),
         "lrru_sum": (lambda: Post_process_deconv(types.SimpleNamespace(kernel_size=3, dkn_residual=False)),
                      22, 2, 12, 16, 1.5, "normal", 2, 1.0),
     }
-    for name, (factory, seed, B, H, W, sigma, omode, nmode, scale) in pp_cases.items():
+    for name, (factory, seed, B, H, W, sigma, omode, nmode, scale, *rest) in pp_cases.items():
+        gs = rest[0] if rest else 1.0
+
         def quiet_factory():
             with contextlib.redirect_stdout(io.StringIO()):
                 return factory()
-        out32, inp = run_postprocessor(quiet_factory, seed, B, H, W, sigma, omode, torch.float32)
-        out64, _ = run_postprocessor(quiet_factory, seed, B, H, W, sigma, omode, torch.float64)
+        out32, inp = run_postprocessor(quiet_factory, seed, B, H, W, sigma, omode, torch.float32, gs)
+        out64, _ = run_postprocessor(quiet_factory, seed, B, H, W, sigma, omode, torch.float64, gs)
         arrays = {f"in_{k}": v.numpy() for k, v in inp.items()}
         arrays.update({f"f32_{k}": v.numpy() for k, v in out32.items()})
         arrays.update({f"f64_{k}": v.numpy() for k, v in out64.items()})

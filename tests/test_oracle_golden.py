@@ -23,7 +23,7 @@ def _close(a, b, rtol, atol, what):
 
 
 def test_fixtures_present():
-    assert len(PP) == 10 and len(NL) == 5 and len(GEN) == 4
+    assert len(PP) == 12 and len(NL) == 5 and len(GEN) == 4
 
 
 @pytest.mark.parametrize("path", GEN, ids=[os.path.basename(p)[:-4] for p in GEN])
@@ -70,7 +70,7 @@ def test_postprocessor_matches_reference(path, prec):
     g = O.postprocessor_backward(gout, init, weight, offset, w9, mode, scale)
     for k in ("grad_init", "grad_weight", "grad_offset", "grad_w", "grad_b"):
         ref = z[f"{prec}_{k}"]
-        scale_k = max(1.0, float(np.abs(ref).max()))
+        scale_k = float(np.abs(ref).max())   # the tensor's own scale (the pp_small_grad fixtures hold gradients ~1e-6)
         _close(g[k], ref, rtol, atol * scale_k * (50 if k in ("grad_w", "grad_b") and prec == "f32" else 1), k)
 
 
