@@ -169,3 +169,54 @@ def test_ref_port_matches_fixtures(path):
                                                        t("grad_out"), residual=(mode == 1), scale=scale)
     for got, key in ((out, "out"), (gw, "grad_weight"), (go, "grad_offset"), (gw9, "grad_w"), (gb, "grad_b")):
         np.testing.assert_allclose(got.numpy(), z["f32_" + key], rtol=1e-6, atol=1e-6, err_msg=key)
+
+
+MODEL = sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz")))
+
+
+@pytest.mark.parametrize("path", MODEL, ids=[os.path.basename(p)[6:-4] for p in MODEL])
+def test_oracle_matches_the_reference_model_run(path):
+    """Model level (tests/golden/make_golden_model.py): the tensors captured inside the reference's own
+    models.JSPSR.Model at the propagation boundary (models/JSPSR.py:371-375), its loss gradient, RMSE and MAE.
+    The reference ran in fp32 only, so the gate is 1e-5 of each tensor's own scale; the fp32 C oracle forms tap
+    positions with the reference's operation order (same cells)."""
+    from oracle import c_oracle as C
+    from oracle import epilogue_oracle as E
+    C.build()
+    z = np.load(path)
+    assert str(z["meta"]).startswith("torch ") and "torchvision" in str(z["meta"])
+    mode, scale = (1 if bool(z["residual"]) else 2), float(z["scale"])
+    w9, b1 = z["in_w"].reshape(9), z["in_b"]
+    out = C.forward(z["in_dem"], z["in_weight"], z["in_offset"], w9, b1, mode, scale)
+    assert np.abs(out - z["ref_out"]).max() <= 1e-5 * np.abs(z["ref_out"]).max()
+    g = C.backward(z["ref_grad_out"], z["in_dem"], z["in_weight"], z["in_offset"], w9, mode, scale, need_grad_init=False)
+    gmax = np.abs(z["ref_grad_out"]).max()
+    for k in ("grad_weight", "grad_offset", "grad_w", "grad_b"):
+        ref = z["ref_" + k].reshape(np.asarray(g[k]).shape)
+        floor = 1.2e-7 * gmax * (np.sqrt(z["ref_grad_out"].size) if k in ("grad_w", "grad_b") else 1.0)
+        assert np.abs(g[k] - ref).max() <= 1e-5 * np.abs(ref).max() + floor, k
+    _, _, vmin, vmax, border = (float(v) for v in z["cfg"])
+    m = E.dem_metrics(z["ref_out"], z["in_hr_dem"], border, vmin, vmax, True)
+    for i in range(len(m["rmse"])):
+        assert f"{m['rmse'][i]:.4f}" == f"{z['ref_sample_rmse'][i]:.4f}" and f"{m['mae'][i]:.4f}" == f"{z['ref_sample_mae'][i]:.4f}"
+    lo = E.multi_loss(z["ref_out"].astype(np.float64), z["in_hr_dem"].astype(np.float64))
+    got = np.array([float(lo[k]) for k in ("L1", "L2", "Grad", "Total")])
+    assert np.all(np.abs(got - z["ref_losses"]) <= 1e-5 * np.abs(z["ref_losses"]))
+
+
+def test_fixture_provenance_is_recorded_and_uniform():
+    """Every fixture names the torch / torchvision build that produced it (the reference pins torchvision 0.16, this image
+    has 0.26: DESIGN.md section 2), and they all come from the same one."""
+    metas = set()
+    for p in PP + NL + GEN + MODEL:
+        z = np.load(p)
+        assert "meta" in z.files, p
+        metas.add(str(z["meta"]))
+    assert metas == {"torch 2.11.0+cu128 torchvision 0.26.0+cu128"}, metas
+    try:
+        import torchvision
+    except ImportError:
+        return
+    # when torchvision is importable (build container and GPU box), it is the version the fixtures were made with, so
+    # test_ref_port_matches_fixtures really re-runs the fixtures' operator
+    assert torchvision.__version__.split("+")[0] == "0.26.0"
