@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 105 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 106 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,
@@ -162,6 +162,20 @@ int jspsr_gen_spn_forward(const void *init, const void *feature, const float *co
  */
 int jspsr_gen_tail_grad_feature(const void *gz, const float *conv_w, void *grad_feature, int B, int C,
                                 int H, int W, int dtype, void *stream);
+
+/*
+ * Parameter gradients of the Generator tail: grad_conv_w[j,c] = sum over (b,y,x) of gz[b,j,y,x] * feature[b,c,y,x]
+ * ([25,C], the layout of conv_w) and grad_conv_b[j] = sum of gz[b,j,y,x] - the backward of Generator.conv_weight /
+ * conv_offset (spn.py:41-52) w.r.t. their weights and biases, which the reference gets from cuDNN's convolution
+ * backward.  One pass over gz and feature, contraction over the pixel index on the tensor cores (tcgen05, tf32
+ * 3-product split, short fp32 runs combined in fp64).  Either output may be NULL.  workspace: device memory of
+ * jspsr_gen_tail_workspace_bytes() bytes, 16-byte aligned, ZERO on the first call; the kernel leaves it zero.
+ * dtype JSPSR_F32 only; C = 64 or 128.
+ */
+size_t jspsr_gen_tail_workspace_bytes(void);
+int jspsr_gen_tail_grad_params(const void *gz, const void *feature, float *grad_conv_w,
+                               float *grad_conv_b, void *workspace, int B, int C, int H, int W,
+                               int dtype, void *stream);
 
 /* max |row offset| and max |column offset| over a [B,18,H,W] tensor -> out2[2] (device,
  * combined with max so several calls may fold into one pair; zero it first).  Used to

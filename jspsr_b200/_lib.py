@@ -29,6 +29,8 @@ _SIGNATURES = {
     "jspsr_spn_forward_strip": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_float, c_int, c_void_p, c_void_p]),
     "jspsr_gen_spn_forward": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_float, c_int, c_void_p]),
     "jspsr_gen_tail_grad_feature": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
+    "jspsr_gen_tail_workspace_bytes": (c_size_t, []),
+    "jspsr_gen_tail_grad_params": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "jspsr_spn_offset_absmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "jspsr_spn_iterate": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "jspsr_nlspn_affinity_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),

@@ -62,7 +62,7 @@ cudaError_t launch_offset_absmax(const void* offset, size_t, size_t cs, int B, b
 // for this rank's flags >= stamp - 1: the neighbours have finished reading the buffer that is being overwritten.
 template <typename T>
 __global__ void __launch_bounds__(256) halo_push_kernel(const T* __restrict__ band, int Hs, int W, const StripPeerDev sp) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !(sp.debug & 4)) {
         if (sp.wait_up) wait_stamp(sp.wait_up, sp.stamp - 1u);
         if (sp.wait_dn) wait_stamp(sp.wait_dn, sp.stamp - 1u);
     }
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const T* __restrict__ ba
         if (up) up[i] = band[i];
         if (dn) dn[i] = last[i];
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();  // every thread's peer stores are ordered before thread 0's system-scope fence (cumulativity)
+    if (threadIdx.x == 0) __threadfence_system();
     if (threadIdx.x == 0 && atomicAdd(sp.tickets, 1u) == gridDim.x - 1) {
         sp.tickets[0] = 0u;
         __threadfence_system();

@@ -37,6 +37,8 @@ struct StripPeerDev {
     unsigned* tickets = nullptr;        // [2] local counters of finished edge CTAs (zero between launches)
     unsigned stamp = 0;
     int halo = 0;
+    int debug = 0;  // JSPSR_STRIP_PEER_DEBUG (timing experiments only, results are NOT valid): 1 = plain tile order,
+                    // 2 = no row copy in the push, 4 = no waits, 8 = no push at all (with 4)
 };
 
 // Gradient all-reduce fused into the backward (jspsr_peer_reduce): slots[p] = rank p's buffer as mapped here,

@@ -266,6 +266,39 @@ def gen_tail_grad_feature(gz, conv_w) -> torch.Tensor:
     return out
 
 
+_gen_workspaces = {}
+_GEN_WGRAD_LIBRARY = False   # measurements only (tools/gen_train_time.py): the cuBLAS batched GEMM the kernel replaced
+
+
+def gen_tail_grad_params(gz, feature, need_w: bool = True, need_b: bool = True):
+    """(grad_conv_w [25,C], grad_conv_b [25]) = (sum_{b,y,x} gz[b,j,y,x] * feature[b,c,y,x], sum_{b,y,x} gz[b,j,y,x]):
+    the weight / bias gradients of the Generator tail's two 1x1 convolutions (spn.py:41-52) in one pass over gz and
+    feature (gen_tail_wgrad.cu: contraction over the pixel index on tcgen05).  fp32 tensors."""
+    _require_cuda(gz, feature)
+    if gz.dim() != 4 or gz.shape[1] != 25:
+        raise RuntimeError(f"gz must be [B,25,H,W], got {tuple(gz.shape)}")
+    B, _, H, W = gz.shape
+    if feature.dim() != 4 or feature.shape[0] != B or tuple(feature.shape[2:]) != (H, W):
+        raise RuntimeError(f"feature must be [B,C,H,W] with B, H, W = {(B, H, W)}, got {tuple(feature.shape)}")
+    if gz.dtype != torch.float32 or feature.dtype != torch.float32:
+        raise RuntimeError("gen_tail_grad_params takes float32 gz and feature")
+    C = feature.shape[1]
+    gz, feature = gz.contiguous(), feature.contiguous()
+    key = (gz.device.index, _stream_ptr(gz))
+    ws = _gen_workspaces.get(key)
+    if ws is None:   # zero on first use; the kernel leaves it zeroed
+        ws = torch.zeros(_lib.lib().jspsr_gen_tail_workspace_bytes(), dtype=torch.uint8, device=gz.device)
+        _gen_workspaces[key] = ws
+    gw = torch.empty(25, C, dtype=torch.float32, device=gz.device) if need_w else None
+    gb = torch.empty(25, dtype=torch.float32, device=gz.device) if need_b else None
+    with torch.cuda.device(gz.device):
+        rc = _lib.lib().jspsr_gen_tail_grad_params(_ptr(gz), _ptr(feature), _ptr(gw), _ptr(gb), _ptr(ws), B, C, H, W,
+                                                   F32, _stream_ptr(gz))
+    _lib.check(rc, "jspsr_gen_tail_grad_params")
+    _count()
+    return gw, gb
+
+
 def offset_absmax(offset: torch.Tensor) -> torch.Tensor:
     """[max |row offset|, max |col offset|] as a 2-element fp32 device tensor."""
     _require_cuda(offset)
@@ -387,8 +420,8 @@ class _Propagate(torch.autograd.Function):
 
 class _GenPropagate(torch.autograd.Function):
     """Generator tail + propagation.  Forward: one fused kernel that also materialises weight/offset when a
-    gradient is needed.  Backward: the fused propagation backward kernel, then the (tiny-N) 1x1-convolution
-    gradients as plain library GEMMs."""
+    gradient is needed.  Backward: the fused propagation backward kernel, then the two tensor-core kernels of the
+    1x1 convolutions' gradients (feature: gen_tail_backward.cu; weights + biases: gen_tail_wgrad.cu)."""
 
     @staticmethod
     def forward(ctx, init, feature, conv_w, conv_b, w, b, norm_mode, scale):
@@ -420,14 +453,21 @@ class _GenPropagate(torch.autograd.Function):
             torch.mul(gwt, weight * (1.0 - weight), out=gz4[:, :9])
             gz4[:, 9:17].copy_(goff[:, :8])
             gz4[:, 17:].copy_(goff[:, 10:])
-        # the 1x1-convolution gradients as per-sample library GEMMs on the native NCHW layout (measured on B200, 2048
-        # tiles: einsum over (b,h,w) took 21.4 + 7.7 ms)
-        fview = feature.contiguous().view(B, C, H * W)
+        # the 1x1-convolution parameter gradients: one pass over gz and the feature, contraction over the pixel index on
+        # tcgen05 (gen_tail_wgrad.cu); bf16 tensors (autocast) go through the library's tensor-core batched GEMM
         g_conv_b = g_conv_w = g_feat = None
-        if ctx.needs_input_grad[3]:
-            g_conv_b = gz.sum(dim=2, dtype=torch.float32).sum(dim=0).to(conv_w.dtype)
-        if ctx.needs_input_grad[2]:   # [B,25,HW] x [B,HW,C] -> [B,25,C] -> sum over the batch
-            g_conv_w = torch.bmm(gz, fview.transpose(1, 2)).sum(dim=0, dtype=torch.float32).to(conv_w.dtype)
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            if gz.dtype == torch.float32 and feature.dtype == torch.float32 and not _GEN_WGRAD_LIBRARY:
+                g_conv_w, g_conv_b = gen_tail_grad_params(gz.view(B, 25, H, W), feature, ctx.needs_input_grad[2],
+                                                          ctx.needs_input_grad[3])
+                g_conv_w = None if g_conv_w is None else g_conv_w.to(conv_w.dtype)
+                g_conv_b = None if g_conv_b is None else g_conv_b.to(conv_w.dtype)
+            else:
+                fview = feature.contiguous().view(B, C, H * W)
+                if ctx.needs_input_grad[3]:
+                    g_conv_b = gz.sum(dim=2, dtype=torch.float32).sum(dim=0).to(conv_w.dtype)
+                if ctx.needs_input_grad[2]:   # [B,25,HW] x [B,HW,C] -> [B,25,C] -> sum over the batch
+                    g_conv_w = torch.bmm(gz, fview.transpose(1, 2)).sum(dim=0, dtype=torch.float32).to(conv_w.dtype)
         if ctx.needs_input_grad[1]:   # [B,25,HW] x [25,C] -> [B,C,HW]: tensor-core kernel (gen_tail_backward.cu)
             g_feat = gen_tail_grad_feature(gz.view(B, 25, H, W), conv_w)
         if gw is not None:

@@ -30,7 +30,7 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 25, names
+    assert len(names) == 27, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in include/*.h but not exported"
@@ -76,7 +76,7 @@ def test_peer_argument_validation_needs_no_gpu(lib):
 
 def test_version_and_workspace(lib):
     h = lib.lib()
-    assert h.jspsr_version() == 105
+    assert h.jspsr_version() == 106
     assert 64 <= h.jspsr_spn_workspace_bytes() <= 4096
     assert h.jspsr_spn_host_scratch_bytes(2, 128, 128, 0) >= 2 * 2 * 128 * 128 * 4 * 29
 

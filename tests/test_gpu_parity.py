@@ -860,6 +860,44 @@ def test_generator_tail_grad_feature_kernel(jb, B, C, H, W):
     assert_close(gotb.float(), refb, 2.0 ** -8, "grad_feature bf16")
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 128, 128), (1, 64, 21, 200), (3, 128, 9, 36), (1, 64, 1, 4), (1, 128, 40, 136),
+                                     (5, 128, 128, 128), (2, 128, 7, 33), (40, 128, 128, 128)])
+def test_generator_tail_grad_params_kernel(jb, B, C, H, W):
+    """grad_conv_w = sum_pixels gz x feature and grad_conv_b = sum_pixels gz on tcgen05 (K = pixel index, 3-product tf32
+    split, short fp32 runs folded in fp64) against fp64; tolerance 1e-5 of the tensor's scale plus the random-walk
+    floor of an fp32 reduction.  H*W % 4 != 0 takes the bounds-checked loader, ragged H*W the zero-filled TMA tail."""
+    from jspsr_b200 import functional as F
+    rng = np.random.default_rng(170 + C + H * W + B)
+    gz = rng.normal(size=(B, 25, H, W)).astype(np.float32)
+    gz[:, 3] *= 1e-3                                  # rows of very different magnitude share one accumulator
+    feat = (rng.normal(size=(B, C, H, W)) + 0.5).astype(np.float32)   # non-zero mean: the sums do not cancel
+    ref_w = np.einsum("bjhw,bchw->jc", gz.astype(np.float64), feat.astype(np.float64))
+    ref_b = gz.astype(np.float64).sum(axis=(0, 2, 3))
+    for rep in range(2):                              # the second call finds the workspace zeroed by the first
+        gw, gb = F.gen_tail_grad_params(dev(gz), dev(feat))
+        for j in range(25):                           # per row: each row of the matrix is its own tensor scale
+            assert_close(gw[j], ref_w[j], FP32_TOL, f"grad_conv_w row {j} (call {rep})", gout=gz[:, j])
+        assert_close(gb, ref_b, FP32_TOL, f"grad_conv_b (call {rep})", gout=gz)
+    only_w, none_b = F.gen_tail_grad_params(dev(gz), dev(feat), need_b=False)
+    assert none_b is None and torch.equal(only_w, gw)
+    # linearity in gz (a size-independent property): the kernel of the sum is the sum of the kernels to rounding
+    gz2 = rng.normal(size=gz.shape).astype(np.float32)
+    a, _ = F.gen_tail_grad_params(dev(gz2), dev(feat))
+    both, _ = F.gen_tail_grad_params(dev(gz) + dev(gz2), dev(feat))
+    assert_close(both, (gw + a).double().cpu().numpy(), 2 * FP32_TOL, "grad_conv_w linearity", gout=gz)
+
+
+def test_generator_tail_grad_params_rejects(jb):
+    from jspsr_b200 import functional as F
+    gz = torch.randn(1, 25, 8, 8, device="cuda")
+    with pytest.raises(RuntimeError, match="C = 64 and C = 128"):
+        F.gen_tail_grad_params(gz, torch.randn(1, 32, 8, 8, device="cuda"))
+    with pytest.raises(RuntimeError, match="float32"):
+        F.gen_tail_grad_params(gz.bfloat16(), torch.randn(1, 64, 8, 8, device="cuda").bfloat16())
+    with pytest.raises(RuntimeError, match="feature must be"):
+        F.gen_tail_grad_params(gz, torch.randn(2, 64, 8, 8, device="cuda"))
+
+
 def test_generator_tail_kernels_capture_into_a_cuda_graph(jb):
     """The tcgen05 kernels only enqueue on the given stream (tensor maps are encoded on the host, nothing synchronises),
     so forward and feature gradient replay from a CUDA graph with identical results."""
