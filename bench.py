@@ -721,7 +721,7 @@ def side_numbers(torch, F, device, B):
 
         un = timed(unfused, n=3)
         # training step through the fused tail: forward (weight/offset written) + spn_backward_kernel in GEN_PREACT mode
-        # (writes the pre-activation gradients) + gen_grad_feature_kernel + the weight gradient as a library GEMM
+        # (writes the pre-activation gradients) + gen_grad_feature_kernel + gen_grad_weight_kernel (no library GEMM left)
         featg = feat.clone().requires_grad_()
         cwg, cbg = cw.clone().requires_grad_(), cb.clone().requires_grad_()
         wg, bg = w.clone().requires_grad_(), b.clone().requires_grad_()
@@ -748,6 +748,10 @@ def side_numbers(torch, F, device, B):
         tr_u = timed(train_unfused, n=2)
         gz = torch.randn(Bg, 25, TILE, TILE, device=device, generator=g_)
         gf = timed(lambda: F.gen_tail_grad_feature(gz, cw))
+        gp = timed(lambda: F.gen_tail_grad_params(gz, feat))          # weight + bias gradients, one pass (tcgen05)
+        F._GEN_WGRAD_LIBRARY = True                                   # the cuBLAS bmm + reduction the kernel replaced
+        tr_lib = timed(train_fused, n=3)
+        F._GEN_WGRAD_LIBRARY = False
         del featg, gout, gz
         torch.cuda.empty_cache()
         feat16 = feat.bfloat16()
@@ -757,6 +761,8 @@ def side_numbers(torch, F, device, B):
             "unfused_ms": un, "speedup_vs_unfused": un / fused,
             "training_step_ms": tr_f, "training_step_unfused_ms": tr_u, "training_speedup_vs_unfused": tr_u / tr_f,
             "grad_feature_kernel_ms": gf, "grad_feature_frac_of_hbm_peak": (100 + 4 * C) * npx / (gf * 1e-3) / 1e9 / peak,
+            "grad_params_kernel_ms": gp, "grad_params_frac_of_hbm_peak": (100 + 4 * C) * npx / (gp * 1e-3) / 1e9 / peak,
+            "training_step_ms_with_library_weight_gradient": tr_lib,
             "autocast_bf16_features": {"ms": fused16, "frac_of_hbm_peak": (C * 2 + 8) * npx / (fused16 * 1e-3) / 1e9 / peak,
                                        "ms_with_weight_offset_written": fused16_wo,
                                        "frac_of_hbm_peak_with_weight_offset_written":

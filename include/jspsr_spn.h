@@ -170,7 +170,8 @@ int jspsr_gen_tail_grad_feature(const void *gz, const float *conv_w, void *grad_
  * backward.  One pass over gz and feature, contraction over the pixel index on the tensor cores (tcgen05, tf32
  * 3-product split, short fp32 runs combined in fp64).  Either output may be NULL.  workspace: device memory of
  * jspsr_gen_tail_workspace_bytes() bytes, 16-byte aligned, ZERO on the first call; the kernel leaves it zero.
- * dtype JSPSR_F32 only; C = 64 or 128.
+ * dtype: JSPSR_F32, or JSPSR_BF16 for bf16 gz and feature (torch.autocast; exact in tf32, one product); the outputs are
+ * always fp32 (the parameters' dtype).  C = 64 or 128.
  */
 size_t jspsr_gen_tail_workspace_bytes(void);
 int jspsr_gen_tail_grad_params(const void *gz, const void *feature, float *grad_conv_w,

@@ -39,9 +39,9 @@ JSPSR_DECLARE_VARIANT(wide)
 namespace narrow {  // gen_tail_backward.cu / gen_tail_wgrad.cu stage no DEM tile: compiled once
 cudaError_t launch_gen_grad_feature(const LaunchArgs& la, const CUtensorMap& tmap_gz, const void* gz, int C,
                                     const float* conv_w, void* grad_feature);
-cudaError_t launch_gen_grad_weight(const void* gz, const void* feature, int C, float* grad_w, float* grad_b, void* ws, int B,
-                                   int HW, int run_len, bool use_tma, const CUtensorMap& tmap_f, const CUtensorMap& tmap_gz,
-                                   cudaStream_t stream);
+cudaError_t launch_gen_grad_weight(const void* gz, const void* feature, int C, bool bf16, float* grad_w, float* grad_b, void* ws,
+                                   int B, int HW, int run_len, bool use_tma, const CUtensorMap& tmap_f,
+                                   const CUtensorMap& tmap_gz, cudaStream_t stream);
 size_t gen_grad_weight_workspace_bytes();
 }
 }  // namespace jspsr
@@ -133,18 +133,20 @@ static bool make_feature_tmap(CUtensorMap* map, const void* feature, int B, int 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// TMA descriptor for a tensor viewed as [planes][H*W] fp32 (K-major operands of the weight-gradient contraction);
-// box = 32 consecutive pixels of `box_planes` planes
-static bool make_plane_tmap(CUtensorMap* map, const void* base, size_t planes, size_t HW, int box_planes, bool swizzle128) {
+// TMA descriptor for a tensor viewed as [planes][H*W] (K-major operands of the weight-gradient contraction);
+// box = 128 bytes of consecutive pixels of `box_planes` planes
+static bool make_plane_tmap(CUtensorMap* map, const void* base, size_t planes, size_t HW, int box_planes, bool swizzle128,
+                            bool bf16) {
     if (tma_disabled_by_env()) return false;
-    if (((uintptr_t)base & 15) != 0 || (HW * 4) % 16 != 0 || box_planes > 256 || planes > 0xffffffffull) return false;
+    const size_t es = bf16 ? 2 : 4;
+    if (((uintptr_t)base & 15) != 0 || (HW * es) % 16 != 0 || box_planes > 256 || planes > 0xffffffffull) return false;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)planes};
-    cuuint64_t strides[1] = {(cuuint64_t)HW * 4};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_planes};
+    cuuint64_t strides[1] = {(cuuint64_t)HW * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_planes};
     cuuint32_t estr[2] = {1u, 1u};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+    return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -478,27 +480,28 @@ size_t jspsr_gen_tail_workspace_bytes(void) { return narrow::gen_grad_weight_wor
 int jspsr_gen_tail_grad_params(const void* gz, const void* feature, float* grad_conv_w, float* grad_conv_b, void* workspace,
                                int B, int C, int H, int W, int dtype, void* stream) {
     if (int e = check_common(B, H, W, 0, dtype)) return e;
-    if (dtype != JSPSR_F32)
-        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_tail_grad_params is instantiated for fp32 gz / feature (dtype 0)");
+    if (dtype == JSPSR_MIXED) return fail(JSPSR_ERR_BAD_ARG, "jspsr_gen_tail_grad_params: dtype is 0 (f32) or 1 (bf16)");
+    const bool bf16 = dtype == JSPSR_BF16;
+    const size_t es = bf16 ? 2 : 4;
     if (C != 64 && C != 128)
         return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_gen_tail_grad_params is instantiated for C = 64 and C = 128, got C = %d", C);
     if (!gz || !feature || !workspace || (!grad_conv_w && !grad_conv_b)) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
-    if (int e = check_align(gz, 4, "gz")) return e;
-    if (int e = check_align(feature, 4, "feature")) return e;
+    if (int e = check_align(gz, es, "gz")) return e;
+    if (int e = check_align(feature, es, "feature")) return e;
     if (int e = check_align(grad_conv_w, 4, "grad_conv_w")) return e;
     if (int e = check_align(grad_conv_b, 4, "grad_conv_b")) return e;
     if (int e = check_align(workspace, 16, "workspace")) return e;
     const size_t HW = (size_t)H * W;
     if (HW > 0x7fffffffull) return fail(JSPSR_ERR_UNSUPPORTED, "H * W = %zu exceeds 2^31 - 1", HW);
-    int run_len = 4;   // K-blocks of 32 pixels per fp32 accumulation run (JSPSR_GEN_WGRAD_RUN overrides: measurements)
+    int run_len = 4;   // K-blocks (128 bytes of pixels per plane) per fp32 accumulation run (JSPSR_GEN_WGRAD_RUN overrides: measurements)
     if (const char* e = getenv("JSPSR_GEN_WGRAD_RUN")) {
         const int v = atoi(e);
         if (v >= 2 && v <= (1 << 20)) run_len = v;
     }
     CUtensorMap tmap_f{}, tmap_gz{};
-    const bool use_tma = make_plane_tmap(&tmap_f, feature, (size_t)B * C, HW, C, true) &&
-                         make_plane_tmap(&tmap_gz, gz, (size_t)B * 25, HW, 25, false);
-    cudaError_t ce = narrow::launch_gen_grad_weight(gz, feature, C, grad_conv_w, grad_conv_b, workspace, B, (int)HW, run_len,
+    const bool use_tma = make_plane_tmap(&tmap_f, feature, (size_t)B * C, HW, C, true, bf16) &&
+                         make_plane_tmap(&tmap_gz, gz, (size_t)B * 25, HW, 25, false, bf16);
+    cudaError_t ce = narrow::launch_gen_grad_weight(gz, feature, C, bf16, grad_conv_w, grad_conv_b, workspace, B, (int)HW, run_len,
                                                     use_tma, tmap_f, tmap_gz, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "gen_grad_weight launch");
     return JSPSR_OK;

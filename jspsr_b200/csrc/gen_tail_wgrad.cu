@@ -32,11 +32,12 @@
 namespace jspsr {
 inline namespace JSPSR_VARIANT {
 
-constexpr int GW_KB = 32;          // pixels per K-block: one 128-byte row of every plane
+constexpr int GW_ROW_BYTES = 128;  // a K-block is one 128-byte row of every plane: 32 fp32 / 64 bf16 pixels
 constexpr int GW_STAGES = 4;
 constexpr int GW_N = 32;           // MMA N: 25 rows of gz, zero padded
 constexpr int GW_GZ_BYTES = 4096;  // ring bytes reserved for the gz box (25 x 128 used; keeps the stages 1024-byte aligned)
-constexpr int GW_B_BYTES = GW_N * GW_KB * 4;
+template <typename FT> constexpr int gw_kb() { return GW_ROW_BYTES / (int)sizeof(FT); }   // pixels per K-block
+template <typename FT> constexpr int gw_b_bytes() { return GW_N * gw_kb<FT>() * 4; }        // one B buffer (tf32)
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -59,24 +60,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ws layout (doubles): [25 * C] weight sums | [32] bias sums | ticket (one 8-byte word)
-template <int C, bool TMA>
+// FT = float: hi / lo split of both operands, three products.  FT = __nv_bfloat16 (torch.autocast: Generator.block emits
+// bf16 and the backward kernel writes bf16 gradients): every value is exact in tf32, one product, 64 pixels per K-block.
+template <typename FT, int C, bool TMA>
 __global__ void __launch_bounds__(GEN_CTA_THREADS, 2)
-gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ feature, float* __restrict__ grad_w,
+gen_grad_weight_kernel(const FT* __restrict__ gz, const FT* __restrict__ feature, float* __restrict__ grad_w,
                        float* __restrict__ grad_b, double* __restrict__ ws, const long long n_blocks,
                        const int blocks_per_sample, const int HW, const int run_len,
                        const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_gz) {
-    constexpr int F_BYTES = C * GW_KB * 4, STAGE_BYTES = F_BYTES + GW_GZ_BYTES;
+    constexpr bool F16 = sizeof(FT) == 2;
+    constexpr int GW_KB = gw_kb<FT>(), GW_B_BYTES = gw_b_bytes<FT>();
+    constexpr int F_BYTES = C * GW_ROW_BYTES, STAGE_BYTES = F_BYTES + GW_GZ_BYTES;
     constexpr int RING_BYTES = TMA ? GW_STAGES * STAGE_BYTES : 0;
     constexpr uint32_t SBO = 128, LBO = GW_N / 8 * 128;         // K-major, no swizzle: 8-row groups / 16-byte K chunks of B
-    constexpr uint32_t A_BUF = 2 * GW_KB, COL_LO = GW_KB, COL_ACC = 2 * A_BUF, TMEM_COLS = 256;
+    // A buffer: fp32 = 32 hi + 32 lo columns, bf16 = 64 exact columns
+    constexpr uint32_t A_BUF = 64, COL_LO = 32, COL_ACC = 2 * A_BUF, TMEM_COLS = 256;
     // instruction descriptor: D fp32 | A, B tf32 | both K-major | N = 32 | M = 128
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GW_N >> 3) << 17) | ((GEN_THREADS >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char dsm_raw[];
     // SWIZZLE_128B boxes want a 1024-byte aligned destination: align by hand (the launch reserves the slack)
     unsigned char* dsm = dsm_raw + ((1024u - (smem_u32(dsm_raw) & 1023u)) & 1023u);
     unsigned char* ring = dsm;                         // [GW_STAGES][ feature C x 128 B (swizzled) | gz 25 x 128 B ]
-    unsigned char* b_hi = dsm + RING_BYTES;            // [2][32 x 32] tf32, core-matrix layout
-    unsigned char* b_lo = b_hi + 2 * GW_B_BYTES;
+    unsigned char* b_hi = dsm + RING_BYTES;            // [2][32 rows x GW_KB] tf32, core-matrix layout
+    unsigned char* b_lo = b_hi + 2 * GW_B_BYTES;       // fp32 only
     __shared__ __align__(8) uint64_t bar_full[GW_STAGES], bar_empty[GW_STAGES], bar_a_full[2], bar_b_full[2], bar_ab_free[2],
         bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
@@ -107,7 +113,8 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // rows 25..31 of the B operand stay zero for the whole kernel
-    for (int i = t; i < 4 * GW_B_BYTES / 16; i += GEN_CTA_THREADS) reinterpret_cast<float4*>(b_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < (F16 ? 2 : 4) * GW_B_BYTES / 16; i += GEN_CTA_THREADS)
+        reinterpret_cast<float4*>(b_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -122,7 +129,7 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
                 if (i >= GW_STAGES) mbar_wait(&bar_empty[s], (uint32_t)(((i / GW_STAGES) - 1) & 1));
                 const long long kb = kb0 + i;
                 const int b = (int)(kb / blocks_per_sample), pix0 = (int)(kb % blocks_per_sample) * GW_KB;
-                mbar_arrive_expect_tx(&bar_full[s], F_BYTES + GEN_NOUT * GW_KB * 4);
+                mbar_arrive_expect_tx(&bar_full[s], F_BYTES + GEN_NOUT * GW_ROW_BYTES);
                 tma_load_2d(ring + s * STAGE_BYTES, &tmap_f, &bar_full[s], pix0, b * C);
                 tma_load_2d(ring + s * STAGE_BYTES + F_BYTES, &tmap_gz, &bar_full[s], pix0, b * GEN_NOUT);
             }
@@ -143,10 +150,12 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
 #pragma unroll
             for (int ks = 0; ks < GW_KB / 8; ++ks) {
                 const uint64_t dbh = umma_desc_kmajor(smem_u32(b_hi) + p * GW_B_BYTES + ks * 2 * LBO, LBO, SBO);
-                const uint64_t dbl = umma_desc_kmajor(smem_u32(b_lo) + p * GW_B_BYTES + ks * 2 * LBO, LBO, SBO);
                 umma_tf32_ts(d_tmem, a_tmem + ks * 8, dbh, IDESC, (first && ks == 0) ? 0u : 1u);
-                umma_tf32_ts(d_tmem, a_tmem + COL_LO + ks * 8, dbh, IDESC, 1u);
-                umma_tf32_ts(d_tmem, a_tmem + ks * 8, dbl, IDESC, 1u);
+                if (!F16) {
+                    const uint64_t dbl = umma_desc_kmajor(smem_u32(b_lo) + p * GW_B_BYTES + ks * 2 * LBO, LBO, SBO);
+                    umma_tf32_ts(d_tmem, a_tmem + COL_LO + ks * 8, dbh, IDESC, 1u);
+                    umma_tf32_ts(d_tmem, a_tmem + ks * 8, dbl, IDESC, 1u);
+                }
             }
             umma_commit(&bar_ab_free[p]);
             if (last) {
@@ -171,36 +180,53 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const uint32_t a_lane = lane_tmem + (uint32_t)p * A_BUF;
-            const unsigned char* row = ring + s * STAGE_BYTES + c * (GW_KB * 4);
+            const unsigned char* row = ring + s * STAGE_BYTES + c * GW_ROW_BYTES;
             const long long kb = kb0 + i;
             const int b = (int)(kb / blocks_per_sample), pix0 = (int)(kb % blocks_per_sample) * GW_KB;
-            const float* gp = feature + ((size_t)b * C + (c < C ? c : 0)) * (size_t)HW + pix0;
+            const FT* gp = feature + ((size_t)b * C + (c < C ? c : 0)) * (size_t)HW + pix0;
 #pragma unroll
-            for (int k0 = 0; k0 < GW_KB; k0 += 16) {
-                float hi[16], lo[16];
+            for (int k0 = 0; k0 < GW_KB; k0 += 16) {  // 16 pixels = 4 (fp32) / 2 (bf16) 16-byte chunks of the row
+                float v[16];
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < C) {
-                        if (TMA) {  // SWIZZLE_128B: 16-byte chunk q of row r lives at chunk q ^ (r & 7)
-                            v = *reinterpret_cast<const float4*>(row + ((((k0 >> 2) + j4) ^ (c & 7)) << 4));
-                        } else {
-                            const int k = k0 + 4 * j4;
-                            if (pix0 + k < HW) v.x = ld_stream(gp + k);
-                            if (pix0 + k + 1 < HW) v.y = ld_stream(gp + k + 1);
-                            if (pix0 + k + 2 < HW) v.z = ld_stream(gp + k + 2);
-                            if (pix0 + k + 3 < HW) v.w = ld_stream(gp + k + 3);
+                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                if (c < C) {
+                    if (TMA) {  // SWIZZLE_128B: 16-byte chunk q of row r lives at chunk q ^ (r & 7)
+                        constexpr int PER = 16 / (int)sizeof(FT);  // pixels per chunk
+#pragma unroll
+                        for (int q = 0; q < 16 / PER; ++q) {
+                            const uint4 raw = *reinterpret_cast<const uint4*>(row + (((k0 / PER + q) ^ (c & 7)) << 4));
+                            if (F16) {  // a bf16 is the upper half of its fp32
+                                const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[q * PER + 2 * e] = __uint_as_float(wds[e] << 16);
+                                    v[q * PER + 2 * e + 1] = __uint_as_float(wds[e] & 0xFFFF0000u);
+                                }
+                            } else {
+                                v[q * PER] = __uint_as_float(raw.x);
+                                v[q * PER + 1] = __uint_as_float(raw.y);
+                                v[q * PER + 2] = __uint_as_float(raw.z);
+                                v[q * PER + 3] = __uint_as_float(raw.w);
+                            }
                         }
-                    }
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        hi[4 * j4 + e] = tf32_rn(vv[e]);
-                        lo[4 * j4 + e] = vv[e] - hi[4 * j4 + e];
+                        for (int e = 0; e < 16; ++e)
+                            if (pix0 + k0 + e < HW) v[e] = to_f32(ld_stream(gp + k0 + e));
                     }
                 }
-                tmem_st16(a_lane + k0, hi);
-                tmem_st16(a_lane + COL_LO + k0, lo);
+                if (F16) {
+                    tmem_st16(a_lane + k0, v);
+                } else {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        hi[e] = tf32_rn(v[e]);
+                        lo[e] = v[e] - hi[e];
+                    }
+                    tmem_st16(a_lane + k0, hi);
+                    tmem_st16(a_lane + COL_LO + k0, lo);
+                }
             }
             if (TMA) mbar_arrive(&bar_empty[s]);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -209,7 +235,8 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
         }
     } else {
         // =========================== gz producers + accumulator folding ===========================
-        const int j = t >> 2, q4 = t & 3;  // row of gz / 8-pixel quarter of the K-block handled by this thread
+        const int j = t >> 2, q4 = t & 3;  // row of gz / quarter (32 bytes) of the K-block's row handled by this thread
+        constexpr int QP = GW_KB / 4;      // pixels per quarter: 8 (fp32) / 16 (bf16)
         const uint32_t boff = (uint32_t)((j >> 3) * SBO + (j & 7) * 16);
         const uint32_t acc_lane = tmem + ((uint32_t)(warp * 32) << 16) + COL_ACC;
         double tot[GEN_NOUT];  // thread = channel t: its 25 weight-gradient totals
@@ -244,30 +271,45 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
             if (i >= 2) mbar_wait(&bar_ab_free[p], (uint32_t)(((i >> 1) - 1) & 1));
             float part = 0.f;
             if (j < GEN_NOUT) {
-                float4 v0, v1;
+                float e[QP];
                 if (TMA) {
-                    const unsigned char* src = ring + s * STAGE_BYTES + F_BYTES + j * (GW_KB * 4) + q4 * 32;
-                    v0 = *reinterpret_cast<const float4*>(src);
-                    v1 = *reinterpret_cast<const float4*>(src + 16);
+                    const unsigned char* src = ring + s * STAGE_BYTES + F_BYTES + j * GW_ROW_BYTES + q4 * 32;
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(src), r1 = *reinterpret_cast<const uint4*>(src + 16);
+                    const uint32_t wds[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (F16) {
+                            e[2 * k] = __uint_as_float(wds[k] << 16);
+                            e[2 * k + 1] = __uint_as_float(wds[k] & 0xFFFF0000u);
+                        } else {
+                            e[k] = __uint_as_float(wds[k]);
+                        }
+                    }
                 } else {
                     const long long kb = kb0 + i;
-                    const int b = (int)(kb / blocks_per_sample), pix = (int)(kb % blocks_per_sample) * GW_KB + q4 * 8;
-                    const float* gp = gz + ((size_t)b * GEN_NOUT + j) * (size_t)HW + pix;
-                    float e[8];
+                    const int b = (int)(kb / blocks_per_sample), pix = (int)(kb % blocks_per_sample) * GW_KB + q4 * QP;
+                    const FT* gp = gz + ((size_t)b * GEN_NOUT + j) * (size_t)HW + pix;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) e[k] = pix + k < HW ? ld_stream(gp + k) : 0.f;
-                    v0 = make_float4(e[0], e[1], e[2], e[3]);
-                    v1 = make_float4(e[4], e[5], e[6], e[7]);
+                    for (int k = 0; k < QP; ++k) e[k] = pix + k < HW ? to_f32(ld_stream(gp + k)) : 0.f;
                 }
-                part = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
-                const float4 h0 = make_float4(tf32_rn(v0.x), tf32_rn(v0.y), tf32_rn(v0.z), tf32_rn(v0.w));
-                const float4 h1 = make_float4(tf32_rn(v1.x), tf32_rn(v1.y), tf32_rn(v1.z), tf32_rn(v1.w));
-                unsigned char* dh = b_hi + p * GW_B_BYTES + boff + (2 * q4) * LBO;
-                unsigned char* dl = b_lo + p * GW_B_BYTES + boff + (2 * q4) * LBO;
-                *reinterpret_cast<float4*>(dh) = h0;
-                *reinterpret_cast<float4*>(dh + LBO) = h1;
-                *reinterpret_cast<float4*>(dl) = make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w);
-                *reinterpret_cast<float4*>(dl + LBO) = make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w);
+#pragma unroll
+                for (int k = 0; k < QP; k += 8)
+                    part += ((e[k] + e[k + 1]) + (e[k + 2] + e[k + 3])) + ((e[k + 4] + e[k + 5]) + (e[k + 6] + e[k + 7]));
+                // K-major core matrices: 4 consecutive pixels of row j = one 16-byte chunk; this thread owns chunks
+                // q4 * QP / 4 ... of the block
+                unsigned char* dh = b_hi + p * GW_B_BYTES + boff + (q4 * (QP / 4)) * LBO;
+                unsigned char* dl = b_lo + p * GW_B_BYTES + boff + (q4 * (QP / 4)) * LBO;
+#pragma unroll
+                for (int k = 0; k < QP; k += 4) {
+                    if (F16) {
+                        *reinterpret_cast<float4*>(dh + (k / 4) * LBO) = make_float4(e[k], e[k + 1], e[k + 2], e[k + 3]);
+                    } else {
+                        const float4 hh = make_float4(tf32_rn(e[k]), tf32_rn(e[k + 1]), tf32_rn(e[k + 2]), tf32_rn(e[k + 3]));
+                        *reinterpret_cast<float4*>(dh + (k / 4) * LBO) = hh;
+                        *reinterpret_cast<float4*>(dl + (k / 4) * LBO) =
+                            make_float4(e[k] - hh.x, e[k + 1] - hh.y, e[k + 2] - hh.z, e[k + 3] - hh.w);
+                    }
+                }
             }
             if (TMA) mbar_arrive(&bar_empty[s]);
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
@@ -325,43 +367,51 @@ gen_grad_weight_kernel(const float* __restrict__ gz, const float* __restrict__ f
 
 size_t gen_grad_weight_workspace_bytes() { return (size_t)(GEN_NOUT * 128 + 32 + 1) * sizeof(double); }
 
-template <int C, bool TMA>
-static cudaError_t launch_gw(const float* gz, const float* feature, float* grad_w, float* grad_b, void* ws, int B, int HW,
+template <typename FT, int C, bool TMA>
+static cudaError_t launch_gw(const void* gz, const void* feature, float* grad_w, float* grad_b, void* ws, int B, int HW,
                              int run_len, const CUtensorMap& tmap_f, const CUtensorMap& tmap_gz, cudaStream_t stream) {
     // two CTAs per SM by construction: 256 of the SM's 512 TMEM columns each; the request is padded for the ring-less
     // instantiation so that a third CTA can never become resident and spin in tcgen05.alloc
-    size_t dyn = (TMA ? (size_t)GW_STAGES * (C * GW_KB * 4 + GW_GZ_BYTES) : 0) + 4 * GW_B_BYTES + 1024;  // + alignment slack
+    constexpr int KB = gw_kb<FT>();
+    size_t dyn = (TMA ? (size_t)GW_STAGES * (C * GW_ROW_BYTES + GW_GZ_BYTES) : 0) + 4 * gw_b_bytes<float>() + 1024;  // + alignment slack
     if (dyn < (size_t)76 * 1024) dyn = (size_t)76 * 1024;
-    const cudaError_t attr = ensure_dynamic_smem((const void*)gen_grad_weight_kernel<C, TMA>, dyn);
+    const cudaError_t attr = ensure_dynamic_smem((const void*)gen_grad_weight_kernel<FT, C, TMA>, dyn);
     if (attr != cudaSuccess) return attr;
-    const int bps = (HW + GW_KB - 1) / GW_KB;
+    const int bps = (HW + KB - 1) / KB;
     const long long n_blocks = (long long)B * bps;
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long want = (long long)2 * sms;
     const unsigned grid = (unsigned)(n_blocks < want ? n_blocks : want);
-    gen_grad_weight_kernel<C, TMA><<<grid, GEN_CTA_THREADS, dyn, stream>>>(gz, feature, grad_w, grad_b, (double*)ws, n_blocks,
-                                                                          bps, HW, run_len, tmap_f, tmap_gz);
+    gen_grad_weight_kernel<FT, C, TMA><<<grid, GEN_CTA_THREADS, dyn, stream>>>((const FT*)gz, (const FT*)feature, grad_w, grad_b,
+                                                                              (double*)ws, n_blocks, bps, HW, run_len, tmap_f,
+                                                                              tmap_gz);
     return cudaGetLastError();
 }
-
-// use_tma: tmap_f ([B*C planes][HW], box [C][32], SWIZZLE_128B) and tmap_gz ([B*25 planes][HW], box [25][32]) are valid
-cudaError_t launch_gen_grad_weight(const void* gz, const void* feature, int C, float* grad_w, float* grad_b, void* ws, int B,
-                                   int HW, int run_len, bool use_tma, const CUtensorMap& tmap_f, const CUtensorMap& tmap_gz,
-                                   cudaStream_t stream) {
-    if (run_len < 2) run_len = 2;  // a run is folded one block after it closes: two accumulators need runs of >= 2 blocks
-    const float* g = (const float*)gz;
-    const float* f = (const float*)feature;
+template <typename FT>
+static cudaError_t launch_gw_c(const void* gz, const void* feature, int C, float* grad_w, float* grad_b, void* ws, int B, int HW,
+                               int run_len, bool use_tma, const CUtensorMap& tmap_f, const CUtensorMap& tmap_gz,
+                               cudaStream_t stream) {
     if (C == 128) {
-        return use_tma ? launch_gw<128, true>(g, f, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream)
-                       : launch_gw<128, false>(g, f, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream);
+        return use_tma ? launch_gw<FT, 128, true>(gz, feature, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream)
+                       : launch_gw<FT, 128, false>(gz, feature, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream);
     }
     if (C == 64) {
-        return use_tma ? launch_gw<64, true>(g, f, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream)
-                       : launch_gw<64, false>(g, f, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream);
+        return use_tma ? launch_gw<FT, 64, true>(gz, feature, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream)
+                       : launch_gw<FT, 64, false>(gz, feature, grad_w, grad_b, ws, B, HW, run_len, tmap_f, tmap_gz, stream);
     }
     return cudaErrorInvalidValue;
+}
+
+// use_tma: tmap_f ([B*C planes][HW], box [C][128 bytes], SWIZZLE_128B) and tmap_gz ([B*25 planes][HW], box [25][128 bytes])
+// are valid; bf16: gz and feature are bf16 (64 pixels per K-block)
+cudaError_t launch_gen_grad_weight(const void* gz, const void* feature, int C, bool bf16, float* grad_w, float* grad_b, void* ws,
+                                   int B, int HW, int run_len, bool use_tma, const CUtensorMap& tmap_f,
+                                   const CUtensorMap& tmap_gz, cudaStream_t stream) {
+    if (run_len < 2) run_len = 2;  // a run is folded one block after it closes: two accumulators need runs of >= 2 blocks
+    if (bf16) return launch_gw_c<__nv_bfloat16>(gz, feature, C, grad_w, grad_b, ws, B, HW, run_len, use_tma, tmap_f, tmap_gz, stream);
+    return launch_gw_c<float>(gz, feature, C, grad_w, grad_b, ws, B, HW, run_len, use_tma, tmap_f, tmap_gz, stream);
 }
 
 }  // namespace JSPSR_VARIANT

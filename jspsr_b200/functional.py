@@ -273,15 +273,16 @@ _GEN_WGRAD_LIBRARY = False   # measurements only (tools/gen_train_time.py): the 
 def gen_tail_grad_params(gz, feature, need_w: bool = True, need_b: bool = True):
     """(grad_conv_w [25,C], grad_conv_b [25]) = (sum_{b,y,x} gz[b,j,y,x] * feature[b,c,y,x], sum_{b,y,x} gz[b,j,y,x]):
     the weight / bias gradients of the Generator tail's two 1x1 convolutions (spn.py:41-52) in one pass over gz and
-    feature (gen_tail_wgrad.cu: contraction over the pixel index on tcgen05).  fp32 tensors."""
+    feature (gen_tail_wgrad.cu: contraction over the pixel index on tcgen05).  fp32 or bf16 tensors, fp32 results."""
     _require_cuda(gz, feature)
     if gz.dim() != 4 or gz.shape[1] != 25:
         raise RuntimeError(f"gz must be [B,25,H,W], got {tuple(gz.shape)}")
     B, _, H, W = gz.shape
     if feature.dim() != 4 or feature.shape[0] != B or tuple(feature.shape[2:]) != (H, W):
         raise RuntimeError(f"feature must be [B,C,H,W] with B, H, W = {(B, H, W)}, got {tuple(feature.shape)}")
-    if gz.dtype != torch.float32 or feature.dtype != torch.float32:
-        raise RuntimeError("gen_tail_grad_params takes float32 gz and feature")
+    if gz.dtype != feature.dtype or gz.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"gen_tail_grad_params takes gz and feature in one dtype, float32 or bfloat16; got {gz.dtype}, "
+                           f"{feature.dtype}")
     C = feature.shape[1]
     gz, feature = gz.contiguous(), feature.contiguous()
     key = (gz.device.index, _stream_ptr(gz))
@@ -293,7 +294,7 @@ def gen_tail_grad_params(gz, feature, need_w: bool = True, need_b: bool = True):
     gb = torch.empty(25, dtype=torch.float32, device=gz.device) if need_b else None
     with torch.cuda.device(gz.device):
         rc = _lib.lib().jspsr_gen_tail_grad_params(_ptr(gz), _ptr(feature), _ptr(gw), _ptr(gb), _ptr(ws), B, C, H, W,
-                                                   F32, _stream_ptr(gz))
+                                                   _dtype_code(gz), _stream_ptr(gz))
     _lib.check(rc, "jspsr_gen_tail_grad_params")
     _count()
     return gw, gb
@@ -454,20 +455,19 @@ class _GenPropagate(torch.autograd.Function):
             gz4[:, 9:17].copy_(goff[:, :8])
             gz4[:, 17:].copy_(goff[:, 10:])
         # the 1x1-convolution parameter gradients: one pass over gz and the feature, contraction over the pixel index on
-        # tcgen05 (gen_tail_wgrad.cu); bf16 tensors (autocast) go through the library's tensor-core batched GEMM
+        # tcgen05 (gen_tail_wgrad.cu)
         g_conv_b = g_conv_w = g_feat = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            if gz.dtype == torch.float32 and feature.dtype == torch.float32 and not _GEN_WGRAD_LIBRARY:
-                g_conv_w, g_conv_b = gen_tail_grad_params(gz.view(B, 25, H, W), feature, ctx.needs_input_grad[2],
+            if _GEN_WGRAD_LIBRARY:   # measurements only: the cuBLAS batched GEMM + reduction pass the kernel replaced
+                fview = feature.contiguous().view(B, C, H * W)
+                g_conv_b = gz.sum(dim=2, dtype=torch.float32).sum(dim=0).to(conv_w.dtype)
+                g_conv_w = torch.bmm(gz, fview.transpose(1, 2)).sum(dim=0, dtype=torch.float32).to(conv_w.dtype)
+            else:
+                f_ = feature if feature.dtype == gz.dtype else feature.to(gz.dtype)
+                g_conv_w, g_conv_b = gen_tail_grad_params(gz.view(B, 25, H, W), f_, ctx.needs_input_grad[2],
                                                           ctx.needs_input_grad[3])
                 g_conv_w = None if g_conv_w is None else g_conv_w.to(conv_w.dtype)
                 g_conv_b = None if g_conv_b is None else g_conv_b.to(conv_w.dtype)
-            else:
-                fview = feature.contiguous().view(B, C, H * W)
-                if ctx.needs_input_grad[3]:
-                    g_conv_b = gz.sum(dim=2, dtype=torch.float32).sum(dim=0).to(conv_w.dtype)
-                if ctx.needs_input_grad[2]:   # [B,25,HW] x [B,HW,C] -> [B,25,C] -> sum over the batch
-                    g_conv_w = torch.bmm(gz, fview.transpose(1, 2)).sum(dim=0, dtype=torch.float32).to(conv_w.dtype)
         if ctx.needs_input_grad[1]:   # [B,25,HW] x [25,C] -> [B,C,HW]: tensor-core kernel (gen_tail_backward.cu)
             g_feat = gen_tail_grad_feature(gz.view(B, 25, H, W), conv_w)
         if gw is not None:

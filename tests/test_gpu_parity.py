@@ -878,6 +878,15 @@ def test_generator_tail_grad_params_kernel(jb, B, C, H, W):
         for j in range(25):                           # per row: each row of the matrix is its own tensor scale
             assert_close(gw[j], ref_w[j], FP32_TOL, f"grad_conv_w row {j} (call {rep})", gout=gz[:, j])
         assert_close(gb, ref_b, FP32_TOL, f"grad_conv_b (call {rep})", gout=gz)
+    # bf16 operands (torch.autocast): exact in tf32, one product per K-step, 64-pixel blocks; fp32 results
+    gzb, fb = dev(gz).bfloat16(), dev(feat).bfloat16()
+    refb_w = np.einsum("bjhw,bchw->jc", gzb.double().cpu().numpy(), fb.double().cpu().numpy())
+    refb_b = gzb.double().cpu().numpy().sum(axis=(0, 2, 3))
+    gwb, gbb = F.gen_tail_grad_params(gzb, fb)
+    assert gwb.dtype == torch.float32 and gbb.dtype == torch.float32
+    for j in range(25):
+        assert_close(gwb[j], refb_w[j], FP32_TOL, f"grad_conv_w row {j} (bf16 operands)", gout=gz[:, j])
+    assert_close(gbb, refb_b, FP32_TOL, "grad_conv_b (bf16 operands)", gout=gz)
     only_w, none_b = F.gen_tail_grad_params(dev(gz), dev(feat), need_b=False)
     assert none_b is None and torch.equal(only_w, gw)
     # linearity in gz (a size-independent property): the kernel of the sum is the sum of the kernels to rounding
@@ -892,8 +901,8 @@ def test_generator_tail_grad_params_rejects(jb):
     gz = torch.randn(1, 25, 8, 8, device="cuda")
     with pytest.raises(RuntimeError, match="C = 64 and C = 128"):
         F.gen_tail_grad_params(gz, torch.randn(1, 32, 8, 8, device="cuda"))
-    with pytest.raises(RuntimeError, match="float32"):
-        F.gen_tail_grad_params(gz.bfloat16(), torch.randn(1, 64, 8, 8, device="cuda").bfloat16())
+    with pytest.raises(RuntimeError, match="one dtype"):
+        F.gen_tail_grad_params(gz.bfloat16(), torch.randn(1, 64, 8, 8, device="cuda"))
     with pytest.raises(RuntimeError, match="feature must be"):
         F.gen_tail_grad_params(gz, torch.randn(2, 64, 8, 8, device="cuda"))
 
