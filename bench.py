@@ -688,6 +688,19 @@ def side_numbers(torch, F, device, B):
                             "frac_of_hbm_peak_compulsory": (4 + 108 + 4 * T) * npix / (it * 1e-3) / 1e9 / peak,
                             "frac_of_hbm_peak_as_run": 116 * T * npix / (it * 1e-3) / 1e9 / peak,
                             "note": "T launches of the forward kernel, all T outputs kept"}
+    # the single-launch form (one 16-CTA cluster per sample, tap state in registers, feature in distributed shared memory)
+    os.environ["JSPSR_SPN_ITER_FUSED"] = "1"
+    try:
+        fused = F.spn_iterate(init, aff, offset, T)
+        itf = timed(lambda: F.spn_iterate(init, aff, offset, T), n=3)
+    finally:
+        os.environ.pop("JSPSR_SPN_ITER_FUSED", None)
+    same = bool(torch.equal(fused, F.spn_iterate(init, aff, offset, T)))
+    del fused
+    out["nlspn_loop_T6"]["fused_single_launch"] = {
+        "ms": itf, "bit_identical_to_T_launches": same,
+        "frac_of_hbm_peak_compulsory": (4 + 108 + 4 * T) * npix / (itf * 1e-3) / 1e9 / peak,
+        "note": "JSPSR_SPN_ITER_FUSED=1 (spn_iterate_fused.cu); the default is whichever of the two is faster here"}
     del aff, gout, weight, offset
     torch.cuda.empty_cache()
     # the Generator's last two layers (1x1 convolutions C -> 9 / 16, sigmoid, zero centre

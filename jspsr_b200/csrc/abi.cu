@@ -43,6 +43,8 @@ cudaError_t launch_gen_grad_weight(const void* gz, const void* feature, int C, b
                                    int B, int HW, int run_len, bool use_tma, const CUtensorMap& tmap_f,
                                    const CUtensorMap& tmap_gz, cudaStream_t stream);
 size_t gen_grad_weight_workspace_bytes();
+cudaError_t launch_spn_iterate_fused(const float* feat_init, const float* aff, const float* offset, float* list_out, int B,
+                                     int H, int W, int T, cudaStream_t stream);
 }
 }  // namespace jspsr
 
@@ -528,6 +530,18 @@ int jspsr_spn_iterate(const void* feat_init, const void* aff, const void* offset
     if (feat_fix && !scratch) return fail(JSPSR_ERR_BAD_ARG, "preserve_input needs a [B,1,H,W] scratch buffer");
     const bool bf16 = dtype == JSPSR_BF16;
     const size_t es = bf16 ? 2 : 4, px = (size_t)H * W, n = (size_t)B * px;
+    // Optional single-launch form (JSPSR_SPN_ITER_FUSED=1): one 16-CTA cluster per sample keeps the iteration-invariant
+    // tap state in registers and the feature in (distributed) shared memory for all T applications
+    // (spn_iterate_fused.cu; bit-identical results).  OFF by default: measured on B200 it does not beat T launches - the
+    // shared-memory gather, not HBM, bounds an application.
+    if (const char* e = getenv("JSPSR_SPN_ITER_FUSED")) {
+        if (e[0] == '1' && !bf16 && !feat_fix && T >= 2 && H <= 128 && W <= 128) {
+            cudaError_t ce = narrow::launch_spn_iterate_fused((const float*)feat_init, (const float*)aff, (const float*)offset,
+                                                              (float*)list_out, B, H, W, T, (cudaStream_t)stream);
+            if (ce == cudaSuccess) return JSPSR_OK;
+            if (ce != cudaErrorNotSupported) return cuda_fail(ce, "spn_iterate_fused launch");
+        }
+    }
     // Optional L2 blocking (JSPSR_SPN_ITER_CHUNK_MB > 0): run all T steps on one chunk of samples whose
     // affinities/offsets fit the L2 before moving on.  OFF by default: measured on B200 (tools/iter_bench.py,
     // 4096 tiles, T = 6) the dependent, sub-wave launches it creates are 1.6-2.8x SLOWER than T full-batch

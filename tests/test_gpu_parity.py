@@ -986,6 +986,33 @@ def test_generator_tail_tma_and_manual_paths_agree_bitwise(jb):
                 assert torch.equal(a_, b_), C
 
 
+@pytest.mark.parametrize("B,H,W,T,sigma", [(3, 128, 128, 6, 1.5), (2, 100, 90, 3, 1.5), (2, 128, 128, 4, 4.0), (1, 17, 128, 2, 2.0),
+                                           (20, 128, 128, 2, 1.5)])
+def test_iterate_fused_single_launch_is_bit_identical(jb, monkeypatch, B, H, W, T, sigma):
+    """JSPSR_SPN_ITER_FUSED=1: all T applications in one launch (16-CTA cluster per sample, iteration-invariant tap state in
+    registers, feature exchanged through distributed shared memory) against the T-launch loop: equal bits, including taps
+    that leave the staged tile (sigma = 4: the global path reading the previous application's output) and ragged samples."""
+    from jspsr_b200 import functional as F
+    g = torch.Generator(device="cuda").manual_seed(11 + H + W)
+    feat = torch.rand(B, 1, H, W, device="cuda", generator=g)
+    aff = torch.softmax(torch.randn(B, 9, H, W, device="cuda", generator=g), dim=1)
+    off = (sigma * torch.randn(B, 18, H, W, device="cuda", generator=g)).clamp_(-12, 12)
+    off[:, 8:10] = 0
+    ref = F.spn_iterate(feat, aff, off, T)
+    monkeypatch.setenv("JSPSR_SPN_ITER_FUSED", "1")
+    got = F.spn_iterate(feat, aff, off, T)
+    assert torch.equal(got, ref)
+    # non-finite offsets go through the same global path
+    off2 = off.clone()
+    off2[0, 0, H // 2, W // 3] = float("inf")
+    off2[0, 3, H // 3, W // 2] = float("nan")
+    got2 = F.spn_iterate(feat, aff, off2, T)
+    monkeypatch.delenv("JSPSR_SPN_ITER_FUSED")
+    ref2 = F.spn_iterate(feat, aff, off2, T)
+    assert torch.equal(torch.isnan(got2), torch.isnan(ref2))
+    assert torch.equal(torch.nan_to_num(got2), torch.nan_to_num(ref2))
+
+
 def test_nlspn_loop_dtype_mixes_and_empty_loop(jb):
     """jspsr_spn_iterate has no mixed mode.  The autocast mix (fp32 feature, bf16 affinities / offsets) is
     promoted to fp32 - what torchvision's operator does in the reference - instead of being read as fp32 (garbage, out of
