@@ -313,6 +313,12 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         out_keep = step()
     barrier()
+    if world > 1:
+        # One more untimed step AFTER the host barrier: its backward exchanges gradients with every rank inside the
+        # kernel, so the GPUs leave it within microseconds of each other with the timed steps already queued behind it.
+        # Without it the ranks' host threads leave the barrier up to milliseconds apart, and the first timed step of the
+        # early ranks measures that skew (it showed up as one 8.6 ms step among 3.9 ms ones at N = 8).
+        out_keep = step()
     launches0 = F.launch_count()
     sampler = ClockSampler(local_rank)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -334,7 +340,8 @@ def run_ours(args, rank, world, local_rank):
     # per-step device times (start of step i -> start of step i + 1): a single hiccup and a steady gap look different
     marks = [e[0] for e in evs] + [t_end]
     per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
-    step_stats = {"p50_ms": statistics.median(per_step), "max_ms": max(per_step), "min_ms": min(per_step)}
+    step_stats = {"p50_ms": statistics.median(per_step), "max_ms": max(per_step), "min_ms": min(per_step),
+                  "slowest_step": per_step.index(max(per_step))}
     if world > 1:
         t = torch.tensor([ms, fwd_ms, bwd_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
