@@ -267,7 +267,7 @@ def gen_tail_grad_feature(gz, conv_w) -> torch.Tensor:
 
 
 _gen_workspaces = {}
-_GEN_WGRAD_LIBRARY = False   # measurements only (tools/gen_train_time.py): the cuBLAS batched GEMM the kernel replaced
+_GEN_WGRAD_LIBRARY = False   # measurements only (bench.py generator_tail_fused): the cuBLAS batched GEMM the kernel replaced
 
 
 def gen_tail_grad_params(gz, feature, need_w: bool = True, need_b: bool = True):
