@@ -312,6 +312,11 @@ def run_ours(args, rank, world, local_rank):
     out_keep = None
     for _ in range(max(args.warmup, 3)):
         out_keep = step()
+    # everything slow on the host (NVML initialisation inside ClockSampler took 160 ms on one rank of four, event creation)
+    # happens BEFORE the barrier: between the aligning step below and the timed loop there is only Python bookkeeping
+    sampler = ClockSampler(local_rank)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if world > 1:
         # One more untimed step AFTER the host barrier: its backward exchanges gradients with every rank inside the
@@ -320,9 +325,6 @@ def run_ours(args, rank, world, local_rank):
         # early ranks measures that skew (it showed up as one 8.6 ms step among 3.9 ms ones at N = 8).
         out_keep = step()
     launches0 = F.launch_count()
-    sampler = ClockSampler(local_rank)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
         step(evs[i])
