@@ -197,8 +197,21 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         // affinity until the slow pass has its value.  The final sum runs in tap order whatever the
         // mix of fast and slow taps, so the result does not depend on tiling or strip layout.
         unsigned slow = 0u;
+        // Centre tap with a zero offset pair - what every producer in the reference emits (spn.py:72, LRRU.py, nlspn.py
+        // insert a zero pair at the reference index): its position is the pixel itself, so the footprint address is known
+        // without the position / floor / range arithmetic and the four loads are lane-consecutive (no bank conflicts).
+        // Taken only when the whole warp agrees (one uniform branch); same loads, same bilerp with lh = lw = +0, hence
+        // the same bits, including NaN / inf neighbours (0 * inf = NaN is kept: no fast-math).
+        const TI* ctr = tile + (ry + HALO_T) * SW + (cx + HALO_L);
+        const bool centre_fast =
+            __all_sync(__activemask(), ((__float_as_uint(oh[4]) | __float_as_uint(ow[4])) << 1) == 0u &&
+                                           (unsigned)(ry + HALO_T - c.r_lo) < c.r_span);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
+            if (k == 4 && centre_fast) {
+                a[4] = (s_w[4] * a[4]) * bilerp(to_f32(ctr[0]), to_f32(ctr[1]), to_f32(ctr[SW]), to_f32(ctr[SW + 1]), 0.f, 0.f);
+                continue;
+            }
             const FastTap t = fast_tap<TI>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
             const float val = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
             a[k] = t.ok ? (s_w[k] * a[k]) * val : a[k];
@@ -217,7 +230,7 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
 #pragma unroll
         for (int k = 1; k < 9; ++k) acc += a[k];
         acc += s_w[9];
-        if (mode == NORM_RESIDUAL) acc = fmaf(scale, to_f32(tile[(ry + HALO_T) * SW + (cx + HALO_L)]), acc);
+        if (mode == NORM_RESIDUAL) acc = fmaf(scale, to_f32(ctr[0]), acc);
         st_stream(out_b + in.p, acc);
     };
 
