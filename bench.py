@@ -690,6 +690,34 @@ def side_numbers(torch, F, device, B):
     out["backward_with_grad_init"] = {"ms": g, "frac_of_hbm_peak": 228 * npix / (g * 1e-3) / 1e9 / peak,
                                       "note": "scatter into a block-floating-point tile of native integer shared-memory "
                                               "atomics (exact, order-independent inside a CTA); used by NLSPN only"}
+    # SURVEY.md section 8d's "adversarial" set: offsets ~ N(0, 16^2), so most taps leave the staged tile and take the
+    # bounds-checked global path (the price of unbounded offsets, not a configuration the reference produces)
+    nf = min(B, 512)
+    far = (16.0 * torch.randn((nf, 18, TILE, TILE), device=device,
+                              generator=torch.Generator(device=device).manual_seed(77))).clamp_(-64, 64)
+    far[:, 8:10] = 0
+    f = timed(lambda: F.spn_forward(init[:nf], weight[:nf], far, w, b, 1, 1.0), n=3)
+    g = timed(lambda: F.spn_backward(gout[:nf], init[:nf], weight[:nf], far, w, 1, 1.0, need_grad_init=False), n=3)
+    pxf = nf * TILE * TILE
+    out["far_offsets_sigma16"] = {"tiles": nf, "fwd_ms": f, "bwd_ms": g,
+                                  "fwd_frac_of_hbm_peak": FWD_BYTES["f32"] * pxf / (f * 1e-3) / 1e9 / peak,
+                                  "bwd_frac_of_hbm_peak": BWD_BYTES["f32"] * pxf / (g * 1e-3) / 1e9 / peak,
+                                  "note": "offsets N(0, 16^2) clipped to +-64: taps outside the staged tile go through global "
+                                          "loads with per-corner bounds checks (L2 gathers); results still exact"}
+    del far
+    # whole raster (runtime channel stride, narrow staged halo): one 8192 x 8192 image
+    rs = 8192
+    gr = torch.Generator(device=device).manual_seed(78)
+    r_init = torch.rand(1, 1, rs, rs, device=device, generator=gr)
+    r_w = torch.sigmoid(1.5 * torch.randn(1, 9, rs, rs, device=device, generator=gr))
+    r_o = (1.5 * torch.randn(1, 18, rs, rs, device=device, generator=gr)).clamp_(-8, 8)
+    r_g = torch.randn(1, 1, rs, rs, device=device, generator=gr)
+    f = timed(lambda: F.spn_forward(r_init, r_w, r_o, w, b, 1, 1.0))
+    g = timed(lambda: F.spn_backward(r_g, r_init, r_w, r_o, w, 1, 1.0, need_grad_init=False))
+    out["raster_8192"] = {"fwd_ms": f, "bwd_ms": g, "fwd_frac_of_hbm_peak": FWD_BYTES["f32"] * rs * rs / (f * 1e-3) / 1e9 / peak,
+                          "bwd_frac_of_hbm_peak": BWD_BYTES["f32"] * rs * rs / (g * 1e-3) / 1e9 / peak}
+    del r_init, r_w, r_o, r_g
+    torch.cuda.empty_cache()
     T = 6
     aff = weight * 0.1
     it = timed(lambda: F.spn_iterate(init, aff, offset, T), n=3)
