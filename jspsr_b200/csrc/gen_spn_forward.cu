@@ -239,6 +239,7 @@ gen_spn_forward_kernel(const float* __restrict__ init, const FT* __restrict__ fe
         const uint32_t tmem = s_tmem;
 #pragma unroll 1
         for (int r = 0; r < TH; ++r) {
+            __syncwarp();  // the previous row's out-of-tile taps may have split the warp; tcgen05.ld below is .sync.aligned
             mbar_wait(&bar_acc_full[r & 1], (uint32_t)((r >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v[32];

@@ -74,6 +74,7 @@ nlspn_affinity_fwd_kernel(const T* __restrict__ conv_out, const T* __restrict__ 
 
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
+        __syncwarp();  // reconverge the lanes that took the out-of-tile path on the previous pixel (see spn_forward.cu)
         if (it > 0) load_inputs(it, active, p);
         if (!active) continue;
         const float fy = (float)(c.y0 + pix_row<TH, true>(it)), fx = (float)(c.x0 + pix_col<TH, true>(it));
@@ -234,6 +235,7 @@ nlspn_affinity_bwd_kernel(const T* __restrict__ grad_offset, const T* __restrict
 
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
+        __syncwarp();  // reconverge the lanes that took the out-of-tile path on the previous pixel (see spn_forward.cu)
         if (it > 0) load_inputs(it, active, p);
         if (!active) continue;
         const float fy = (float)(c.y0 + pix_row<TH, true>(it)), fx = (float)(c.x0 + pix_col<TH, true>(it));

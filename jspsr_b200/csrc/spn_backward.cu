@@ -180,6 +180,7 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
 
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
+        __syncwarp();  // reconverge the lanes that took the out-of-tile path on the previous pixel (see spn_forward.cu)
         if (it > 0) load_inputs(it, active, p);
         if (!active) continue;
         const int ry = pix_row<TH, true>(it), cx = pix_col<TH, true>(it);

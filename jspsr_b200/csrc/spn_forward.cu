@@ -244,6 +244,8 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
     //  registers cost more than the overlap gains, warp-level parallelism already hides the latency.)
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
+        __syncwarp();  // lanes that took the out-of-tile path on the previous pixel rejoin here: without it a warp stays split for the
+                       // rest of the loop (ncu: 5.8 active threads per instruction with far offsets), every later pixel issued per fragment
         if (it > 0) load_inputs(it, cur);
         compute(it, cur);
     }
