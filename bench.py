@@ -807,6 +807,10 @@ def side_numbers(torch, F, device, B):
         feat16 = feat.bfloat16()
         fused16 = timed(lambda: F.gen_spn_forward(ini, feat16, cw, cb, w, b, 1, 1.0, False))
         fused16_wo = timed(lambda: F.gen_spn_forward(ini, feat16, cw, cb, w, b, 1, 1.0, True))
+        gz16 = torch.randn(Bg, 25, TILE, TILE, device=device, generator=g_).bfloat16()
+        gp16 = timed(lambda: F.gen_tail_grad_params(gz16, feat16))
+        gf16 = timed(lambda: F.gen_tail_grad_feature(gz16, cw))
+        del gz16
         res.update({
             "unfused_ms": un, "speedup_vs_unfused": un / fused,
             "training_step_ms": tr_f, "training_step_unfused_ms": tr_u, "training_speedup_vs_unfused": tr_u / tr_f,
@@ -814,6 +818,10 @@ def side_numbers(torch, F, device, B):
             "grad_params_kernel_ms": gp, "grad_params_frac_of_hbm_peak": (100 + 4 * C) * npx / (gp * 1e-3) / 1e9 / peak,
             "training_step_ms_with_library_weight_gradient": tr_lib,
             "autocast_bf16_features": {"ms": fused16, "frac_of_hbm_peak": (C * 2 + 8) * npx / (fused16 * 1e-3) / 1e9 / peak,
+                                       "grad_params_kernel_ms": gp16,
+                                       "grad_params_frac_of_hbm_peak": (50 + 2 * C) * npx / (gp16 * 1e-3) / 1e9 / peak,
+                                       "grad_feature_kernel_ms": gf16,
+                                       "grad_feature_frac_of_hbm_peak": (50 + 2 * C) * npx / (gf16 * 1e-3) / 1e9 / peak,
                                        "ms_with_weight_offset_written": fused16_wo,
                                        "frac_of_hbm_peak_with_weight_offset_written":
                                            (C * 2 + 8 + 54) * npx / (fused16_wo * 1e-3) / 1e9 / peak},
