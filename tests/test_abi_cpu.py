@@ -95,6 +95,11 @@ def test_argument_validation_needs_no_gpu(lib):
         (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 1, None), -2, "fp32"),
         (lambda: h.jspsr_gen_spn_forward(one, one, one, one, one, one, one, one, None, 1, 64, 8, 8, 1, 1.0, 0, None), -1, "together"),
         (lambda: h.jspsr_gen_spn_forward(one, one, ctypes.c_void_p(20), one, one, one, one, None, None, 1, 64, 8, 8, 1, 1.0, 0, None), -4, "conv_w"),
+        (lambda: h.jspsr_gen_tail_grad_params(one, one, one, one, one, 1, 32, 8, 8, 0, None), -2, "C = 64 and C = 128"),
+        (lambda: h.jspsr_gen_tail_grad_params(one, one, one, one, one, 1, 64, 8, 8, 2, None), -1, "dtype is 0"),
+        (lambda: h.jspsr_gen_tail_grad_params(one, one, None, None, one, 1, 64, 8, 8, 0, None), -1, "null"),
+        (lambda: h.jspsr_gen_tail_grad_params(one, one, one, one, None, 1, 64, 8, 8, 0, None), -1, "null"),
+        (lambda: h.jspsr_gen_tail_grad_params(one, one, one, one, ctypes.c_void_p(24), 1, 64, 8, 8, 0, None), -4, "workspace"),
         (lambda: h.jspsr_spn_iterate(one, one, one, None, None, one, None, 1, 8, 8, 2, 2, None), -2, "mixed"),
         (lambda: h.jspsr_spn_forward(one, one, one, one, one, one, 1, 8, 8, 1, 1.0, 3, None), -1, "dtype"),
         (lambda: h.jspsr_spn_iterate(one, one, one, None, None, one, None, 1, 8, 8, 0, 0, None), -1, "T="),
