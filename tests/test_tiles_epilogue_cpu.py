@@ -104,6 +104,23 @@ def test_oracle_loss_matches_reference(epi_ref, tag):
     assert abs(float(o32["Total"]) - float(epi_ref[tag + "_Total_f32"])) <= 1e-5 * float(o32["Total"])
 
 
+def test_sobel_restatement_matches_an_independent_implementation():
+    """kornia.filters.spatial_gradient is absent from /root/reference and from this image, so the EdgeLoss term is pinned to a
+    restatement of its published algorithm (replicate pad, Sobel pair / 8).  Second opinion from a third-party
+    implementation that IS here: scipy.ndimage.sobel with mode="nearest" (= replicate) is the same operator up to the 1/8
+    normalisation; both the oracle and the stub the fixture generator used must agree with it."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    import torch
+    from tests.golden.make_golden_epilogue import sobel_like_kornia
+    rng = np.random.default_rng(5)
+    for shape in ((2, 1, 9, 13), (1, 1, 1, 5), (3, 1, 32, 32)):
+        x = rng.normal(size=shape)
+        want = np.stack([np.stack([ndi.sobel(x[b, 0], axis=1, mode="nearest"), ndi.sobel(x[b, 0], axis=0, mode="nearest")]) / 8.0
+                         for b in range(shape[0])])[:, None]                     # [B,1,2,H,W]: d/dx, d/dy
+        np.testing.assert_allclose(E.spatial_gradient(x), want, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(sobel_like_kornia(torch.from_numpy(x)).numpy(), want, rtol=0, atol=1e-14)
+
+
 def test_oracle_loss_gradient_is_the_derivative():
     # finite differences of Total (fp64) away from the kinks of |.|
     rng = np.random.default_rng(5)
