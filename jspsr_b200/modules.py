@@ -68,6 +68,10 @@ def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, c
     sub-modules: convd1, convd2, convf1, convf2, conv, block, conv_weight, conv_offset); its body up to `block`
     (spn.py:57-65: cuDNN convolutions, not on the hot path) runs as is, its parameters stay where they are, so
     checkpoints and optimizer groups are unchanged.  `postprocessor` is a PostProcessor (either implementation).
+    The twin pair of the LRRU baseline is accepted as well: models/LRRU.py:202-247 `BasicDepthEncoder` (last body block
+    `ref` instead of `block`, plain nn.Conv2d heads with a functional sigmoid, bc = 16 -> 64 feature channels) with
+    models/LRRU.py:250-298 `Post_process_deconv` (`dkn_residual`, no scale), as used four times per forward at
+    LRRU.py:454-498 (`weight_i, offset_i = self.weight_offset_i(x, ctx); x = self.Post_process(x, weight_i, offset_i)`).
     The weight/offset tensors never exist in inference; with autograd they are written once by the fused kernel
     and consumed by the fused backward.
 
@@ -81,16 +85,34 @@ def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, c
         dem = dem.detach()
     d2 = generator.convd2(generator.convd1(dem))
     f2 = generator.convf2(generator.convf1(context))
-    feature = generator.block(generator.conv(torch.cat((d2, f2), dim=1)))
-    cw, co = generator.conv_weight[0], generator.conv_offset.conv[0]
-    if generator.kernel_size != 3 or cw.kernel_size != (1, 1) or co.kernel_size != (1, 1):
-        raise NotImplementedError("generator_postprocess needs the reference's 3x3 window and 1x1 output convolutions")
+    last = generator.block if hasattr(generator, "block") else generator.ref           # spn.Generator / LRRU twin
+    feature = last(generator.conv(torch.cat((d2, f2), dim=1)))
+    cw, co = _head_conv(generator.conv_weight), _head_conv(generator.conv_offset)
+    if (generator.kernel_size != 3 or cw.kernel_size != (1, 1) or co.kernel_size != (1, 1) or cw.out_channels != 9
+            or co.out_channels != 16 or cw.bias is None or co.bias is None):
+        raise NotImplementedError("generator_postprocess needs the reference's 3x3 window and biased 1x1 output "
+                                  "convolutions (C -> 9 and C -> 16)")
     conv_w = torch.cat((cw.weight.flatten(1), co.weight.flatten(1)), dim=0)
     conv_b = torch.cat((cw.bias, co.bias))
-    mode = NORM_RESIDUAL if postprocessor.residual else NORM_SUM
+    residual = postprocessor.residual if hasattr(postprocessor, "residual") else postprocessor.dkn_residual
+    mode = NORM_RESIDUAL if residual else NORM_SUM
     init = dem if init_dem is None else init_dem
     return F.gen_propagate(init, feature, conv_w, conv_b, postprocessor.w, postprocessor.b, mode,
-                           float(postprocessor.scale))
+                           float(getattr(postprocessor, "scale", 1.0)))
+
+
+def _head_conv(m: nn.Module) -> nn.Conv2d:
+    """The 1x1 convolution inside one of the Generator's two heads: spn.py:41-52 wraps it (Sequential(Conv2d, Sigmoid) /
+    Basic2d with .conv = Sequential(Conv2d)), LRRU.py:219-224 uses plain nn.Conv2d modules."""
+    if isinstance(m, nn.Conv2d):
+        return m
+    if hasattr(m, "conv"):
+        m = m.conv
+    if isinstance(m, nn.Sequential) and len(m) > 0 and isinstance(m[0], nn.Conv2d):
+        return m[0]
+    if isinstance(m, nn.Conv2d):
+        return m
+    raise NotImplementedError(f"generator_postprocess: no 1x1 convolution found in {type(m).__name__}")
 
 
 class Post_process_deconv(nn.Module, ABC):

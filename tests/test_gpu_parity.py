@@ -843,6 +843,59 @@ def test_generator_tail_autocast_bf16_features(jb):
         assert p_.grad is not None and p_.grad.dtype == p_.dtype and torch.isfinite(p_.grad).all(), n
 
 
+def test_generator_postprocess_accepts_the_lrru_twin(jb):
+    """models/LRRU.py:202-247 BasicDepthEncoder + models/LRRU.py:250-298 Post_process_deconv through generator_postprocess:
+    last body block `ref`, plain nn.Conv2d heads with a functional sigmoid, `dkn_residual`, no scale - against the unfused
+    evaluation (the reference's own sequence with torch's 1x1 convolutions and our propagation), forward and all gradients."""
+    import types
+    import torch.nn as nn
+    import jspsr_b200
+    torch.manual_seed(8)
+
+    class Twin(nn.Module):   # structural twin of BasicDepthEncoder (sub-module names and shapes, bc = 16)
+        def __init__(self, cin=8, bc=16):
+            super().__init__()
+            self.kernel_size, self.num, self.idx_ref = 3, 8, 4
+            mk = lambda i, o: nn.Sequential(nn.Conv2d(i, o, 3, padding=1), nn.ReLU())
+            self.convd1, self.convd2 = mk(1, 2 * bc), mk(2 * bc, 2 * bc)
+            self.convf1, self.convf2 = mk(cin, 2 * bc), mk(2 * bc, 2 * bc)
+            self.conv, self.ref = mk(4 * bc, 4 * bc), mk(4 * bc, 4 * bc)
+            self.conv_weight = nn.Conv2d(4 * bc, 9, 1)
+            self.conv_offset = nn.Conv2d(4 * bc, 16, 1)
+
+        def forward(self, depth, context):      # LRRU.py:226-247
+            B, _, H, W = depth.shape
+            feature = self.ref(self.conv(torch.cat((self.convd2(self.convd1(depth)), self.convf2(self.convf1(context))), 1)))
+            weight = torch.sigmoid(self.conv_weight(feature))
+            lo = list(torch.chunk(self.conv_offset(feature).view(B, 8, 2, H, W), 8, dim=1))
+            lo.insert(4, torch.zeros((B, 1, 2, H, W)).type_as(weight))
+            return weight, torch.cat(lo, dim=1).view(B, -1, H, W)
+
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for dkn in (True, False):
+            gen = Twin().cuda()
+            with torch.no_grad():
+                gen.conv_offset.weight.mul_(6.0)
+            pp = jspsr_b200.Post_process_deconv(types.SimpleNamespace(kernel_size=3, dkn_residual=dkn)).cuda()
+            depth = torch.rand(2, 1, 40, 136, device="cuda") + 0.2
+            ctx = torch.randn(2, 8, 40, 136, device="cuda")
+            gout = torch.randn(2, 1, 40, 136, device="cuda")
+            out = jspsr_b200.generator_postprocess(gen, pp, depth, ctx)
+            out.backward(gout)
+            fused = {n: p.grad.clone() for n, p in list(gen.named_parameters()) + list(pp.named_parameters())}
+            gen.zero_grad(); pp.zero_grad()
+            weight, offset = gen(depth, ctx)
+            ref = pp(depth, weight, offset)
+            ref.backward(gout)
+            assert_close(out, ref.detach().double().cpu().numpy(), FP32_TOL, f"LRRU twin out (dkn_residual={dkn})")
+            for n, p_ in list(gen.named_parameters()) + list(pp.named_parameters()):
+                assert_close(fused[n], p_.grad.double().cpu().numpy(), 5 * FP32_TOL, f"grad of LRRU twin {n}", gout=gout)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
 @pytest.mark.parametrize("B,C,H,W", [(2, 64, 128, 128), (1, 64, 21, 200), (3, 128, 9, 36), (1, 64, 1, 1), (1, 128, 40, 136)])
 def test_generator_tail_grad_feature_kernel(jb, B, C, H, W):
     """grad_feature = gz x conv_w on tcgen05 (3-product tf32 split) against fp64, fp32 and bf16 operands."""

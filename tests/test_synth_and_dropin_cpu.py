@@ -119,3 +119,41 @@ def test_generator_postprocess_matches_the_reference_generators_structure(monkey
     assert torch.allclose(torch.sigmoid(z[:, :9]), weight, atol=1e-6)
     assert torch.allclose(z[:, 9:17], offset[:, :8], atol=1e-5) and torch.allclose(z[:, 17:], offset[:, 10:], atol=1e-5)
     assert torch.all(offset[:, 8:10] == 0)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree only exists in the build container")
+def test_generator_postprocess_drives_the_reference_lrru_encoder(monkeypatch):
+    """The LRRU twin: the reference's OWN models.LRRU.BasicDepthEncoder (LRRU.py:202-247) + Post_process_deconv through
+    jspsr_b200.generator_postprocess - `ref` instead of `block`, plain nn.Conv2d heads, functional sigmoid, bc = 16 (64
+    feature channels), `dkn_residual` instead of `residual`, no scale.  Kernel call intercepted: no GPU here."""
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import types
+    from models.LRRU import BasicDepthEncoder, Post_process_deconv as RefPost
+    import jspsr_b200 as jb
+    from jspsr_b200 import functional as F
+    torch.manual_seed(1)
+    enc = BasicDepthEncoder(kernel_size=3, bc=16, norm_layer=torch.nn.BatchNorm2d).eval()
+    args = types.SimpleNamespace(kernel_size=3, dkn_residual=True)
+    ref_pp, pp = RefPost(args), jb.Post_process_deconv(args)
+    assert set(ref_pp.state_dict()) == set(pp.state_dict())
+    captured = {}
+    hook = enc.ref.register_forward_hook(lambda _m, _i, o: captured.__setitem__("feature", o.detach()))
+    depth, ctx = torch.rand(1, 1, 16, 24), torch.randn(1, 32, 16, 24)
+    with torch.no_grad():
+        weight, offset = enc(depth, ctx)                                 # the reference's own forward
+    hook.remove()
+    seen = {}
+
+    def fake_kernel(init, feature, conv_w, conv_b, w, b, mode, scale):
+        seen.update(init=init, feature=feature, conv_w=conv_w, conv_b=conv_b, mode=mode, scale=scale)
+        return init
+    monkeypatch.setattr(F, "gen_propagate", fake_kernel)
+    with torch.no_grad():
+        jb.generator_postprocess(enc, pp, depth, ctx)
+    assert torch.equal(seen["feature"], captured["feature"]) and seen["feature"].shape[1] == 64
+    assert seen["mode"] == 1 and seen["scale"] == 1.0
+    z = torch.einsum("nc,bchw->bnhw", seen["conv_w"], seen["feature"]) + seen["conv_b"].view(1, -1, 1, 1)
+    assert torch.allclose(torch.sigmoid(z[:, :9]), weight, atol=1e-6)
+    assert torch.allclose(z[:, 9:17], offset[:, :8], atol=1e-5) and torch.allclose(z[:, 17:], offset[:, 10:], atol=1e-5)
