@@ -195,9 +195,23 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
         float gm[9];
         unsigned slow = 0u;
         acc_b += go;
+        // centre tap with a zero offset pair (every producer of the reference): footprint address known, loads
+        // lane-consecutive; same values into the same arithmetic as the general path (see spn_forward.cu)
+        const TI* ctr = tile + (ry + HALO_T) * SW + (cx + HALO_L);
+        const bool centre_fast =
+            __all_sync(__activemask(), ((__float_as_uint(oh[4]) | __float_as_uint(ow[4])) << 1) == 0u &&
+                                           (unsigned)(ry + HALO_T - c.r_lo) < c.r_span);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            const FastTap t = fast_tap<TI>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+            FastTap t;
+            if (k == 4 && centre_fast) {
+                t.v1 = to_f32(ctr[0]); t.v2 = to_f32(ctr[1]); t.v3 = to_f32(ctr[SW]); t.v4 = to_f32(ctr[SW + 1]);
+                t.lh = 0.f; t.lw = 0.f;
+                t.h0 = g.row0 + c.y0 + ry; t.w0 = c.x0 + cx;
+                t.ok = true;
+            } else {
+                t = fast_tap<TI>(tile_lo, c, hk[k / 3] + oh[k], wk[k % 3] + ow[k]);
+            }
             // value and both derivatives (torchvision get_coordinate_weight) share the two row differences
             const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
             const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
