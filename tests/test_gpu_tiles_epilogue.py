@@ -446,9 +446,11 @@ def test_torch_extension_path_equals_ctypes_path_bitwise(jb):
             assert F.launch_count() - n0 == 3                            # forward, loss, backward
             res.append([out.detach(), losses.detach(), w_.grad, o_.grad, post.w.grad, post.b.grad] +
                        ([i_.grad] if need_init else []))
-        for a, b2 in zip(*res):
+        for idx, (a, b2) in enumerate(zip(*res)):
             assert a.dtype == b2.dtype and a.shape == b2.shape
-            if a.numel() > 16:
+            if idx == 6:       # grad_init: CTA tiles are flushed with fp32 RED (and out-of-tile taps scatter with fp32
+                assert torch.allclose(a, b2, rtol=1e-5, atol=1e-8)       # atomics), whose order across CTAs is not fixed
+            elif a.numel() > 16:
                 assert torch.equal(a, b2)
             else:                                                        # global sums: fp64 atomics, order-dependent
                 assert torch.allclose(a, b2, rtol=1e-5, atol=1e-7)
