@@ -971,14 +971,30 @@ def test_generator_tail_kernels_capture_into_a_cuda_graph(jb):
     gz = torch.randn(4, 25, 64, 128, device="cuda")
     ref_out = F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0)
     ref_gf = F.gen_tail_grad_feature(gz, cw)
+    ref_gw, ref_gb = F.gen_tail_grad_params(gz, feat)
+    feat_loop = torch.rand(3, 1, 128, 128, device="cuda")
+    aff_loop = torch.softmax(torch.randn(3, 9, 128, 128, device="cuda"), dim=1)
+    off_loop = torch.randn(3, 18, 128, 128, device="cuda")
+    ref_loop = F.spn_iterate(feat_loop, aff_loop, off_loop, 3)
     s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):                      # the per-stream reduction workspace exists before the capture
+        F.gen_tail_grad_params(gz, feat)
+    torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=s):
-        out = F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0)
-        gf = F.gen_tail_grad_feature(gz, cw)
-    out.zero_(); gf.zero_()
-    graph.replay(); torch.cuda.synchronize()
-    assert torch.equal(out, ref_out) and torch.equal(gf, ref_gf)
+    os.environ["JSPSR_SPN_ITER_FUSED"] = "1"        # the cluster launch of the single-launch loop is capturable too
+    try:
+        with torch.cuda.graph(graph, stream=s):
+            out = F.gen_spn_forward(init, feat, cw, cb, w, b, 1, 1.0)
+            gf = F.gen_tail_grad_feature(gz, cw)
+            gw, gb = F.gen_tail_grad_params(gz, feat)
+            loop = F.spn_iterate(feat_loop, aff_loop, off_loop, 3)
+    finally:
+        os.environ.pop("JSPSR_SPN_ITER_FUSED", None)
+    for rep in range(2):                            # a replay finds the workspace zeroed by the previous one
+        out.zero_(); gf.zero_(); gw.zero_(); gb.zero_(); loop.zero_()
+        graph.replay(); torch.cuda.synchronize()
+        assert torch.equal(out, ref_out) and torch.equal(gf, ref_gf) and torch.equal(loop, ref_loop)
+        assert torch.allclose(gw, ref_gw, rtol=1e-6, atol=1e-6) and torch.allclose(gb, ref_gb, rtol=1e-6, atol=1e-6)
 
 
 def test_generator_tail_full_size_properties(jb):
