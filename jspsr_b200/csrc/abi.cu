@@ -1,5 +1,6 @@
 // C ABI of libjspsr_spn.so (see include/jspsr_spn.h): argument validation, TMA
 // descriptor encoding, launches.  No torch types, no allocation, no synchronisation.
+#include <initializer_list>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -90,6 +91,19 @@ static bool choose_wide(int W) {
         if (e[0] == 'n') return false;
     }
     return W <= 1024;
+}
+
+// bf16 weight / offset streamed two pixels per thread as 32-bit words (spn_forward.cu, PAIR): every streamed pointer
+// must be aligned to a pixel pair; JSPSR_SPN_PAIR=0 selects the one-pixel kernels (A/B runs, tests of both)
+static bool pair_ok(int dtype, std::initializer_list<const void*> bf16_ptrs, std::initializer_list<const void*> io_ptrs) {
+    if (dtype == JSPSR_F32) return false;
+    if (const char* e = getenv("JSPSR_SPN_PAIR")) {
+        if (e[0] == '0') return false;
+    }
+    const uintptr_t io_mask = dtype == JSPSR_BF16 ? 3 : 7;
+    for (const void* p : bf16_ptrs) if (((uintptr_t)p & 3) != 0) return false;
+    for (const void* p : io_ptrs) if (((uintptr_t)p & io_mask) != 0) return false;
+    return true;
 }
 
 static bool tma_disabled_by_env() {
@@ -250,6 +264,7 @@ static int spn_forward_strip_impl(const void* init, const void* weight, const vo
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
     la.status = status;
     la.stream = (cudaStream_t)stream;
+    la.pair = pair_ok(dtype, {weight, offset}, {out});
     const bool wide = choose_wide(W);
     la.use_tma = make_init_tmap(&la.tmap, init, B, init_rows, W, dtype == JSPSR_BF16, la.tile_h, wide);
     cudaError_t ce = wide ? wide::launch_spn_forward(la) : narrow::launch_spn_forward(la);
@@ -396,6 +411,7 @@ int jspsr_spn_backward_reduce(const void* grad_out, const void* init, const void
     if (prd.world > 1) la.peer_reduce = &prd;
     la.mode = norm_mode; la.scale = scale; la.bf16 = dtype != JSPSR_F32; la.init_f32 = dtype == JSPSR_MIXED;
     la.stream = (cudaStream_t)stream;
+    la.pair = pair_ok(dtype, {weight, offset, grad_weight, grad_offset}, {grad_out});
     const bool wide = choose_wide(W);
     la.use_tma = make_init_tmap(&la.tmap, init, B, H, W, dtype == JSPSR_BF16, la.tile_h, wide);
     if (grad_init) {

@@ -39,7 +39,11 @@ __device__ __forceinline__ void scatter_corner_global(float* __restrict__ gi_b, 
 // w.r.t. the PRE-ACTIVATIONS of Generator.conv_weight / conv_offset (spn.py:41-52,66-73): channels 0..8 =
 // dL/d(weight_k) * weight_k * (1 - weight_k) (sigmoid'), channels 9..24 = the 16 offset gradients without the centre
 // pair - the operand of the two 1x1-convolution gradient GEMMs, written here instead of by four elementwise passes.
-template <typename T, typename TI, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH, bool GZ = false>
+// PACK (bf16 weight / offset, compile-time stride, no grad_init): the 27 bf16 inputs of a pixel are kept two to a
+// register (14 instead of 27) and widened where a tap needs them - same operations in the same order as the plain path.
+// At four resident CTAs (64 registers) the plain bf16 kernel spills about ten registers, and those local-memory
+// accesses go through the same load/store pipe that bounds the kernel (ncu: LSU wavefronts 77 %, issue 69 %).
+template <typename T, typename TI, bool TMA, bool GRAD_INIT, bool ACC, int CS, int TH, bool GZ = false, bool PACK = false>
 __global__ void __launch_bounds__(THREADS, sizeof(T) == 2 ? BWD_MIN_BLOCKS_BF16 : BWD_MIN_BLOCKS)
 spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, const T* __restrict__ weight,
                     const T* __restrict__ offset, const float* __restrict__ w9, float* __restrict__ grad_init,
@@ -174,6 +178,136 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
             s_gis = gi_scale_from_sum(S);
         }
     }
+    if constexpr (PACK) {
+        static_assert(sizeof(T) == 2 && CS != 0 && !GRAD_INIT && !ACC, "PACK: bf16, compile-time stride, plain stores");
+        // 27 bf16 inputs of a pixel in 14 registers: value i (a0..a8, then oh_k / ow_k interleaved) is half i & 1 of pk[i >> 1]
+        uint32_t pk[14];
+        auto val_of = [&](int i) { return bf16x2_half(pk[i >> 1], i & 1); };
+        auto load_packed = [&](int it) {
+            const int y = c.y0 + pix_row<TH, true>(it), x = c.x0 + pix_col<TH, true>(it);
+            active = (y < g.H) && (x < g.W);
+            p = (size_t)y * g.W + x;
+            if (active) {
+                const T* pw = wgt_b + p;
+                const T* po = off_b + p;
+                go = ld_stream(gout_b + p);
+                unsigned u[28];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) u[k] = ld_stream_u16(pw + k * cs);
+#pragma unroll
+                for (int k = 0; k < 18; ++k) u[9 + k] = ld_stream_u16(po + k * cs);
+                u[27] = 0u;
+#pragma unroll
+                for (int j = 0; j < 14; ++j) pk[j] = u[2 * j] | (u[2 * j + 1] << 16);
+            }
+        };
+        // one pixel; the affinity of tap k is widened and normalised where it is needed (one FFMA covers the three modes
+        // exactly: a - mean = fma(a, 1, -mean), a * inv = fma(a, inv, -0), a = fma(a, 1, -0)), so the inputs stay packed
+        auto pixel = [&](const int ry, const int cx) {
+            float nmul = 1.f, nadd = -0.f, s = 0.f;
+            if (mode != NORM_NONE) {
+                s = val_of(0);
+#pragma unroll
+                for (int k = 1; k < 9; ++k) s += val_of(k);
+                if (mode == NORM_RESIDUAL) nadd = -__fdiv_rn(s, 9.f);
+                else nmul = __fdiv_rn(1.f, s);
+            }
+            auto m_of = [&](int k) { return fmaf(val_of(k), nmul, nadd); };
+            const float fy = (float)(g.row0 + c.y0 + ry), fx = (float)(c.x0 + cx);
+            const float hk[3] = {fy - 1.f, fy, fy + 1.f};
+            const float wk[3] = {fx - 1.f, fx, fx + 1.f};
+            T* po = goff_b + p;
+            float gm[9];
+            unsigned slow = 0u;
+            acc_b += go;
+            const TI* ctr = tile + (ry + HALO_T) * SW + (cx + HALO_L);
+            // centre offsets = values 9 + 8 (high half of pk[8]) and 9 + 9 (low half of pk[9])
+            const bool centre_fast =
+                __all_sync(__activemask(), (((pk[8] >> 16) | pk[9]) & 0x7fffu) == 0u && (unsigned)(ry + HALO_T - c.r_lo) < c.r_span);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                FastTap t;
+                if (k == 4 && centre_fast) {
+                    t.v1 = to_f32(ctr[0]); t.v2 = to_f32(ctr[1]); t.v3 = to_f32(ctr[SW]); t.v4 = to_f32(ctr[SW + 1]);
+                    t.lh = 0.f; t.lw = 0.f;
+                    t.ok = true;
+                } else {
+                    t = fast_tap<TI>(tile_lo, c, hk[k / 3] + val_of(9 + 2 * k), wk[k % 3] + val_of(10 + 2 * k));
+                }
+                const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
+                const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
+                float dh = bot - top;
+                float val = fmaf(t.lh, dh, top);
+                float dw = fmaf(t.lh, d43 - d21, d21);
+                if (!t.ok) {
+                    val = dh = dw = 0.f;
+                    slow |= 1u << k;
+                }
+                const float ga = go * m_of(k);
+                const float gkm = ga * s_w[k];
+                acc_w[k] = fmaf(ga, val, acc_w[k]);
+                gm[k] = (go * s_w[k]) * val;
+                if (!(GZ && k == 4)) {
+                    store(po + och(k) * cs, gkm * dh);
+                    store(po + (och(k) + 1) * cs, gkm * dw);
+                }
+            }
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (slow & (1u << k)) {
+                        const float h = hk[k / 3] + val_of(9 + 2 * k), w = wk[k % 3] + val_of(10 + 2 * k);
+                        const SlowTap t = slow_tap<TI>(init_b, g, h, w, nullptr);
+                        const float d21 = t.v2 - t.v1, d43 = t.v4 - t.v3;
+                        const float top = fmaf(t.lw, d21, t.v1), bot = fmaf(t.lw, d43, t.v3);
+                        const float dh = bot - top, val = fmaf(t.lh, dh, top), dw = fmaf(t.lh, d43 - d21, d21);
+                        const float ga = go * m_of(k), gkm = ga * s_w[k];
+                        acc_w[k] = fmaf(ga, val, acc_w[k]);
+                        gm[k] += (go * s_w[k]) * val;
+                        if (!(GZ && k == 4)) {
+                            store(po + och(k) * cs, gkm * dh);
+                            store(po + (och(k) + 1) * cs, gkm * dw);
+                        }
+                    }
+                }
+            }
+            if (mode == NORM_RESIDUAL) {
+                float sg = gm[0];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) sg += gm[k];
+                const float mean = __fdiv_rn(sg, 9.f);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gm[k] -= mean;
+            } else if (mode == NORM_SUM) {
+                float dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dot = fmaf(gm[k], m_of(k), dot);
+                const float inv = __fdiv_rn(1.f, s);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gm[k] = (gm[k] - dot) * inv;
+            }
+            if (GZ) {
+                const float mean = __fdiv_rn(s, 9.f);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const float mk = m_of(k);
+                    const float raw = mode == NORM_RESIDUAL ? mk + mean : (mode == NORM_SUM ? mk * s : mk);
+                    gm[k] *= raw * (1.f - raw);
+                }
+            }
+            T* pw = gwgt_b + p;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) store(pw + k * cs, gm[k]);
+        };
+        load_packed(0);
+        stage_tile_wait<TMA>(&bar);
+#pragma unroll 1
+        for (int it = 0; it < PPT; ++it) {
+            __syncwarp();
+            if (it > 0) load_packed(it);
+            if (active) pixel(pix_row<TH, true>(it), pix_col<TH, true>(it));
+        }
+    } else {
     load_inputs(0, active, p);
     stage_tile_wait<TMA>(&bar);
     if (GRAD_INIT) gscale = s_gis.scale;  // published before the barrier inside stage_tile_wait
@@ -313,6 +447,8 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
         }
     }
 
+    }  // !PAIR
+
     // ---- grad_init: flush the shared accumulation tile (one 16-byte vector RED per 4 columns) ----
     if (GRAD_INIT) {
         __syncthreads();
@@ -420,10 +556,10 @@ spn_backward_kernel(const TI* __restrict__ gout, const TI* __restrict__ init, co
     }
 }
 
-template <typename T, typename TI, bool TMA, bool GI, bool ACC, int CS, int TH, bool GZ = false>
+template <typename T, typename TI, bool TMA, bool GI, bool ACC, int CS, int TH, bool GZ = false, bool PACK = false>
 static void launch_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_backward_kernel<T, TI, TMA, GI, ACC, CS, TH, GZ><<<grid, THREADS, 0, la.stream>>>(
+    spn_backward_kernel<T, TI, TMA, GI, ACC, CS, TH, GZ, PACK><<<grid, THREADS, 0, la.stream>>>(
         (const TI*)la.grad_out, (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.grad_init,
         (T*)la.grad_weight, (T*)la.grad_offset, la.grad_w9, la.grad_b1, (ReduceWs*)la.workspace, la.g, la.mode,
         la.scale, la.tmap, la.peer_reduce ? *la.peer_reduce : PeerReduceDev{});
@@ -433,6 +569,12 @@ static void launch_one(const LaunchArgs& la) {
 template <typename T, typename TI, bool GI, bool ACC, int TH, bool GZ = false>
 static void launch_variant(const LaunchArgs& la) {
     const size_t cs = (size_t)la.g.H * la.g.W;
+    if constexpr (sizeof(T) == 2 && !GI && !ACC) {  // bf16 on 128 x 128 planes: inputs packed two to a register
+        if (la.pair && la.use_tma && cs == 16384) {
+            launch_one<T, TI, true, GI, ACC, 16384, TH, GZ, true>(la);
+            return;
+        }
+    }
     if (la.use_tma && cs == 16384) launch_one<T, TI, true, GI, ACC, 16384, TH, GZ>(la);
     else if (la.use_tma) launch_one<T, TI, true, GI, ACC, 0, TH, GZ>(la);
     else launch_one<T, TI, false, GI, ACC, 0, TH, GZ>(la);

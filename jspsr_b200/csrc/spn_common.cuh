@@ -67,6 +67,39 @@ __device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) {
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
     return __uint_as_float(((unsigned)u) << 16);
 }
+__device__ __forceinline__ unsigned ld_stream_u16(const __nv_bfloat16* p) {  // the bf16's bits, zero-extended
+    unsigned short u;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
+    return (unsigned)u;
+}
+// two horizontally adjacent bf16 pixels as one 32-bit word (4-byte aligned: even x on rows of even length)
+__device__ __forceinline__ uint32_t ld_stream_x2(const __nv_bfloat16* p) {
+    uint32_t u;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(u) : "l"(p));
+    return u;
+}
+// half 0 = the pixel at the lower address; a bf16 widens to fp32 by moving its 16 bits to the top
+__device__ __forceinline__ float bf16x2_half(uint32_t u, int half) {
+    return __uint_as_float(half == 0 ? (u << 16) : (u & 0xffff0000u));
+}
+// two adjacent pixels of an fp32 / bf16 plane as two floats
+__device__ __forceinline__ void ld_stream_pair(const float* p, float (&v)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_pair(const __nv_bfloat16* p, float (&v)[2]) {
+    const uint32_t u = ld_stream_x2(p);
+    v[0] = bf16x2_half(u, 0);
+    v[1] = bf16x2_half(u, 1);
+}
+// the same with a per-lane choice: one PRMT, sel = 0x1044 (low half) / 0x3244 (high half)
+__device__ __forceinline__ float bf16x2_pick(uint32_t u, unsigned sel) { return __uint_as_float(__byte_perm(u, 0u, sel)); }
+__device__ __forceinline__ void st_stream_x2(float* p, float v0, float v1) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v0), "f"(v1) : "memory");
+}
+__device__ __forceinline__ void st_stream_x2(__nv_bfloat16* p, float v0, float v1) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v0, v1);  // .x = v0 (low half, lower address)
+    asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(p), "r"(*reinterpret_cast<const uint32_t*>(&b)) : "memory");
+}
 __device__ __forceinline__ void st_stream(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }

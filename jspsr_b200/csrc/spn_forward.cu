@@ -99,7 +99,12 @@ __device__ __noinline__ void strip_peer_push(const StripPeerDev& sp, const Geom&
 // that neighbour's flag before they stage their DEM tile, store their edge rows a second time into the neighbour's
 // next DEM buffer (peer memory over NVLink), and the last of them to finish raises the neighbour's flag.  All other
 // CTAs run exactly the non-PEER code, so the bulk of the band is computed while the boundary rows travel.
-template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR, bool PEER = false>
+// PAIR (bf16 weight / offset on 128-byte aligned rows): a thread owns two horizontally adjacent pixels and streams
+// their 27 channels as 27 bf16x2 words instead of 54 scalar loads, then runs the same per-pixel arithmetic on the
+// low and the high halves one after the other (identical bits).  The kernels with bf16 inputs are bound by the
+// load/store pipe (27 LDG + 36 LDS of a random gather per pixel-warp), not by HBM: halving the LDG count and
+// amortising the address arithmetic over two pixels is what this mapping buys.
+template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR, bool PEER = false, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, FWD_MIN_BLOCKS)
 spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, const T* __restrict__ offset,
                    const float* __restrict__ w9, const float* __restrict__ b1, TI* __restrict__ out,
@@ -181,12 +186,8 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         }
     };
 
-    auto compute = [&](int it, PixelIn& in) {
-        if (!in.active) return;
-        float (&a)[9] = in.a;
-        float (&oh)[9] = in.oh;
-        float (&ow)[9] = in.ow;
-        const int ry = pix_row<TH, LINEAR>(it), cx = pix_col<TH, LINEAR>(it);
+    // one pixel at tile-local (ry, cx): consumes a[] / oh[] / ow[], returns the output value
+    auto compute = [&](const int ry, const int cx, float (&a)[9], float (&oh)[9], float (&ow)[9]) -> float {
         normalise9(a, mode);
 
         // torchvision: (out_y - pad + i*dil) formed as an integer, converted, + offset
@@ -231,8 +232,158 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         for (int k = 1; k < 9; ++k) acc += a[k];
         acc += s_w[9];
         if (mode == NORM_RESIDUAL) acc = fmaf(scale, to_f32(ctr[0]), acc);
-        st_stream(out_b + in.p, acc);
+        return acc;
     };
+
+    if constexpr (PAIR) {
+        static_assert(sizeof(T) == 2 && !LINEAR && PPT >= 2, "PAIR: bf16 weight / offset, 128-byte aligned rows, >= 2 pixels per thread");
+        // pair `jt` of this thread: a warp covers 64 consecutive x of one row (lane l: x = 2 l, 2 l + 1)
+        struct PairIn {
+            uint32_t a[9], oh[9], ow[9];
+            bool active;
+            size_t p;
+        };
+        auto pair_row = [](int jt) {
+            if (TH >= 2 * WARPS) return (int)(threadIdx.x >> 5) + WARPS * (jt / (TILE_W / 64));
+            return (jt * THREADS + (int)threadIdx.x) >> 6;
+        };
+        auto pair_col = [](int jt) {
+            if (TH >= 2 * WARPS) return 2 * (int)(threadIdx.x & 31) + 64 * (jt % (TILE_W / 64));
+            return 2 * ((jt * THREADS + (int)threadIdx.x) & 63);
+        };
+        auto load_pair = [&](int jt, PairIn& in) {
+            const int y = c.y0 + pair_row(jt), x = c.x0 + pair_col(jt);
+            in.active = (y < g.H) && (x < g.W);  // W is even here: both pixels or neither
+            in.p = (size_t)y * g.W + x;
+            if (in.active) {
+                const T* pw = wgt_b + in.p;
+                const T* po = off_b + in.p;
+                if (CS) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) in.a[k] = ld_stream_x2(pw + k * cs);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        in.oh[k] = ld_stream_x2(po + (2 * k) * cs);
+                        in.ow[k] = ld_stream_x2(po + (2 * k + 1) * cs);
+                    }
+                } else {
+                    const T* pw3 = step_ptr(pw, 3 * csb);
+                    const T* pw6 = step_ptr(pw, 6 * csb);
+                    in.a[0] = ld_stream_x2(pw);
+                    in.a[1] = ld_stream_x2(step_ptr(pw, csb));
+                    in.a[2] = ld_stream_x2(step_ptr(pw, 2 * csb));
+                    in.a[3] = ld_stream_x2(pw3);
+                    in.a[4] = ld_stream_x2(step_ptr(pw3, csb));
+                    in.a[5] = ld_stream_x2(step_ptr(pw3, 2 * csb));
+                    in.a[6] = ld_stream_x2(pw6);
+                    in.a[7] = ld_stream_x2(step_ptr(pw6, csb));
+                    in.a[8] = ld_stream_x2(step_ptr(pw6, 2 * csb));
+#pragma unroll
+                    for (int k3 = 0; k3 < 3; ++k3) {
+                        const T* pb = k3 == 0 ? po : step_ptr(po, (size_t)(6 * k3) * csb);
+                        in.oh[3 * k3] = ld_stream_x2(pb);
+                        in.ow[3 * k3] = ld_stream_x2(step_ptr(pb, csb));
+                        in.oh[3 * k3 + 1] = ld_stream_x2(step_ptr(pb, 2 * csb));
+                        in.ow[3 * k3 + 1] = ld_stream_x2(step_ptr(pb, 3 * csb));
+                        in.oh[3 * k3 + 2] = ld_stream_x2(step_ptr(pb, 4 * csb));
+                        in.ow[3 * k3 + 2] = ld_stream_x2(step_ptr(pb, 5 * csb));
+                    }
+                }
+            }
+        };
+        // One pixel of the pair: half `sub` of the 27 words.  Same
+        // arithmetic, in the same order, as compute() above, arranged so that nothing but the 27 words, two normalisation
+        // constants and the running sum stays live: the affinity of tap k is widened and normalised when the tap needs it
+        // (one FFMA covers the three modes exactly: a - mean = fma(a, 1, -mean), a * inv = fma(a, inv, -0),
+        // a = fma(a, 1, -0)), and the tap contributions are summed as they come.  A pixel with an out-of-tile tap (rare) is
+        // summed again from scratch in the same tap order with those taps taken from global memory, so the result does not
+        // depend on which taps were on chip.
+        auto compute_half = [&](const int ry, const int cx, const PairIn& in, const int sub) -> float {
+            float nmul = 1.f, nadd = -0.f;
+            if (mode != NORM_NONE) {
+                float s = bf16x2_half(in.a[0], sub);
+#pragma unroll
+                for (int k = 1; k < 9; ++k) s += bf16x2_half(in.a[k], sub);
+                if (mode == NORM_RESIDUAL) nadd = -__fdiv_rn(s, 9.f);
+                else nmul = __fdiv_rn(1.f, s);
+            }
+            const float fy = (float)(g.row0 + c.y0 + ry), fx = (float)(c.x0 + cx);
+            const float hk[3] = {fy - 1.f, fy, fy + 1.f};
+            const float wk[3] = {fx - 1.f, fx, fx + 1.f};
+            const TI* ctr = tile + (ry + HALO_T) * SW + (cx + HALO_L);
+            const bool centre_fast =
+                __all_sync(__activemask(), ((__float_as_uint(bf16x2_half(in.oh[4], sub)) | __float_as_uint(bf16x2_half(in.ow[4], sub))) << 1) == 0u &&
+                                               (unsigned)(ry + HALO_T - c.r_lo) < c.r_span);
+            bool slow = false;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float m = fmaf(bf16x2_half(in.a[k], sub), nmul, nadd);
+                float val;
+                if (k == 4 && centre_fast) {
+                    val = bilerp(to_f32(ctr[0]), to_f32(ctr[1]), to_f32(ctr[SW]), to_f32(ctr[SW + 1]), 0.f, 0.f);
+                } else {
+                    const FastTap t = fast_tap<TI>(tile_lo, c, hk[k / 3] + bf16x2_half(in.oh[k], sub), wk[k % 3] + bf16x2_half(in.ow[k], sub));
+                    val = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+                    slow |= !t.ok;
+                }
+                const float ck = __fmul_rn(s_w[k] * m, val);  // (no contraction with the running sum: compute() adds
+                acc = k == 0 ? ck : __fadd_rn(acc, ck);        //  rounded products)
+            }
+            if (slow) {
+#pragma unroll  // (a rolled loop would index the words dynamically and push them into local memory)
+                for (int k = 0; k < 9; ++k) {
+                    const float m = fmaf(bf16x2_half(in.a[k], sub), nmul, nadd);
+                    const float h = hk[k / 3] + bf16x2_half(in.oh[k], sub), w = wk[k % 3] + bf16x2_half(in.ow[k], sub);
+                    const FastTap t = fast_tap<TI>(tile_lo, c, h, w);
+                    float val = bilerp(t.v1, t.v2, t.v3, t.v4, t.lh, t.lw);
+                    if (!t.ok) {
+                        const SlowTap u = slow_tap<TI>(init_b, g, h, w, status);
+                        val = bilerp(u.v1, u.v2, u.v3, u.v4, u.lh, u.lw);
+                    }
+                    const float ck = __fmul_rn(s_w[k] * m, val);
+                    acc = k == 0 ? ck : __fadd_rn(acc, ck);
+                }
+            }
+            acc += s_w[9];
+            if (mode == NORM_RESIDUAL) acc = fmaf(scale, to_f32(ctr[0]), acc);
+            return acc;
+        };
+        // Lanes 0..15 take their left pixel first, lanes 16..31 their right one: in either pass the warp's 32 pixels sit
+        // at x = 2 l + (l >= 16), i.e. on 32 different shared-memory banks when the offsets agree - with every lane on its
+        // left pixel, lanes l and l + 16 are 32 columns apart and share a bank (ncu: 121 instead of 99 shared wavefronts
+        // per pixel-warp, on a kernel whose load/store pipe is 89 % busy).  The upper lanes swap the halves of their words
+        // once after the load (a per-lane byte selector in the unpacking itself made ptxas spill 18 of the 27 words).
+        const int first = (int)((threadIdx.x >> 4) & 1u);
+        const unsigned swap_sel = first ? 0x1032u : 0x3210u;
+        PairIn cur;
+        auto swap_halves = [&](PairIn& in) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                in.a[k] = __byte_perm(in.a[k], 0u, swap_sel);
+                in.oh[k] = __byte_perm(in.oh[k], 0u, swap_sel);
+                in.ow[k] = __byte_perm(in.ow[k], 0u, swap_sel);
+            }
+        };
+        load_pair(0, cur);
+        stage_tile_wait<TMA>(&bar);
+#pragma unroll 1
+        for (int jt = 0; jt < PPT / 2; ++jt) {
+            __syncwarp();
+            if (jt > 0) load_pair(jt, cur);
+            const int ry = pair_row(jt), cx = pair_col(jt);
+            float ra = 0.f, rb = 0.f;
+            if (cur.active) {
+                swap_halves(cur);
+                ra = compute_half(ry, cx + first, cur, 0);
+            }
+            __syncwarp();  // the first pixel may have split the warp on its out-of-tile path
+            if (cur.active) rb = compute_half(ry, cx + (first ^ 1), cur, 1);
+            if (cur.active) st_stream_x2(out_b + cur.p, first ? rb : ra, first ? ra : rb);
+        }
+        if (PEER) strip_peer_push<TI, TH>(sp, g, out);
+        return;
+    }
 
     // the first pixel's 27 streamed loads are in flight while the tile lands
     PixelIn cur;
@@ -247,16 +398,16 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
         __syncwarp();  // lanes that took the out-of-tile path on the previous pixel rejoin here: without it a warp stays split for the
                        // rest of the loop (ncu: 5.8 active threads per instruction with far offsets), every later pixel issued per fragment
         if (it > 0) load_inputs(it, cur);
-        compute(it, cur);
+        if (cur.active) st_stream(out_b + cur.p, compute(pix_row<TH, LINEAR>(it), pix_col<TH, LINEAR>(it), cur.a, cur.oh, cur.ow));
     }
 
     if (PEER) strip_peer_push<TI, TH>(sp, g, out);
 }
 
-template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR, bool PEER = false>
+template <typename T, typename TI, bool TMA, int CS, int TH, bool LINEAR, bool PEER = false, bool PAIR = false>
 static void launch_fwd_one(const LaunchArgs& la) {
     dim3 grid((unsigned)((size_t)la.g.tiles_x * la.g.tiles_y * la.g.B));
-    spn_forward_kernel<T, TI, TMA, CS, TH, LINEAR, PEER><<<grid, THREADS, 0, la.stream>>>(
+    spn_forward_kernel<T, TI, TMA, CS, TH, LINEAR, PEER, PAIR><<<grid, THREADS, 0, la.stream>>>(
         (const TI*)la.init, (const T*)la.weight, (const T*)la.offset, la.w9, la.b1, (TI*)la.out, la.g, la.mode, la.scale,
         la.status, la.tmap, PEER ? *la.strip_peer : StripPeerDev{});
 }
@@ -278,6 +429,12 @@ template <typename T, typename TI, int TH>
 static void launch_fwd_th(const LaunchArgs& la) {
     const size_t cs = (size_t)la.g.H * la.g.W;
     const bool aligned = ((size_t)la.g.W * sizeof(T)) % 128 == 0;
+    if constexpr (sizeof(T) == 2 && TH >= 4) {  // bf16 weight / offset on 128 x 128 planes: two pixels per thread
+        if (la.pair && la.use_tma && cs == 16384 && aligned) {
+            launch_fwd_one<T, TI, true, 16384, TH, false, false, true>(la);
+            return;
+        }
+    }
     if (la.use_tma && cs == 16384 && aligned) launch_fwd_one<T, TI, true, 16384, TH, false>(la);
     else if (la.use_tma && aligned) launch_fwd_one<T, TI, true, 0, TH, false>(la);
     else if (la.use_tma) launch_fwd_one<T, TI, true, 0, TH, true>(la);

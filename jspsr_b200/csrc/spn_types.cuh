@@ -75,6 +75,7 @@ struct LaunchArgs {
     bool bf16 = false;      // weight / offset (and their gradients) are bf16
     bool init_f32 = false;  // with bf16: init / out / grad_out stay fp32 (JSPSR_MIXED, what torch.autocast produces)
     bool use_tma = false;
+    bool pair = false;      // bf16 weight / offset streamed as bf16x2 words, two pixels per thread (abi.cu: pair_ok)
     int* status = nullptr;
     int tile_h = 16;  // rows per CTA (16 / 8 / 4 / 2), chosen by abi.cu; the TMA box is encoded to match
     cudaStream_t stream = nullptr;

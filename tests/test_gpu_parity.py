@@ -407,6 +407,56 @@ def test_bf16_io_against_fp32_oracle_on_rounded_inputs(jb, mode):
         assert_close(got[k], ref[k], 1e-4, "bf16 " + k)
 
 
+@pytest.mark.parametrize("io", ["bf16", "mixed"])
+def test_bf16_two_pixel_and_packed_kernels_on_128x128_planes(jb, io, monkeypatch):
+    """128 x 128 planes with bf16 weight / offset take the two-pixels-per-thread forward (spn_forward.cu, PAIR) and the
+    packed-register backward (spn_backward.cu, PACK).  Both are the one-pixel kernels' arithmetic in another order of
+    issue: bit-identical to JSPSR_SPN_PAIR=0 for every normalisation mode, tile height, on-chip and out-of-tile taps
+    (sigma 16 sends two thirds of the taps through the global path), and within the bf16 bound of the fp32 oracle."""
+    from jspsr_b200 import functional as F
+    dt = torch.bfloat16
+    dti = torch.bfloat16 if io == "bf16" else torch.float32
+    for B, sigma, ths in ((3, 1.5, ("16", "8", "4")), (2, 16.0, ("16", "8")), (40, 1.5, (None,))):
+        init, weight, offset, gout, w9, b1 = make_inputs(71 + B, B, 128, 128, sigma)
+        ti, tg = dev(init, dti), dev(gout, dti)
+        tw, to = dev(weight, dt), dev(offset, dt)
+        w, b = dev(w9.reshape(1, 1, 3, 3)), dev(b1)
+        for th in ths:
+            if th is None:
+                monkeypatch.delenv("JSPSR_SPN_TILE_H", raising=False)
+            else:
+                monkeypatch.setenv("JSPSR_SPN_TILE_H", th)
+            for mode in (0, 1, 2):
+                res = {}
+                for pair in ("0", "1"):
+                    monkeypatch.setenv("JSPSR_SPN_PAIR", pair)
+                    res[pair] = (F.spn_forward(ti, tw, to, w, b, mode, 0.7),
+                                 F.spn_backward(tg, ti, tw, to, w, mode, 0.7, need_grad_init=False))
+                tag = f"{io} B={B} sigma={sigma} th={th} mode={mode}"
+                assert torch.equal(res["0"][0], res["1"][0]), "out " + tag
+                assert torch.equal(res["0"][1][1], res["1"][1][1]), "grad_weight " + tag
+                assert torch.equal(res["0"][1][2], res["1"][1][2]), "grad_offset " + tag
+                assert_close(res["1"][1][3], res["0"][1][3].double().cpu().numpy(), 1e-6, "grad_w " + tag, gout=tg)
+                assert_close(res["1"][1][4], res["0"][1][4].double().cpu().numpy(), 1e-6, "grad_b " + tag, gout=tg)
+        monkeypatch.delenv("JSPSR_SPN_TILE_H", raising=False)
+        monkeypatch.setenv("JSPSR_SPN_PAIR", "1")
+        if B == 3:  # against the oracle on the rounded inputs: fp64 for the output, fp32 for the gradients (a tap whose
+                    # fp32 position rounds onto an integer row takes the other one-sided derivative: module docstring)
+            rnd = lambda a, t: torch.from_numpy(a).to(t).to(torch.float32).numpy()
+            ri, rg, rw, ro = rnd(init, dti), rnd(gout, dti), rnd(weight, dt), rnd(offset, dt)
+            d = lambda a: a.astype(np.float64)
+            for mode in (1, 2):
+                out = F.spn_forward(ti, tw, to, w, b, mode, 0.7)
+                g = F.spn_backward(tg, ti, tw, to, w, mode, 0.7, need_grad_init=False)
+                ref_out = C.forward(d(ri), d(rw), d(ro), d(w9), d(b1), mode, 0.7)
+                ref = C.backward(rg, ri, rw, ro, w9, mode, 0.7)
+                assert_close(out, ref_out, BF16_TOL if io == "bf16" else FP32_TOL, f"{io} out mode {mode}")
+                assert_close(g[1], ref["grad_weight"], BF16_TOL, f"{io} grad_weight mode {mode}")
+                assert_close(g[2], ref["grad_offset"], BF16_TOL, f"{io} grad_offset mode {mode}")
+                assert_close(g[3], ref["grad_w"].reshape(1, 1, 3, 3), 1e-4, f"{io} grad_w mode {mode}")
+                assert_close(g[4], ref["grad_b"].reshape(1), 1e-4, f"{io} grad_b mode {mode}")
+
+
 # ---------------------------------------------------------------------------
 # (3) properties at BASELINE.json sizes
 # ---------------------------------------------------------------------------
