@@ -418,6 +418,8 @@ def test_bf16_two_pixel_and_packed_kernels_on_128x128_planes(jb, io, monkeypatch
     dti = torch.bfloat16 if io == "bf16" else torch.float32
     for B, sigma, ths in ((3, 1.5, ("16", "8", "4")), (2, 16.0, ("16", "8")), (40, 1.5, (None,))):
         init, weight, offset, gout, w9, b1 = make_inputs(71 + B, B, 128, 128, sigma)
+        if B == 2:  # non-finite and absurd offsets go through the same out-of-tile path (bits compared, NaN included)
+            offset[0, 0, 5, 7], offset[0, 3, 64, 64], offset[1, 17, 127, 126], offset[1, 6, 0, 1] = np.inf, np.nan, -np.inf, 3.0e38
         ti, tg = dev(init, dti), dev(gout, dti)
         tw, to = dev(weight, dt), dev(offset, dt)
         w, b = dev(w9.reshape(1, 1, 3, 3)), dev(b1)
@@ -433,9 +435,12 @@ def test_bf16_two_pixel_and_packed_kernels_on_128x128_planes(jb, io, monkeypatch
                     res[pair] = (F.spn_forward(ti, tw, to, w, b, mode, 0.7),
                                  F.spn_backward(tg, ti, tw, to, w, mode, 0.7, need_grad_init=False))
                 tag = f"{io} B={B} sigma={sigma} th={th} mode={mode}"
-                assert torch.equal(res["0"][0], res["1"][0]), "out " + tag
-                assert torch.equal(res["0"][1][1], res["1"][1][1]), "grad_weight " + tag
-                assert torch.equal(res["0"][1][2], res["1"][1][2]), "grad_offset " + tag
+                bits = lambda t: t.view(torch.int16 if t.dtype == torch.bfloat16 else torch.int32)
+                assert torch.equal(bits(res["0"][0]), bits(res["1"][0])), "out " + tag
+                assert torch.equal(bits(res["0"][1][1]), bits(res["1"][1][1])), "grad_weight " + tag
+                assert torch.equal(bits(res["0"][1][2]), bits(res["1"][1][2])), "grad_offset " + tag
+                if B == 2:
+                    continue  # grad_w / grad_b are NaN there
                 assert_close(res["1"][1][3], res["0"][1][3].double().cpu().numpy(), 1e-6, "grad_w " + tag, gout=tg)
                 assert_close(res["1"][1][4], res["0"][1][4].double().cpu().numpy(), 1e-6, "grad_b " + tag, gout=tg)
         monkeypatch.delenv("JSPSR_SPN_TILE_H", raising=False)
