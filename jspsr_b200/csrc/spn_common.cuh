@@ -91,8 +91,6 @@ __device__ __forceinline__ void ld_stream_pair(const __nv_bfloat16* p, float (&v
     v[0] = bf16x2_half(u, 0);
     v[1] = bf16x2_half(u, 1);
 }
-// the same with a per-lane choice: one PRMT, sel = 0x1044 (low half) / 0x3244 (high half)
-__device__ __forceinline__ float bf16x2_pick(uint32_t u, unsigned sel) { return __uint_as_float(__byte_perm(u, 0u, sel)); }
 __device__ __forceinline__ void st_stream_x2(float* p, float v0, float v1) {
     asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v0), "f"(v1) : "memory");
 }

@@ -244,7 +244,7 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
     };
 
     if constexpr (PAIR) {
-        static_assert(sizeof(T) == 2 && !LINEAR && PPT >= 2, "PAIR: bf16 weight / offset, 128-byte aligned rows, >= 2 pixels per thread");
+        static_assert(sizeof(T) == 2 && CS != 0 && !LINEAR && PPT >= 2, "PAIR: bf16 weight / offset, compile-time stride, 128-byte aligned rows, >= 2 pixels per thread");
         // pair `jt` of this thread: a warp covers 64 consecutive x of one row (lane l: x = 2 l, 2 l + 1)
         struct PairIn {
             uint32_t a[9], oh[9], ow[9];
@@ -266,36 +266,12 @@ spn_forward_kernel(const TI* __restrict__ init, const T* __restrict__ weight, co
             if (in.active) {
                 const T* pw = wgt_b + in.p;
                 const T* po = off_b + in.p;
-                if (CS) {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) in.a[k] = ld_stream_x2(pw + k * cs);
+                for (int k = 0; k < 9; ++k) in.a[k] = ld_stream_x2(pw + k * cs);
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        in.oh[k] = ld_stream_x2(po + (2 * k) * cs);
-                        in.ow[k] = ld_stream_x2(po + (2 * k + 1) * cs);
-                    }
-                } else {
-                    const T* pw3 = step_ptr(pw, 3 * csb);
-                    const T* pw6 = step_ptr(pw, 6 * csb);
-                    in.a[0] = ld_stream_x2(pw);
-                    in.a[1] = ld_stream_x2(step_ptr(pw, csb));
-                    in.a[2] = ld_stream_x2(step_ptr(pw, 2 * csb));
-                    in.a[3] = ld_stream_x2(pw3);
-                    in.a[4] = ld_stream_x2(step_ptr(pw3, csb));
-                    in.a[5] = ld_stream_x2(step_ptr(pw3, 2 * csb));
-                    in.a[6] = ld_stream_x2(pw6);
-                    in.a[7] = ld_stream_x2(step_ptr(pw6, csb));
-                    in.a[8] = ld_stream_x2(step_ptr(pw6, 2 * csb));
-#pragma unroll
-                    for (int k3 = 0; k3 < 3; ++k3) {
-                        const T* pb = k3 == 0 ? po : step_ptr(po, (size_t)(6 * k3) * csb);
-                        in.oh[3 * k3] = ld_stream_x2(pb);
-                        in.ow[3 * k3] = ld_stream_x2(step_ptr(pb, csb));
-                        in.oh[3 * k3 + 1] = ld_stream_x2(step_ptr(pb, 2 * csb));
-                        in.ow[3 * k3 + 1] = ld_stream_x2(step_ptr(pb, 3 * csb));
-                        in.oh[3 * k3 + 2] = ld_stream_x2(step_ptr(pb, 4 * csb));
-                        in.ow[3 * k3 + 2] = ld_stream_x2(step_ptr(pb, 5 * csb));
-                    }
+                for (int k = 0; k < 9; ++k) {
+                    in.oh[k] = ld_stream_x2(po + (2 * k) * cs);
+                    in.ow[k] = ld_stream_x2(po + (2 * k + 1) * cs);
                 }
             }
         };
