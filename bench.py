@@ -905,6 +905,28 @@ def config_batch_latency(torch, jspsr_b200, F, device, dtype):
         e1.record()
         torch.cuda.synchronize()
         res[f"B{B}"] = {"us_per_fwd_bwd": e0.elapsed_time(e1) / n * 1e3, "l2_resident": True}
+        if dtype == torch.float32 and B == 70:
+            # BASELINE config 2 at its own batch: the tensors torch.autocast(bfloat16) hands to the layer (bf16 weight /
+            # offset from the Generator's convolutions, fp32 DEM), same two launches in a graph
+            wb, ob = weight.detach().bfloat16(), offset.detach().bfloat16()
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    F.spn_forward(init, wb, ob, w, b, 1, 1.0)
+                    F.spn_backward(gout, init, wb, ob, w, 1, 1.0, need_grad_init=False)
+            torch.cuda.current_stream().wait_stream(s)
+            graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_a, stream=s):
+                F.spn_forward(init, wb, ob, w, b, 1, 1.0)
+                F.spn_backward(gout, init, wb, ob, w, 1, 1.0, need_grad_init=False)
+            for _ in range(5):
+                graph_a.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                graph_a.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"B{B}"]["autocast_bf16_us_per_fwd_bwd"] = e0.elapsed_time(e1) / n * 1e3
         if dtype == torch.float32:
             # the training step as train/train_utils.py:205-214 chains it: propagation -> MultiLoss (L1 + L2 + 0.1 Grad,
             # losses and dTotal/dpred in one kernel) -> propagation backward, three launches in one graph
