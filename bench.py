@@ -718,6 +718,30 @@ def side_numbers(torch, F, device, B):
                           "bwd_frac_of_hbm_peak": BWD_BYTES["f32"] * rs * rs / (g * 1e-3) / 1e9 / peak}
     del r_init, r_w, r_o, r_g
     torch.cuda.empty_cache()
+    # SURVEY.md section 8d's largest single-image shape: 16384 x 16384 (31 GB of inputs, 29 GB of gradients), built
+    # plane by plane so that the generator never holds a second copy
+    if torch.cuda.mem_get_info(device)[0] > 90e9:
+        try:
+            rs = 16384
+            r_init = torch.rand(1, 1, rs, rs, device=device, generator=gr)
+            r_w = torch.empty(1, 9, rs, rs, device=device)
+            r_o = torch.empty(1, 18, rs, rs, device=device)
+            for k in range(9):
+                r_w[0, k] = torch.sigmoid(1.5 * torch.randn(rs, rs, device=device, generator=gr))
+            for k in range(18):
+                r_o[0, k] = (1.5 * torch.randn(rs, rs, device=device, generator=gr)).clamp_(-8, 8)
+            r_o[:, 8:10] = 0
+            r_g = torch.randn(1, 1, rs, rs, device=device, generator=gr)
+            f = timed(lambda: F.spn_forward(r_init, r_w, r_o, w, b, 1, 1.0), n=3, warm=1)
+            g = timed(lambda: F.spn_backward(r_g, r_init, r_w, r_o, w, 1, 1.0, need_grad_init=False), n=3, warm=1)
+            out["raster_16384"] = {"fwd_ms": f, "bwd_ms": g,
+                                   "fwd_frac_of_hbm_peak": FWD_BYTES["f32"] * rs * rs / (f * 1e-3) / 1e9 / peak,
+                                   "bwd_frac_of_hbm_peak": BWD_BYTES["f32"] * rs * rs / (g * 1e-3) / 1e9 / peak}
+            del r_init, r_w, r_o, r_g
+            torch.cuda.empty_cache()
+        except RuntimeError as e:  # reported, never fatal for the bench line
+            out["raster_16384"] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
     T = 6
     aff = weight * 0.1
     it = timed(lambda: F.spn_iterate(init, aff, offset, T), n=3)

@@ -465,11 +465,37 @@ loss_l1_l2_grad_kernel(const float* __restrict__ pred, const float* __restrict__
     }
 }
 
-// One CTA: a slab of rows of one sample's border-cropped window; a warp per row, lanes along x, four columns of a
-// row in flight per lane.  sums[b] = {sum d^2, sum |d|} (fp64 atomics).
+// (pred, gt) -> de-normalised elevation difference of one pixel (MeterBase._prepare clamps pred only)
+template <bool ELEV_LOG>
+__device__ __forceinline__ float denorm_diff(float p, float g, float log_range, float range, float vmin) {
+    const float pc = fminf(fmaxf(p, 0.f), 1.f);
+    float pe, ge;
+    if (ELEV_LOG) {
+        pe = expf(pc * log_range) + vmin;
+        ge = expf(g * log_range) + vmin;
+    } else {
+        pe = __fadd_rn(__fmul_rn(pc, range), vmin);
+        ge = __fadd_rn(__fmul_rn(g, range), vmin);
+    }
+    return pe - ge;
+}
+
+// One CTA: a slab of rows of one sample's border-cropped window.  sums[b] = {sum d^2, sum |d|} (fp64 atomics).
+//
+// VEC (W % 4 == 0, 16-byte aligned planes): a lane owns four consecutive columns of the 16-byte aligned span that
+// covers the window and reads them with one 128-bit load per tensor; the (at most three) columns of the first and last
+// word that belong to the border are dropped by a per-lane mask that does not depend on the row, and a warp has
+// MET_ROWS rows in flight (2 x MET_ROWS 128-bit loads per lane before the first exponential).  The scalar kernel spent
+// 16 of its 43 instructions per pixel on predicated addresses and per-pixel branches and sat at its issue limit
+// (0.53 of the HBM rate at 4096 tiles); this form executes about half as many.
+// !VEC: a warp per row, lanes along x, four columns of a row in flight per lane.
+// Per-pixel arithmetic is the same expression in both, and the fp32 partial sums are folded into fp64 after at most
+// a few dozen pixels, so the two differ only in the association of those short fp32 sums.
+constexpr int MET_ROWS = 4;
+template <bool ELEV_LOG, bool VEC>
 __global__ void __launch_bounds__(THREADS)
 dem_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, double* __restrict__ sums, int H, int W,
-                   int bh, int bw, float log_range, float range, float vmin, int elev_log, int rows_per_cta) {
+                   int bh, int bw, float log_range, float range, float vmin, int rows_per_cta) {
     __shared__ double s_red[WARPS][2];
     const int b = blockIdx.y;
     const int hc = H - 2 * bh, wc = W - 2 * bw;
@@ -477,38 +503,74 @@ dem_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
     const size_t plane = (size_t)b * H * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double d_sq = 0.0, d_ab = 0.0;
-    for (int r = r0 + warp; r < r1; r += WARPS) {
-        const size_t row = plane + (size_t)(bh + r) * W + bw;
-        float a_sq = 0.f, a_ab = 0.f;
-        for (int c0 = lane; c0 < wc; c0 += 128) {
-            float pv[4], gv[4];
+    if (VEC) {
+        const int ca = bw & ~3;                           // first column of the aligned span
+        const int n4 = (W - bw + 3 - ca) >> 2;            // 128-bit words covering columns [bw, W - bw)
+        for (int r = r0 + warp; r < r1; r += WARPS * MET_ROWS) {
+            float a_sq = 0.f, a_ab = 0.f;
+            for (int q = lane; q < n4; q += 32) {
+                const int c = ca + 4 * q;
+                float4 pv[MET_ROWS], gv[MET_ROWS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + 32 * u;
-                pv[u] = (c < wc) ? __ldcs(pred + row + c) : 0.f;
-                gv[u] = (c < wc) ? __ldcs(gt + row + c) : 0.f;
-            }
+                for (int u = 0; u < MET_ROWS; ++u) {
+                    // rows past the slab re-read its last row (valid memory) and are skipped below (warp-uniform)
+                    const size_t o = plane + (size_t)(bh + min(r + u * WARPS, r1 - 1)) * W + c;
+                    pv[u] = __ldcs(reinterpret_cast<const float4*>(pred + o));
+                    gv[u] = __ldcs(reinterpret_cast<const float4*>(gt + o));
+                }
+                const bool m0 = c >= bw && c < W - bw, m1 = c + 1 >= bw && c + 1 < W - bw;
+                const bool m2 = c + 2 >= bw && c + 2 < W - bw, m3 = c + 3 >= bw && c + 3 < W - bw;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (c0 + 32 * u < wc) {
-                    const float pc = fminf(fmaxf(pv[u], 0.f), 1.f);   // MeterBase._prepare clamps pred only
-                    float pe, ge;
-                    if (elev_log) {
-                        pe = expf(pc * log_range) + vmin;
-                        ge = expf(gv[u] * log_range) + vmin;
-                    } else {
-                        pe = __fadd_rn(__fmul_rn(pc, range), vmin);
-                        ge = __fadd_rn(__fmul_rn(gv[u], range), vmin);
+                for (int u = 0; u < MET_ROWS; ++u) {
+                    if (r + u * WARPS < r1) {
+                        float d;
+                        d = denorm_diff<ELEV_LOG>(pv[u].x, gv[u].x, log_range, range, vmin);
+                        d = m0 ? d : 0.f;   // a select, not a product: border pixels may hold anything
+                        a_sq = fmaf(d, d, a_sq);
+                        a_ab += fabsf(d);
+                        d = denorm_diff<ELEV_LOG>(pv[u].y, gv[u].y, log_range, range, vmin);
+                        d = m1 ? d : 0.f;
+                        a_sq = fmaf(d, d, a_sq);
+                        a_ab += fabsf(d);
+                        d = denorm_diff<ELEV_LOG>(pv[u].z, gv[u].z, log_range, range, vmin);
+                        d = m2 ? d : 0.f;
+                        a_sq = fmaf(d, d, a_sq);
+                        a_ab += fabsf(d);
+                        d = denorm_diff<ELEV_LOG>(pv[u].w, gv[u].w, log_range, range, vmin);
+                        d = m3 ? d : 0.f;
+                        a_sq = fmaf(d, d, a_sq);
+                        a_ab += fabsf(d);
                     }
-                    const float d = pe - ge;
-                    a_sq += d * d;
-                    a_ab += fabsf(d);
                 }
             }
+            // fold the fp32 partials (4 x MET_ROWS pixels per 128 columns) into fp64 so that long windows do not lose low bits
+            d_sq += (double)a_sq;
+            d_ab += (double)a_ab;
         }
-        // fold the fp32 row partials into fp64 so that long windows do not lose low bits
-        d_sq += (double)a_sq;
-        d_ab += (double)a_ab;
+    } else {
+        for (int r = r0 + warp; r < r1; r += WARPS) {
+            const size_t row = plane + (size_t)(bh + r) * W + bw;
+            float a_sq = 0.f, a_ab = 0.f;
+            for (int c0 = lane; c0 < wc; c0 += 128) {
+                float pv[4], gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + 32 * u;
+                    pv[u] = (c < wc) ? __ldcs(pred + row + c) : 0.f;
+                    gv[u] = (c < wc) ? __ldcs(gt + row + c) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c0 + 32 * u < wc) {
+                        const float d = denorm_diff<ELEV_LOG>(pv[u], gv[u], log_range, range, vmin);
+                        a_sq = fmaf(d, d, a_sq);
+                        a_ab += fabsf(d);
+                    }
+                }
+            }
+            d_sq += (double)a_sq;
+            d_ab += (double)a_ab;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -614,16 +676,27 @@ extern "C" int jspsr_dem_metrics(const float* pred, const float* gt, double* sum
     cudaError_t ce = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B, (cudaStream_t)stream);
     if (ce == cudaSuccess) {
         const int hc = H - 2 * border_h;
-        // enough CTAs to fill the GPU twice over (8 resident per SM), at least one row per warp each
-        int slabs = (2 * 148 * 8 + B - 1) / B;
-        slabs = max(1, min(slabs, (hc + WARPS - 1) / WARPS));
+        const bool vec = (W % 4 == 0) && !(((uintptr_t)pred | (uintptr_t)gt) & 15);
+        // enough CTAs for four full waves (8 resident per SM: 4096 one-CTA samples would be 3.46 waves, the last one
+        // half empty), at least one row per warp each; the float4 kernel keeps MET_ROWS rows per warp in flight
+        int slabs = (4 * 148 * 8 + B - 1) / B;
+        const int min_rows = vec ? WARPS * MET_ROWS : WARPS;
+        slabs = max(1, min(slabs, (hc + min_rows - 1) / min_rows));
         const int rows_per_cta = (hc + slabs - 1) / slabs;
         slabs = (hc + rows_per_cta - 1) / rows_per_cta;
         const float range = (float)((double)value_max - (double)value_min);
         // data * log(max - min): the reference multiplies by the python float (double) rounded into the fp32 tensor op
         const float log_range = elev_log ? (float)log((double)value_max - (double)value_min) : 0.f;
-        dem_metrics_kernel<<<dim3((unsigned)slabs, (unsigned)B), THREADS, 0, (cudaStream_t)stream>>>(
-            pred, gt, sums, H, W, border_h, border_w, log_range, range, value_min, elev_log, rows_per_cta);
+        const dim3 ctas((unsigned)slabs, (unsigned)B);
+#define JSPSR_LAUNCH_METRICS(E, V)                                                                  \
+    dem_metrics_kernel<E, V><<<ctas, THREADS, 0, (cudaStream_t)stream>>>(pred, gt, sums, H, W, border_h, border_w, \
+                                                                       log_range, range, value_min, rows_per_cta)
+        if (elev_log) {
+            if (vec) JSPSR_LAUNCH_METRICS(true, true); else JSPSR_LAUNCH_METRICS(true, false);
+        } else {
+            if (vec) JSPSR_LAUNCH_METRICS(false, true); else JSPSR_LAUNCH_METRICS(false, false);
+        }
+#undef JSPSR_LAUNCH_METRICS
         ce = cudaGetLastError();
     }
     if (ce != cudaSuccess) {

@@ -259,6 +259,32 @@ def test_metrics_match_oracle(jb, B, H, W, border):
         assert np.allclose(m["mae"].cpu().numpy(), o["mae"], rtol=2e-6, atol=0)
 
 
+@pytest.mark.parametrize("H,W,border", [(40, 36, 0.07), (128, 128, 0.05), (64, 260, 0.02), (37, 52, 0.1)])
+def test_metrics_ignore_whatever_the_border_holds(jb, H, W, border):
+    """The float4 kernel reads whole 16-byte words and drops the border columns of the first / last word by a select:
+    non-finite values in the cropped border (rows and columns) must not reach the sums, whatever the alignment of the
+    window's first column."""
+    rng = np.random.default_rng(H * W)
+    gt = rng.random((3, 1, H, W)).astype(np.float32)
+    pred = (gt + 0.02 * rng.normal(size=gt.shape)).astype(np.float32)
+    bh, bw = int(H * border), int(W * border)
+    assert bh > 0 and bw > 0
+    dirty_p, dirty_g = pred.copy(), gt.copy()
+    for a, v in ((dirty_p, np.nan), (dirty_g, np.inf)):
+        a[..., :bh, :] = v
+        a[..., H - bh:, :] = v
+        a[..., :, :bw] = v
+        a[..., :, W - bw:] = v
+    for elev_log in (True, False):
+        clean = jb.epilogue.dem_metrics(dev(pred), dev(gt), border, -80.0, 929.0, elev_log)
+        dirty = jb.epilogue.dem_metrics(dev(dirty_p), dev(dirty_g), border, -80.0, 929.0, elev_log)
+        o = E.dem_metrics(pred, gt, border, -80.0, 929.0, elev_log)
+        for key in ("sum_sq", "mae", "rmse"):
+            assert torch.equal(clean[key], dirty[key]), key
+        assert np.allclose(clean["rmse"].cpu().numpy(), o["rmse"], rtol=2e-6, atol=0)
+        assert np.allclose(clean["mae"].cpu().numpy(), o["mae"], rtol=2e-6, atol=0)
+
+
 # ------------------------------------------------------------------ the rows chained as the reference chains them
 def _prop_inputs(rng, n, k, sigma=1.5):
     weight = (1.0 / (1.0 + np.exp(-1.5 * rng.normal(size=(n, 9, k, k))))).astype(np.float32)
