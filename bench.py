@@ -742,6 +742,34 @@ def side_numbers(torch, F, device, B):
         except RuntimeError as e:  # reported, never fatal for the bench line
             out["raster_16384"] = {"error": str(e)[:200]}
             torch.cuda.empty_cache()
+    # SURVEY.md section 8d's T = 4: the LRRU-style cascade (LRRU.py:447-498) - four applications, each with fresh
+    # weights / offsets, the previous output detached and blended with the valid input pixels by the model's own
+    # torch code ((1 - mask) * out + mask * d_clear) in between.  Four quarter-batches stand in for the four stages.
+    nq = B // 4
+    if nq > 0:
+        d_clear = init[:nq] * (torch.rand(nq, 1, TILE, TILE, device=device) > 0.9)
+
+        def lrru(blend):
+            o = init[:nq]
+            for st in range(4):
+                if blend == "torch":
+                    mask = torch.sum(d_clear > 0.0, dim=1, keepdim=True)
+                    mask = (mask > 0.0).type_as(d_clear)
+                    o = (1.0 - mask) * o + mask * d_clear
+                elif blend == "kernel":
+                    o = F.preserve_blend(o, d_clear)
+                o = F.spn_forward(o.detach(), weight[st * nq:(st + 1) * nq], offset[st * nq:(st + 1) * nq], w, b, 1, 1.0)
+            return o
+        t0 = timed(lambda: lrru(None), n=3)
+        t1 = timed(lambda: lrru("torch"), n=3)
+        t2 = timed(lambda: lrru("kernel"), n=3)
+        out["lrru_cascade_T4"] = {"tiles": nq, "ms": t0, "gpix_iter_per_s": 4 * nq * TILE * TILE / (t0 * 1e-3) / 1e9,
+                                  "frac_of_hbm_peak": 4 * FWD_BYTES["f32"] * nq * TILE * TILE / (t0 * 1e-3) / 1e9 / peak,
+                                  "ms_with_the_models_torch_blend": t1, "ms_with_preserve_blend_kernel": t2,
+                                  "note": "4 forward launches with fresh weights (Post_process_deconv x 4); the blend between "
+                                          "stages is the reference model's own elementwise torch code (six launches), outside "
+                                          "the module; jspsr_preserve_blend does the same arithmetic in one pass"}
+        del d_clear
     T = 6
     aff = weight * 0.1
     it = timed(lambda: F.spn_iterate(init, aff, offset, T), n=3)

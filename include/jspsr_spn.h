@@ -195,6 +195,17 @@ int jspsr_spn_iterate(const void *feat_init, const void *aff, const void *offset
                       int B, int H, int W, int T, int dtype, void *stream);
 
 /*
+ * Input-preservation blend of the LRRU cascade (models/LRRU.py:447-451, 460-464, 474-478, 488-492) for a
+ * single-channel `fix` (d_clear): dst = (1 - m) * feat + m * fix with m = (fix > 0), element by element over n
+ * elements, one pass instead of the six elementwise kernels of
+ *     mask = (torch.sum(d_clear > 0.0, dim=1, keepdim=True) > 0.0).type_as(d_clear)
+ *     output = (1.0 - mask) * output + mask * d_clear
+ * (same roundings: both products, then the sum).  dst may alias feat.  dtype 0 f32 / 1 bf16 for all three.
+ */
+int jspsr_preserve_blend(const void *feat, const void *fix, void *dst, long long n, int dtype,
+                         void *stream);
+
+/*
  * NLSPN affinity front-end after conv_offset_aff (models/components/nlspn.py:82-175):
  * offset re-packing with the zero centre pair, tanh/gamma scaling, confidence gating
  * (eight 1-tap deformable gathers), abs-sum normalisation, centre weight.

@@ -18,6 +18,8 @@ cudaError_t launch_offset_absmax(const void* offset, size_t n_pairs_block, size_
 cudaError_t launch_halo_push(const void* band, int Hs, int W, bool bf16, const StripPeerDev& sp, cudaStream_t stream);
 cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const float* mask_fix, void* dst, size_t n,
                                   bool bf16, cudaStream_t stream);
+cudaError_t launch_preserve_blend_auto(const void* feat, const void* fix, void* dst, size_t n, bool bf16,
+                                       cudaStream_t stream);
 // The tile kernels exist twice (spn_common.cuh): `wide` stages a 14/15-row, 16-column halo, `narrow` 6/7 rows and
 // 8 columns.  Wide wins on tile batches, narrow on whole rasters; the launcher picks by image width.
 #define JSPSR_DECLARE_VARIANT(NS)                                                                                       \
@@ -531,6 +533,19 @@ int jspsr_spn_offset_absmax(const void* offset, int B, int H, int W, int dtype, 
     if (!offset || !out2) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
     cudaError_t ce = launch_offset_absmax(offset, 0, (size_t)H * W, B, dtype == JSPSR_BF16, out2, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "offset_absmax launch");
+    return JSPSR_OK;
+}
+
+int jspsr_preserve_blend(const void* feat, const void* fix, void* dst, long long n, int dtype, void* stream) {
+    if (n < 0) return fail(JSPSR_ERR_BAD_ARG, "jspsr_preserve_blend: n=%lld is negative", n);
+    if (dtype != JSPSR_F32 && dtype != JSPSR_BF16)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_preserve_blend: dtype %d (one dtype for the three tensors: 0 f32, 1 bf16)", dtype);
+    if (n == 0) return JSPSR_OK;
+    if (!feat || !fix || !dst) return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    const uintptr_t al = dtype == JSPSR_BF16 ? 1 : 3;
+    if (((uintptr_t)feat | (uintptr_t)fix | (uintptr_t)dst) & al) return fail(JSPSR_ERR_ALIGN, "jspsr_preserve_blend: misaligned pointer");
+    cudaError_t ce = launch_preserve_blend_auto(feat, fix, dst, (size_t)n, dtype == JSPSR_BF16, (cudaStream_t)stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "preserve_blend launch");
     return JSPSR_OK;
 }
 

@@ -115,4 +115,52 @@ cudaError_t launch_preserve_blend(const void* feat, const void* feat_fix, const 
     return cudaGetLastError();
 }
 
+// The same blend with the mask derived in the kernel from a single-channel `fix` (mask = fix > 0): the six elementwise
+// passes the LRRU cascade runs between its stages (LRRU.py:447-451 et seq.: sum(d_clear > 0, dim = 1) > 0, type_as,
+// (1 - mask) * x + mask * d_clear) as one pass of 12 B/pixel.  Products and sum are rounded separately, as torch's
+// three kernels round them, so non-finite values propagate identically ((1 - 1) * inf = NaN is kept).
+template <typename T, int V>
+__global__ void __launch_bounds__(256) preserve_blend_auto_kernel(const T* __restrict__ feat, const T* __restrict__ fix,
+                                                                  T* __restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        T f[V], d[V], o[V];
+        if (V == 4 && sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(f) = __ldcs(reinterpret_cast<const float4*>(feat + i));
+            *reinterpret_cast<float4*>(d) = __ldcs(reinterpret_cast<const float4*>(fix + i));
+        } else if (V == 4) {
+            *reinterpret_cast<uint2*>(f) = __ldcs(reinterpret_cast<const uint2*>(feat + i));
+            *reinterpret_cast<uint2*>(d) = __ldcs(reinterpret_cast<const uint2*>(fix + i));
+        } else {
+            f[0] = feat[i];
+            d[0] = fix[i];
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float dv = to_f32(d[j]);
+            const float m = dv > 0.f ? 1.f : 0.f;
+            o[j] = from_f32<T>(__fadd_rn(__fmul_rn(1.f - m, to_f32(f[j])), __fmul_rn(m, dv)));
+        }
+        if (V == 4 && sizeof(T) == 4) __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<float4*>(o));
+        else if (V == 4) __stcs(reinterpret_cast<uint2*>(dst + i), *reinterpret_cast<uint2*>(o));
+        else dst[i] = o[0];
+    }
+}
+
+cudaError_t launch_preserve_blend_auto(const void* feat, const void* fix, void* dst, size_t n, bool bf16,
+                                       cudaStream_t stream) {
+    const size_t align = bf16 ? 7 : 15;
+    const bool vec = (n % 4 == 0) && !(((uintptr_t)feat | (uintptr_t)fix | (uintptr_t)dst) & align);
+    const size_t items = vec ? n / 4 : n;
+    const int blocks = (int)min((size_t)148 * 16, (items + 255) / 256);
+    if (bf16) {
+        if (vec) preserve_blend_auto_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)feat, (const __nv_bfloat16*)fix, (__nv_bfloat16*)dst, n);
+        else preserve_blend_auto_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)feat, (const __nv_bfloat16*)fix, (__nv_bfloat16*)dst, n);
+    } else {
+        if (vec) preserve_blend_auto_kernel<float, 4><<<blocks, 256, 0, stream>>>((const float*)feat, (const float*)fix, (float*)dst, n);
+        else preserve_blend_auto_kernel<float, 1><<<blocks, 256, 0, stream>>>((const float*)feat, (const float*)fix, (float*)dst, n);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace jspsr

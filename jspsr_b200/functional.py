@@ -316,6 +316,30 @@ def offset_absmax(offset: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def preserve_blend(feat: torch.Tensor, fix: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The input-preservation blend the LRRU cascade runs between its stages (models/LRRU.py:447-451 and the three
+    repeats below it) for a single-channel `fix` (d_clear), in one pass:
+        mask = (torch.sum(fix > 0.0, dim=1, keepdim=True) > 0.0).type_as(fix);  (1.0 - mask) * feat + mask * fix
+    Same roundings as the torch expression.  No autograd: the reference detaches the result (`output.detach()`).
+    `out` may be `feat` itself."""
+    _require_cuda(feat, fix, out)
+    if feat.shape != fix.shape or feat.dim() != 4 or feat.shape[1] != 1:
+        raise RuntimeError(f"preserve_blend takes two [B,1,H,W] tensors, got {tuple(feat.shape)} and {tuple(fix.shape)}")
+    if feat.dtype != fix.dtype or (out is not None and (out.dtype != feat.dtype or out.shape != feat.shape)):
+        raise RuntimeError("preserve_blend: feat, fix and out must share one dtype (float32 or bfloat16) and shape")
+    feat, fix = feat.detach().contiguous(), fix.detach().contiguous()
+    if out is None:
+        out = torch.empty_like(feat)
+    elif not out.is_contiguous():
+        raise RuntimeError("preserve_blend: out must be contiguous")
+    with torch.cuda.device(feat.device):
+        rc = _lib.lib().jspsr_preserve_blend(_ptr(feat), _ptr(fix), _ptr(out), feat.numel(), _dtype_code(feat),
+                                             _stream_ptr(feat))
+    _lib.check(rc, "jspsr_preserve_blend")
+    _count()
+    return out
+
+
 def spn_iterate(feat_init, aff, offset, T: int, feat_fix=None, mask_fix=None) -> torch.Tensor:
     """T fixed-affinity applications; returns all intermediates [T,B,1,H,W].  One dtype for all three tensors
     (jspsr_spn_iterate has no mixed mode; `iterate` promotes autocast's mix first)."""

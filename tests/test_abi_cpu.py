@@ -30,7 +30,7 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 27, names
+    assert len(names) == 28, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in include/*.h but not exported"
@@ -114,6 +114,22 @@ def test_argument_validation_needs_no_gpu(lib):
         rc = call()
         assert rc == want, (rc, want, needle)
         assert needle in h.jspsr_last_error().decode(), (needle, h.jspsr_last_error())
+
+
+def test_preserve_blend_argument_validation_needs_no_gpu(lib):
+    """jspsr_preserve_blend (the LRRU cascade's blend, LRRU.py:447-451): host-side checks come before any CUDA work."""
+    h = lib.lib()
+    one = ctypes.c_void_p(16)
+    assert h.jspsr_preserve_blend(one, one, one, -1, 0, None) == -1 and b"negative" in h.jspsr_last_error()
+    assert h.jspsr_preserve_blend(one, one, one, 8, 2, None) == -2 and b"dtype" in h.jspsr_last_error()
+    assert h.jspsr_preserve_blend(None, None, None, 0, 0, None) == 0          # an empty batch is not an error
+    assert h.jspsr_preserve_blend(one, None, one, 8, 0, None) == -1 and b"null" in h.jspsr_last_error()
+    assert h.jspsr_preserve_blend(one, ctypes.c_void_p(18), one, 8, 0, None) == -4
+    assert h.jspsr_preserve_blend(one, ctypes.c_void_p(17), one, 8, 1, None) == -4
+    import jspsr_b200 as jb
+    x = torch.zeros(1, 1, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        jb.functional.preserve_blend(x, x)
 
 
 def test_modules_keep_the_reference_contract():

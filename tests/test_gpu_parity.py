@@ -1183,3 +1183,35 @@ def test_nlspn_loop_dtype_mixes_and_empty_loop(jb):
     mod0 = jb.NLSPN(args0, 8, 1, 3, 3).cuda()
     f0, l0, o0, a0, g0 = mod0(feat, guidance, conf)
     assert f0 is feat and l0 == [] and tuple(o0.shape) == (B, 18, H, W) and tuple(a0.shape) == (B, 9, H, W)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+@pytest.mark.parametrize("shape", [(3, 1, 128, 128), (2, 1, 33, 77), (1, 1, 5, 3)])
+def test_preserve_blend_is_the_lrru_expression_bit_for_bit(jb, dtype, shape):
+    """models/LRRU.py:447-451 (and its three repeats): mask from d_clear > 0, (1 - mask) * x + mask * d_clear - one kernel
+    against the six torch launches of the reference's own lines, including non-finite values on either side."""
+    dt = getattr(torch, dtype)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(shape, device="cuda", generator=g).to(dt)
+    d = torch.rand(shape, device="cuda", generator=g)
+    d = (d * (torch.rand(shape, device="cuda", generator=g) > 0.6)).to(dt)          # sparse valid pixels, zeros elsewhere
+    flat_x, flat_d = x.view(-1), d.view(-1)
+    flat_x[0], flat_d[0] = float("inf"), 1.0         # (1 - 1) * inf = NaN survives
+    flat_x[1], flat_d[1] = 2.0, float("nan")         # NaN > 0 is false: 1 * 2 + 0 * NaN = NaN
+    flat_x[2], flat_d[2] = -0.0, 0.0
+    flat_x[3], flat_d[3] = float("nan"), 0.0
+    flat_x[4], flat_d[4] = 1.5, -3.0                 # negative "depth": not valid, 0 * -3 = -0
+    mask = torch.sum(d > 0.0, dim=1, keepdim=True)
+    mask = (mask > 0.0).type_as(d)
+    ref = (1.0 - mask) * x + mask * d
+    out = jb.functional.preserve_blend(x, d)
+    assert out.dtype == dt and out.shape == x.shape
+    same = (out.view(torch.int16 if dt == torch.bfloat16 else torch.int32) ==
+            ref.view(torch.int16 if dt == torch.bfloat16 else torch.int32)) | (torch.isnan(out) & torch.isnan(ref))
+    assert bool(same.all())
+    x2 = x.clone()
+    assert jb.functional.preserve_blend(x2, d, out=x2) is x2                       # in place
+    assert torch.equal(torch.nan_to_num(x2.float()), torch.nan_to_num(out.float()))
+    with pytest.raises(RuntimeError, match=r"\[B,1,H,W\]"):
+        jb.functional.preserve_blend(x.expand(-1, 2, -1, -1), d.expand(-1, 2, -1, -1))
