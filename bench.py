@@ -790,6 +790,29 @@ def side_numbers(torch, F, device, B):
         "ms": itf, "bit_identical_to_T_launches": same,
         "frac_of_hbm_peak_compulsory": (4 + 108 + 4 * T) * npix / (itf * 1e-3) / 1e9 / peak,
         "note": "JSPSR_SPN_ITER_FUSED=1 (spn_iterate_fused.cu); the default is whichever of the two is faster here"}
+    # the loop as a training step (CompletionFormer-style: loss on the last step's output), forward + backward through
+    # autograd: T applications of the full backward with accumulation ("steps") against T light carry launches + one
+    # gradient kernel that sums over t in registers ("split", the default; spn_iterate_backward.cu)
+    fa, aa, oa = init.clone().requires_grad_(True), aff.clone().requires_grad_(True), offset.clone().requires_grad_(True)
+
+    def train_step():
+        F.iterate(fa, aa, oa, T)[-1].backward(gout)
+        fa.grad = aa.grad = oa.grad = None
+    step_ms = {}
+    for mode in ("steps", "split"):
+        os.environ["JSPSR_ITER_BWD"] = mode
+        try:
+            step_ms[mode] = timed(train_step, n=3)
+        finally:
+            os.environ.pop("JSPSR_ITER_BWD", None)
+    out["nlspn_loop_T6"]["train_step"] = {
+        "fwd_bwd_ms": step_ms["split"], "fwd_bwd_ms_T_backward_applications": step_ms["steps"],
+        "bwd_ms": step_ms["split"] - it, "bwd_ms_T_backward_applications": step_ms["steps"] - it,
+        "note": "backward of the loop: aff / offset are the same at every step, so the step-to-step gradient runs as T "
+                "scatter-only launches and the 27 gradients are summed over t in registers against the T staged features "
+                "(jspsr_spn_iterate_backward); JSPSR_ITER_BWD=steps keeps T full backward applications, whose "
+                "read-modify-write of 27 channels per step is HBM-bound"}
+    del fa, aa, oa
     del aff, gout, weight, offset
     torch.cuda.empty_cache()
     # the Generator's last two layers (1x1 convolutions C -> 9 / 16, sigmoid, zero centre

@@ -195,6 +195,22 @@ int jspsr_spn_iterate(const void *feat_init, const void *aff, const void *offset
                       int B, int H, int W, int T, int dtype, void *stream);
 
 /*
+ * Backward of jspsr_spn_iterate without feat_fix (autograd of the loop nlspn.py:222-235), fp32, 1 <= T <= 8.
+ * grad_list [T,B,1,H,W]: gradient w.r.t. every step's output (zeros where unused); list_out: the forward's
+ * result (steps 0 .. T-2 are read).  Writes grad_aff [B,9,H,W], grad_offset [B,18,H,W] and, unless NULL,
+ * grad_feat [B,1,H,W] (gradient w.r.t. feat_init).  carry_scratch: T * B * H * W floats, caller-owned.
+ * Affinities and offsets do not change over the loop, so the gradient that flows from step to step is computed by
+ * T light launches (a scatter, no gather, no 27-channel gradient traffic) and the 27 gradients are summed over t in
+ * registers by one kernel that holds the T staged features of its tile in shared memory - instead of T
+ * applications of jspsr_spn_backward with JSPSR_BWD_ACCUMULATE, whose read-modify-write of 27 channels per step
+ * is what bounds them.  Same per-step arithmetic; results agree to fp32 rounding.
+ */
+int jspsr_spn_iterate_backward(const void *grad_list, const void *feat_init, const void *list_out,
+                               const void *aff, const void *offset, void *grad_feat, void *grad_aff,
+                               void *grad_offset, void *carry_scratch, int B, int H, int W, int T,
+                               int dtype, void *stream);
+
+/*
  * Input-preservation blend of the LRRU cascade (models/LRRU.py:447-451, 460-464, 474-478, 488-492) for a
  * single-channel `fix` (d_clear): dst = (1 - m) * feat + m * fix with m = (fix > 0), element by element over n
  * elements, one pass instead of the six elementwise kernels of

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "jspsr_gen_tail_workspace_bytes": (c_size_t, []),
     "jspsr_gen_tail_grad_params": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "jspsr_spn_offset_absmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "jspsr_spn_iterate_backward": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "jspsr_preserve_blend": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "jspsr_spn_iterate": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "jspsr_nlspn_affinity_forward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),

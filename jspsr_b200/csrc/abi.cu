@@ -35,6 +35,13 @@ cudaError_t launch_preserve_blend_auto(const void* feat, const void* fix, void* 
                                       int legacy, bool bf16, bool forward, cudaStream_t stream);                        \
     cudaError_t launch_gen_spn_forward(const LaunchArgs& la, const CUtensorMap& tmap_feat, const void* feature, int C,  \
                                        const float* conv_w, const float* conv_b, void* weight_out, void* offset_out);   \
+    cudaError_t launch_iter_carry(const float* g_a, const float* g_b, const float* aff, const float* offset,           \
+                                  const float* asum_in, float* asum_out, float* carry_out, const Geom& g,               \
+                                  cudaStream_t stream);                                                                 \
+    cudaError_t launch_iter_grad(const float* grad_list, const float* carry, const float* feat_init,                    \
+                                 const float* list_out, const float* aff, const float* offset, float* grad_aff,         \
+                                 float* grad_offset, const Geom& g, int T, bool use_tma, const CUtensorMap& tmap_init,  \
+                                 const CUtensorMap& tmap_list, cudaStream_t stream);                                    \
     }
 JSPSR_DECLARE_VARIANT(narrow)
 JSPSR_DECLARE_VARIANT(wide)
@@ -533,6 +540,60 @@ int jspsr_spn_offset_absmax(const void* offset, int B, int H, int W, int dtype, 
     if (!offset || !out2) return fail(JSPSR_ERR_BAD_ARG, "null pointer");
     cudaError_t ce = launch_offset_absmax(offset, 0, (size_t)H * W, B, dtype == JSPSR_BF16, out2, (cudaStream_t)stream);
     if (ce != cudaSuccess) return cuda_fail(ce, "offset_absmax launch");
+    return JSPSR_OK;
+}
+
+int jspsr_spn_iterate_backward(const void* grad_list, const void* feat_init, const void* list_out, const void* aff,
+                               const void* offset, void* grad_feat, void* grad_aff, void* grad_offset, void* carry_scratch,
+                               int B, int H, int W, int T, int dtype, void* stream) {
+    if (int e = check_common(B, H, W, 0, dtype)) return e;
+    if (dtype != JSPSR_F32)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_spn_iterate_backward: fp32 only (run T applications of jspsr_spn_backward for bf16)");
+    if (T <= 0 || T > 8)
+        return fail(JSPSR_ERR_UNSUPPORTED, "jspsr_spn_iterate_backward: T=%d is outside [1, 8] (the T staged features of a CTA live in shared memory)", T);
+    if (!grad_list || !feat_init || !aff || !offset || !grad_aff || !grad_offset || (T > 1 && (!list_out || !carry_scratch)))
+        return fail(JSPSR_ERR_BAD_ARG, "null tensor pointer");
+    for (const void* p : {grad_list, feat_init, list_out, aff, offset, (const void*)grad_feat, (const void*)grad_aff,
+                          (const void*)grad_offset, (const void*)carry_scratch})
+        if (int e = check_align(p, 4, "jspsr_spn_iterate_backward tensor")) return e;
+    LaunchArgs la;
+    if (int e = fill_geom(&la, B, H, W, H, 0, 0, H, 8)) return e;
+    la.tile_h = 8;  // both kernels are instantiated for 8 rows per CTA
+    la.g.tiles_y = (H + 7) / 8;
+    const size_t n = (size_t)B * H * W;
+    if ((size_t)T * B > 0x7fffffffull) return fail(JSPSR_ERR_UNSUPPORTED, "T * B exceeds 2^31 - 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* gl = (const float*)grad_list;
+    float* carry = (float*)carry_scratch;
+    // (A) the carry chain: step t sends P^T g_t to step t - 1 (slot t - 1 of the scratch; step 0 to grad_feat)
+    if (T > 1) {
+        cudaError_t ce = cudaMemsetAsync(carry, 0, (size_t)(T - 1) * n * sizeof(float), st);
+        if (ce != cudaSuccess) return cuda_fail(ce, "carry memset");
+    }
+    if (grad_feat) {
+        cudaError_t ce = cudaMemsetAsync(grad_feat, 0, n * sizeof(float), st);
+        if (ce != cudaSuccess) return cuda_fail(ce, "grad_feat memset");
+    }
+    const bool wide = choose_wide(W);
+    for (int t = T - 1; t >= 0; --t) {
+        float* dst = t > 0 ? carry + (size_t)(t - 1) * n : (float*)grad_feat;
+        if (!dst) break;
+        const float* g_b = t < T - 1 ? carry + (size_t)t * n : nullptr;
+        // slot T - 1 of the scratch: sum_k |a_k| per pixel, written by the first launch of the chain, read by the others
+        float* asum = T > 1 ? carry + (size_t)(T - 1) * n : nullptr;
+        cudaError_t ce = (wide ? wide::launch_iter_carry : narrow::launch_iter_carry)(
+            gl + (size_t)t * n, g_b, (const float*)aff, (const float*)offset, t < T - 1 ? asum : nullptr,
+            t == T - 1 ? asum : nullptr, dst, la.g, st);
+        if (ce != cudaSuccess) return cuda_fail(ce, "iter_carry launch");
+    }
+    // (B) the 27 gradients, summed over t in registers; narrow staged halo: T tiles of a CTA stay resident
+    CUtensorMap tm_init{}, tm_list{};
+    bool use_tma = make_init_tmap(&tm_init, feat_init, B, H, W, false, 8, false);
+    if (use_tma && T > 1) use_tma = make_init_tmap(&tm_list, list_out, (T - 1) * B, H, W, false, 8, false);
+    cudaError_t ce = narrow::launch_iter_grad(gl, carry, (const float*)feat_init, (const float*)list_out, (const float*)aff,
+                                              (const float*)offset, (float*)grad_aff, (float*)grad_offset, la.g, T, use_tma,
+                                              tm_init, tm_list, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "iter_grad launch");
     return JSPSR_OK;
 }
 

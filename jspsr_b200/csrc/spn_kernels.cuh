@@ -201,6 +201,12 @@ __device__ __forceinline__ void gi_add2(int* cell, int* cell_lo, float v_scaled)
 // per-variant entry points used by abi.cu
 cudaError_t launch_spn_forward(const LaunchArgs& la);
 cudaError_t launch_spn_backward(const LaunchArgs& la);
+// backward of the fixed-affinity loop (spn_iterate_backward.cu): 8 rows per CTA, fp32
+cudaError_t launch_iter_carry(const float* g_a, const float* g_b, const float* aff, const float* offset,
+                              const float* asum_in, float* asum_out, float* carry_out, const Geom& g, cudaStream_t stream);
+cudaError_t launch_iter_grad(const float* grad_list, const float* carry, const float* feat_init, const float* list_out,
+                             const float* aff, const float* offset, float* grad_aff, float* grad_offset, const Geom& g, int T,
+                             bool use_tma, const CUtensorMap& tmap_init, const CUtensorMap& tmap_list, cudaStream_t stream);
 int stage_box_cols();        // extents of the staged DEM box = the TMA box
 int stage_box_rows(int th);
 

@@ -534,6 +534,40 @@ def propagate(init, weight, offset, w, b, norm_mode: int, scale: float = 1.0, re
     return _Propagate.apply(init, weight, offset, w, b, norm_mode, scale, reducer)
 
 
+def spn_iterate_backward(grad_list, feat_init, list_out, aff, offset, need_grad_feat=True):
+    """Backward of `spn_iterate` without feat_fix in T light carry launches + one gradient kernel
+    (jspsr_spn_iterate_backward): returns (grad_feat | None, grad_aff, grad_offset).  fp32, T <= 8."""
+    _require_cuda(grad_list, feat_init, list_out, aff, offset)
+    B, H, W = _check_shapes(feat_init, aff, offset)
+    T = list_out.shape[0]
+    if tuple(list_out.shape) != (T, B, 1, H, W) or tuple(grad_list.shape) != (T, B, 1, H, W):
+        raise RuntimeError(f"grad_list / list_out must be [T,B,1,H,W], got {tuple(grad_list.shape)} / {tuple(list_out.shape)}")
+    for t in (grad_list, feat_init, list_out, aff, offset):
+        if t.dtype != torch.float32:
+            raise RuntimeError("spn_iterate_backward is fp32 only")
+    grad_list, feat_init, list_out = grad_list.contiguous(), feat_init.contiguous(), list_out.contiguous()
+    aff, offset = aff.contiguous(), offset.contiguous()
+    grad_aff, grad_offset = torch.empty_like(aff), torch.empty_like(offset)
+    grad_feat = torch.empty_like(feat_init) if need_grad_feat else None
+    carry = torch.empty((T, B, 1, H, W), dtype=torch.float32, device=aff.device)   # T - 1 carries + sum_k |a_k|
+    with torch.cuda.device(aff.device):
+        rc = _lib.lib().jspsr_spn_iterate_backward(_ptr(grad_list), _ptr(feat_init), _ptr(list_out), _ptr(aff), _ptr(offset),
+                                                   _ptr(grad_feat), _ptr(grad_aff), _ptr(grad_offset), _ptr(carry), B, H, W, T,
+                                                   F32, _stream_ptr(aff))
+    _lib.check(rc, "jspsr_spn_iterate_backward")
+    _count((T if need_grad_feat else T - 1) + 1)
+    return grad_feat, grad_aff, grad_offset
+
+
+def _iterate_backward_split_ok(feat_init, aff, offset, feat_fix, T) -> bool:
+    """The split backward covers the loop CompletionFormer runs (fp32, no preserve_input, T <= 8);
+    JSPSR_ITER_BWD=steps keeps the T-application path (tests compare the two)."""
+    import os
+    if os.environ.get("JSPSR_ITER_BWD", "split") == "steps":
+        return False
+    return feat_fix is None and T <= 8 and feat_init.dtype == aff.dtype == offset.dtype == torch.float32
+
+
 class _Iterate(torch.autograd.Function):
     """NLSPN loop (nlspn.py:222-235): T applications with fixed aff/offset, w=1, b=0."""
 
@@ -549,6 +583,9 @@ class _Iterate(torch.autograd.Function):
     def backward(ctx, grad_list):
         feat_init, aff, offset, out, feat_fix, mask_fix = ctx.saved_tensors
         T = ctx.T
+        if _iterate_backward_split_ok(feat_init, aff, offset, feat_fix, T) and grad_list.dtype == torch.float32:
+            gf, ga, go = spn_iterate_backward(grad_list, feat_init, out, aff, offset, need_grad_feat=ctx.needs_input_grad[0])
+            return (gf, ga if ctx.needs_input_grad[1] else None, go if ctx.needs_input_grad[2] else None, None, None, None)
         grad_aff = grad_offset = None
         carry = None  # gradient flowing into step t's output from step t+1
         for t in range(T - 1, -1, -1):

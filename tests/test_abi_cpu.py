@@ -30,7 +30,7 @@ def declared_functions():
 
 def test_header_symbols_are_exported(lib):
     names = declared_functions()
-    assert len(names) == 28, names
+    assert len(names) == 29, names
     handle = ctypes.CDLL(lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} is declared in include/*.h but not exported"
@@ -130,6 +130,22 @@ def test_preserve_blend_argument_validation_needs_no_gpu(lib):
     x = torch.zeros(1, 1, 4, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         jb.functional.preserve_blend(x, x)
+
+
+def test_iterate_backward_argument_validation_needs_no_gpu(lib):
+    """jspsr_spn_iterate_backward (autograd of the loop nlspn.py:222-235): what it does not cover is refused on the host,
+    so that the caller runs T applications of jspsr_spn_backward instead."""
+    h = lib.lib()
+    one = ctypes.c_void_p(16)
+    call = lambda T=6, dtype=0, gl=one, scratch=one, B=2: h.jspsr_spn_iterate_backward(gl, one, one, one, one, one, one, one,
+                                                                                        scratch, B, 8, 8, T, dtype, None)
+    assert call(T=9) == -2 and b"[1, 8]" in h.jspsr_last_error()
+    assert call(T=0) == -2
+    assert call(dtype=1) == -2 and b"fp32 only" in h.jspsr_last_error()
+    assert call(B=0) == -1
+    assert call(gl=None) == -1 and b"null" in h.jspsr_last_error()
+    assert call(scratch=None) == -1                      # T > 1 needs the carry scratch
+    assert call(gl=ctypes.c_void_p(18)) == -4
 
 
 def test_modules_keep_the_reference_contract():

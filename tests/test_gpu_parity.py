@@ -1215,3 +1215,50 @@ def test_preserve_blend_is_the_lrru_expression_bit_for_bit(jb, dtype, shape):
     assert torch.equal(torch.nan_to_num(x2.float()), torch.nan_to_num(out.float()))
     with pytest.raises(RuntimeError, match=r"\[B,1,H,W\]"):
         jb.functional.preserve_blend(x.expand(-1, 2, -1, -1), d.expand(-1, 2, -1, -1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,T,sigma", [(3, 128, 128, 6, 1.5), (2, 128, 128, 1, 1.5), (2, 128, 128, 8, 3.0),
+                                           (2, 37, 150, 3, 1.5), (1, 64, 256, 6, 7.0), (2, 128, 128, 9, 1.5)])
+def test_iterate_backward_split_matches_the_step_by_step_path(jb, monkeypatch, B, H, W, T, sigma):
+    """nlspn.py:222-235 backward: T light carry launches + one gradient kernel (jspsr_spn_iterate_backward) against T
+    applications of the full backward with accumulation - same per-step arithmetic, sums over t associated the same way.
+    Covers the TMA and the manual staging, a 128 x 128 plane (compile-time stride) and others, offsets that leave the
+    narrow staged tile (global-corner path in both kernels), every step's output carrying a gradient, and T = 9, which
+    the split form does not take (falls back)."""
+    F = jb.functional
+    g = torch.Generator(device="cuda").manual_seed(100 + T)
+    feat = torch.rand(B, 1, H, W, device="cuda", generator=g)
+    aff = (0.25 * torch.randn(B, 9, H, W, device="cuda", generator=g))
+    off = (sigma * torch.randn(B, 18, H, W, device="cuda", generator=g)).clamp_(-24, 24)
+    off[:, 8:10] = 0
+    gl = torch.randn(T, B, 1, H, W, device="cuda", generator=g)
+    res = {}
+    for mode in ("steps", "split"):
+        monkeypatch.setenv("JSPSR_ITER_BWD", mode)
+        fa, aa, oa = (t.clone().requires_grad_(True) for t in (feat, aff, off))
+        n0 = F.launch_count()
+        out = F.iterate(fa, aa, oa, T)
+        n1 = F.launch_count()
+        out.backward(gl)
+        res[mode] = (fa.grad, aa.grad, oa.grad, F.launch_count() - n1)
+        assert n1 - n0 == T
+    if T <= 8:
+        assert res["split"][3] == T + 1 and res["steps"][3] == T      # T carry launches + one gradient kernel
+    else:
+        assert res["split"][3] == res["steps"][3] == T
+    for name, a, b in zip(("grad_feat", "grad_aff", "grad_offset"), res["steps"], res["split"]):
+        scale = float(a.abs().max())
+        assert torch.isfinite(b).all(), name
+        # both paths scatter the carry through the block-floating-point tile (each contribution rounded once to
+        # S * 2^-30 of its CTA, spn_backward.cu) with different CTA sums S and associations, and the rounding of step t
+        # is amplified by sum_k |a_k| in every later step: a few 1e-6 of the largest gradient after six steps
+        assert float((a - b).abs().max()) <= 3e-5 * scale + 1e-12, (name, float((a - b).abs().max()), scale)
+    # gradient w.r.t. the feature not requested: the last carry launch is skipped
+    monkeypatch.setenv("JSPSR_ITER_BWD", "split")
+    aa, oa = (t.clone().requires_grad_(True) for t in (aff, off))
+    n1 = F.launch_count()
+    F.iterate(feat, aa, oa, T).backward(gl)
+    assert F.launch_count() - n1 == T + max(T - 1, 0) + 1 if T <= 8 else True
+    for a, b in ((aa.grad, res["split"][1]), (oa.grad, res["split"][2])):   # (fp32 REDs of neighbouring CTAs land in any order)
+        assert float((a - b).abs().max()) <= 3e-5 * float(b.abs().max())

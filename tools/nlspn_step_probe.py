@@ -46,8 +46,15 @@ def main():
         out = F.iterate(fa, aa, oa, T)
         out[-1].backward(gout)
         fa.grad = aa.grad = oa.grad = None
-    t = timed(step, n=3)
-    print(f"autograd fwd + bwd     {t:7.3f} ms")
+    for mode in ("steps", "split"):
+        os.environ["JSPSR_ITER_BWD"] = mode
+        t = timed(step, n=3)
+        print(f"autograd fwd + bwd     {t:7.3f} ms   (JSPSR_ITER_BWD={mode})")
+    gl = torch.zeros(T, B, 1, H, W, device="cuda")
+    gl[-1] = gout
+    out = F.spn_iterate(feat, aff, off, T)
+    t = timed(lambda: F.spn_iterate_backward(gl, feat, out, aff, off))
+    print(f"split backward alone   {t:7.3f} ms")
 
 
 if __name__ == "__main__":
