@@ -560,12 +560,16 @@ def spn_iterate_backward(grad_list, feat_init, list_out, aff, offset, need_grad_
 
 
 def _iterate_backward_split_ok(feat_init, aff, offset, feat_fix, T) -> bool:
-    """The split backward covers the loop CompletionFormer runs (fp32, no preserve_input, T <= 8);
-    JSPSR_ITER_BWD=steps keeps the T-application path (tests compare the two)."""
+    """The split backward covers the loop CompletionFormer runs (fp32, no preserve_input, T <= 8).  It pays from three
+    steps on (tools/iter_bwd_sweep.py, B200, 2048 / 70 / 2 tiles: T = 1: 2.48 vs 1.63 ms, T = 2: a tie, T = 3: 5.05 vs
+    5.34 ms, T = 6: 8.6 vs 11.0 ms), so that is where the default takes it; JSPSR_ITER_BWD=split / steps force one form
+    (tests compare the two)."""
     import os
-    if os.environ.get("JSPSR_ITER_BWD", "split") == "steps":
+    mode = os.environ.get("JSPSR_ITER_BWD", "auto")
+    if mode == "steps":
         return False
-    return feat_fix is None and T <= 8 and feat_init.dtype == aff.dtype == offset.dtype == torch.float32
+    covered = feat_fix is None and T <= 8 and feat_init.dtype == aff.dtype == offset.dtype == torch.float32
+    return covered and (T >= 3 or mode == "split")
 
 
 class _Iterate(torch.autograd.Function):

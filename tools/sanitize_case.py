@@ -52,5 +52,22 @@ for (B, H, W) in ((2, 40, 128), (1, 21, 200), (1, 5, 7)):
             out = F.gen_propagate(init, feat, cw, cb, pp.w, pp.b, 1, 1.0)
             out.square().mean().backward()
             F.gen_spn_forward(init, feat.detach(), cw.detach(), cb.detach(), pp.w, pp.b, 2, 1.0)
+# backward of the fixed-affinity loop, split form (iter_carry_kernel / iter_grad_kernel): TMA and manual staging,
+# offsets that leave the narrow staged tile, T = 1 / 3 / 8, with and without the gradient of the feature
+from jspsr_b200 import epilogue as EP
+for (B, H, W, T, sig) in ((2, 40, 128, 3, 1.5), (1, 37, 150, 8, 6.0), (1, 128, 128, 1, 1.5), (3, 9, 7, 2, 1.0)):
+    fa = torch.rand(B, 1, H, W, device="cuda").requires_grad_()
+    aa = (0.2 * torch.randn(B, 9, H, W, device="cuda")).requires_grad_()
+    oa = (sig * torch.randn(B, 18, H, W, device="cuda")).requires_grad_()
+    F.iterate(fa, aa, oa, T).square().sum().backward()
+    F.iterate(fa.detach(), aa, oa, T)[-1].sum().backward()
+    # the LRRU blend and the RMSE / MAE sums (float4 and scalar kernels; border columns that are not 16-byte aligned)
+    d = fa.detach() * (torch.rand_like(fa) > 0.5)
+    F.preserve_blend(fa.detach(), d)
+    F.preserve_blend(fa.detach().bfloat16(), d.bfloat16())
+    for border in (0.0, 0.05, 0.2):
+        if int(H * border) * 2 < H and int(W * border) * 2 < W:
+            EP.dem_metrics(fa.detach(), d, border, -80.0, 929.0, True)
+            EP.dem_metrics(fa.detach(), d, border, -80.0, 929.0, False)
 torch.cuda.synchronize()
 print("sanitize case done")
