@@ -40,8 +40,9 @@ cudaError_t launch_preserve_blend_auto(const void* feat, const void* fix, void* 
                                   cudaStream_t stream);                                                                 \
     cudaError_t launch_iter_grad(const float* grad_list, const float* carry, const float* feat_init,                    \
                                  const float* list_out, const float* aff, const float* offset, float* grad_aff,         \
-                                 float* grad_offset, const Geom& g, int T, bool use_tma, const CUtensorMap& tmap_init,  \
-                                 const CUtensorMap& tmap_list, cudaStream_t stream);                                    \
+                                 float* grad_offset, const Geom& g, int T, int tile_h, bool use_tma,                    \
+                                 const CUtensorMap& tmap_init, const CUtensorMap& tmap_list, cudaStream_t stream);      \
+    int iter_grad_tile_h(int T);                                                                                        \
     }
 JSPSR_DECLARE_VARIANT(narrow)
 JSPSR_DECLARE_VARIANT(wide)
@@ -588,11 +589,16 @@ int jspsr_spn_iterate_backward(const void* grad_list, const void* feat_init, con
     }
     // (B) the 27 gradients, summed over t in registers; narrow staged halo: T tiles of a CTA stay resident
     CUtensorMap tm_init{}, tm_list{};
-    bool use_tma = make_init_tmap(&tm_init, feat_init, B, H, W, false, 8, false);
-    if (use_tma && T > 1) use_tma = make_init_tmap(&tm_list, list_out, (T - 1) * B, H, W, false, 8, false);
+    int gth = narrow::iter_grad_tile_h(T);
+    // small batches: 8-row CTAs keep the grid at two CTAs per SM or more (measured at 2 tiles: 0.105 vs 0.112 ms)
+    if (gth == 16 && !getenv("JSPSR_ITER_GRAD_TH") && (size_t)la.g.tiles_x * ((H + 15) / 16) * B < (size_t)148 * 2) gth = 8;
+    Geom gg = la.g;
+    gg.tiles_y = (H + gth - 1) / gth;
+    bool use_tma = make_init_tmap(&tm_init, feat_init, B, H, W, false, gth, false);
+    if (use_tma && T > 1) use_tma = make_init_tmap(&tm_list, list_out, (T - 1) * B, H, W, false, gth, false);
     cudaError_t ce = narrow::launch_iter_grad(gl, carry, (const float*)feat_init, (const float*)list_out, (const float*)aff,
-                                              (const float*)offset, (float*)grad_aff, (float*)grad_offset, la.g, T, use_tma,
-                                              tm_init, tm_list, st);
+                                              (const float*)offset, (float*)grad_aff, (float*)grad_offset, gg, T, gth,
+                                              use_tma, tm_init, tm_list, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "iter_grad launch");
     return JSPSR_OK;
 }

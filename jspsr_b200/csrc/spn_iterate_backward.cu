@@ -178,14 +178,16 @@ iter_carry_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b, 
 
 // (B) grad_aff / grad_offset over all T steps.  src(t) = feat_init for t = 0, list_out[t - 1] otherwise;
 // g_t = grad_list[t] + carry[t] (t < T - 1; carry[t] = what step t + 1 sent back, written by (A)).
-template <bool TMA, int CS, int TH>
-__global__ void __launch_bounds__(THREADS, 3)
+// Two shapes: 8 rows x 256 threads (three CTAs per SM up to T = 6, two for T = 7, 8) and 16 rows x 512 threads (two CTAs
+// per SM = 32 warps instead of 24, half the halo rows per output row; T <= 6: 6 x 16.4 KB of tiles per CTA).
+template <bool TMA, int CS, int TH, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3)
 iter_grad_kernel(const float* __restrict__ grad_list, const float* __restrict__ carry, const float* __restrict__ feat_init,
                  const float* __restrict__ list_out, const float* __restrict__ aff, const float* __restrict__ offset,
                  float* __restrict__ grad_aff, float* __restrict__ grad_offset, const Geom g, const int T,
                  const __grid_constant__ CUtensorMap tmap_init, const __grid_constant__ CUtensorMap tmap_list) {
     constexpr int SH = staged_rows(TH);
-    constexpr int PPT = pixels_per_thread(TH);
+    constexpr int PPT = TH * TILE_W / NT;
     constexpr int TILE_ELEMS = iter_tile_stride(TH);  // SH * SW rounded up to 128 bytes: every TMA box lands 128-byte aligned
     extern __shared__ __align__(128) float tiles[];  // [T][TILE_ELEMS]
     __shared__ __align__(8) uint64_t bar;
@@ -204,7 +206,7 @@ iter_grad_kernel(const float* __restrict__ grad_list, const float* __restrict__ 
     } else {
         for (int t = 0; t < T; ++t) {
             const float* src = (t == 0 ? feat_init : list_out + (size_t)(t - 1) * step) + (size_t)c.b * cs;
-            for (int i = threadIdx.x; i < SH * SW; i += THREADS) {
+            for (int i = threadIdx.x; i < SH * SW; i += NT) {
                 const int r = i / SW, q = i - r * SW;
                 const int gy = c.oy + r, gx = c.ox + q;
                 float v = 0.f;
@@ -224,8 +226,8 @@ iter_grad_kernel(const float* __restrict__ grad_list, const float* __restrict__ 
 #pragma unroll 1
     for (int it = 0; it < PPT; ++it) {
         __syncwarp();
-        const int ry = pix_row<TH, true>(it), cx = pix_col<TH, true>(it);
-        const int y = c.y0 + ry, x = c.x0 + cx;
+        const int pi = it * NT + (int)threadIdx.x;  // a warp = 32 consecutive columns of one row
+        const int y = c.y0 + (pi >> 7), x = c.x0 + (pi & (TILE_W - 1));
         if (!(y < g.H && x < g.W)) continue;
         const size_t p = (size_t)y * g.W + x;
         // everything this pixel needs from global memory is requested up front (27 + 2 T - 1 loads in flight per lane)
@@ -299,7 +301,14 @@ iter_grad_kernel(const float* __restrict__ grad_list, const float* __restrict__ 
     }
 }
 
-size_t iter_grad_smem_bytes(int T) { return (size_t)T * iter_tile_stride(8) * sizeof(float); }
+// rows per CTA of iter_grad_kernel for T steps: 16 (512 threads) while its T tiles leave room for two CTAs per SM
+int iter_grad_tile_h(int T) {
+    if (const char* e = getenv("JSPSR_ITER_GRAD_TH")) {
+        if (atoi(e) == 8) return 8;
+        if (atoi(e) == 16 && T <= 6) return 16;
+    }
+    return T <= 6 ? 16 : 8;
+}
 
 cudaError_t launch_iter_carry(const float* g_a, const float* g_b, const float* aff, const float* offset,
                               const float* asum_in, float* asum_out, float* carry_out, const Geom& g, cudaStream_t stream) {
@@ -312,25 +321,36 @@ cudaError_t launch_iter_carry(const float* g_a, const float* g_b, const float* a
     return cudaGetLastError();
 }
 
+// g.tiles_y and the tensor maps' boxes are the caller's, for `tile_h` rows per CTA
 cudaError_t launch_iter_grad(const float* grad_list, const float* carry, const float* feat_init, const float* list_out,
                              const float* aff, const float* offset, float* grad_aff, float* grad_offset, const Geom& g, int T,
-                             bool use_tma, const CUtensorMap& tmap_init, const CUtensorMap& tmap_list, cudaStream_t stream) {
+                             int tile_h, bool use_tma, const CUtensorMap& tmap_init, const CUtensorMap& tmap_list,
+                             cudaStream_t stream) {
     const dim3 grid((unsigned)((size_t)g.tiles_x * g.tiles_y * g.B));
-    const size_t smem = iter_grad_smem_bytes(T);
-    const size_t smem_max = iter_grad_smem_bytes(ITER_BWD_TMAX);  // the opt-in is made once per kernel: ask for the largest T
     const bool cs128 = (size_t)g.H * g.W == 16384;
-#define JSPSR_LAUNCH_ITER_GRAD(TMA_, CS_)                                                                              \
+    // the shared-memory opt-in is made once per kernel: ask for the largest T the shape is used with
+#define JSPSR_LAUNCH_ITER_GRAD(TMA_, CS_, TH_, NT_, TMAX_)                                                             \
     do {                                                                                                               \
-        cudaError_t e = ensure_dynamic_smem((const void*)iter_grad_kernel<TMA_, CS_, 8>, smem_max);                    \
+        const size_t smem = (size_t)T * iter_tile_stride(TH_) * sizeof(float);                                         \
+        cudaError_t e = ensure_dynamic_smem((const void*)iter_grad_kernel<TMA_, CS_, TH_, NT_>,                        \
+                                            (size_t)(TMAX_) * iter_tile_stride(TH_) * sizeof(float));                  \
         if (e != cudaSuccess) return e;                                                                                \
-        iter_grad_kernel<TMA_, CS_, 8><<<grid, THREADS, smem, stream>>>(grad_list, carry, feat_init, list_out, aff, offset, \
-                                                                        grad_aff, grad_offset, g, T, tmap_init, tmap_list); \
+        iter_grad_kernel<TMA_, CS_, TH_, NT_><<<grid, NT_, smem, stream>>>(grad_list, carry, feat_init, list_out, aff, \
+                                                                          offset, grad_aff, grad_offset, g, T,         \
+                                                                          tmap_init, tmap_list);                       \
     } while (0)
+#define JSPSR_LAUNCH_ITER_GRAD_SHAPE(TMA_, CS_)                                                                         \
+    do {                                                                                                               \
+        if (tile_h == 16) JSPSR_LAUNCH_ITER_GRAD(TMA_, CS_, 16, 512, 6);                                               \
+        else JSPSR_LAUNCH_ITER_GRAD(TMA_, CS_, 8, 256, ITER_BWD_TMAX);                                                 \
+    } while (0)
+    if (tile_h == 16 && T > 6) return cudaErrorInvalidValue;
     if (use_tma) {
-        if (cs128) JSPSR_LAUNCH_ITER_GRAD(true, 16384); else JSPSR_LAUNCH_ITER_GRAD(true, 0);
+        if (cs128) JSPSR_LAUNCH_ITER_GRAD_SHAPE(true, 16384); else JSPSR_LAUNCH_ITER_GRAD_SHAPE(true, 0);
     } else {
-        if (cs128) JSPSR_LAUNCH_ITER_GRAD(false, 16384); else JSPSR_LAUNCH_ITER_GRAD(false, 0);
+        if (cs128) JSPSR_LAUNCH_ITER_GRAD_SHAPE(false, 16384); else JSPSR_LAUNCH_ITER_GRAD_SHAPE(false, 0);
     }
+#undef JSPSR_LAUNCH_ITER_GRAD_SHAPE
 #undef JSPSR_LAUNCH_ITER_GRAD
     return cudaGetLastError();
 }

@@ -206,7 +206,9 @@ cudaError_t launch_iter_carry(const float* g_a, const float* g_b, const float* a
                               const float* asum_in, float* asum_out, float* carry_out, const Geom& g, cudaStream_t stream);
 cudaError_t launch_iter_grad(const float* grad_list, const float* carry, const float* feat_init, const float* list_out,
                              const float* aff, const float* offset, float* grad_aff, float* grad_offset, const Geom& g, int T,
-                             bool use_tma, const CUtensorMap& tmap_init, const CUtensorMap& tmap_list, cudaStream_t stream);
+                             int tile_h, bool use_tma, const CUtensorMap& tmap_init, const CUtensorMap& tmap_list,
+                             cudaStream_t stream);
+int iter_grad_tile_h(int T);
 int stage_box_cols();        // extents of the staged DEM box = the TMA box
 int stage_box_rows(int th);
 
