@@ -1220,13 +1220,15 @@ def test_preserve_blend_is_the_lrru_expression_bit_for_bit(jb, dtype, shape):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,H,W,T,sigma", [(3, 128, 128, 6, 1.5), (2, 128, 128, 1, 1.5), (2, 128, 128, 8, 3.0),
                                            (2, 37, 150, 3, 1.5), (1, 64, 256, 6, 7.0), (2, 128, 128, 9, 1.5)])
-def test_iterate_backward_split_matches_the_step_by_step_path(jb, monkeypatch, B, H, W, T, sigma):
+@pytest.mark.parametrize("grad_rows", ["8", "16"])
+def test_iterate_backward_split_matches_the_step_by_step_path(jb, monkeypatch, B, H, W, T, sigma, grad_rows):
     """nlspn.py:222-235 backward: T light carry launches + one gradient kernel (jspsr_spn_iterate_backward) against T
     applications of the full backward with accumulation - same per-step arithmetic, sums over t associated the same way.
     Covers the TMA and the manual staging, a 128 x 128 plane (compile-time stride) and others, offsets that leave the
     narrow staged tile (global-corner path in both kernels), every step's output carrying a gradient, and T = 9, which
     the split form does not take (falls back)."""
     F = jb.functional
+    monkeypatch.setenv("JSPSR_ITER_GRAD_TH", grad_rows)   # both shapes of iter_grad_kernel (16 rows x 512 threads: T <= 6)
     g = torch.Generator(device="cuda").manual_seed(100 + T)
     feat = torch.rand(B, 1, H, W, device="cuda", generator=g)
     aff = (0.25 * torch.randn(B, 9, H, W, device="cuda", generator=g))
