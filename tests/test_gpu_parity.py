@@ -1264,3 +1264,34 @@ def test_iterate_backward_split_matches_the_step_by_step_path(jb, monkeypatch, B
     assert F.launch_count() - n1 == T + max(T - 1, 0) + 1 if T <= 8 else True
     for a, b in ((aa.grad, res["split"][1]), (oa.grad, res["split"][2])):   # (fp32 REDs of neighbouring CTAs land in any order)
         assert float((a - b).abs().max()) <= 3e-5 * float(b.abs().max())
+
+
+@pytest.mark.gpu
+def test_iterate_backward_and_blend_capture_into_a_cuda_graph(jb):
+    """The split loop backward (memsets + T carry launches + the gradient kernel with its shared-memory opt-in) and the
+    LRRU blend enqueue on the capturing stream only and replay: the gradients that depend on no atomics are bit-identical,
+    the carried ones agree to the carry's rounding."""
+    F = jb.functional
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, W, T = 2, 128, 128, 4
+    feat = torch.rand(B, 1, H, W, device="cuda", generator=g)
+    aff = 0.25 * torch.randn(B, 9, H, W, device="cuda", generator=g)
+    off = (1.5 * torch.randn(B, 18, H, W, device="cuda", generator=g)).clamp_(-8, 8)
+    gl = torch.randn(T, B, 1, H, W, device="cuda", generator=g)
+    d = feat * (torch.rand(B, 1, H, W, device="cuda", generator=g) > 0.5)
+    out = F.spn_iterate(feat, aff, off, T)
+    eager = F.spn_iterate_backward(gl, feat, out, aff, off)
+    eager_blend = F.preserve_blend(feat, d)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        captured = F.spn_iterate_backward(gl, feat, out, aff, off)
+        captured_blend = F.preserve_blend(feat, d)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured_blend, eager_blend)
+    for name, a, b in zip(("grad_feat", "grad_aff", "grad_offset"), eager, captured):
+        assert torch.isfinite(b).all()
+        assert float((a - b).abs().max()) <= 3e-5 * float(a.abs().max()), name
