@@ -52,8 +52,13 @@ __device__ __forceinline__ void carry_corner_global(float* __restrict__ dst_b, c
 // asum = sum_k |a_k| per pixel, the iteration-invariant factor of the tile's scale bound: the first launch of a chain
 // (asum_in == nullptr) forms it from the nine affinities and stores it (asum_out), the others read one value per
 // pixel instead of nine in their pre-pass.
+// resident CTAs per SM: 4 (55 registers); 5 (48 registers, no spills) measured the same on the same box (T = 6, 2048 tiles:
+// 8.45 vs 8.46 ms for the whole backward) - the kernel sits at 70 % of both the issue and the LSU wavefront rate
+#ifndef JSPSR_CARRY_MIN_BLOCKS
+#define JSPSR_CARRY_MIN_BLOCKS 4
+#endif
 template <int CS, int TH>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, JSPSR_CARRY_MIN_BLOCKS)
 iter_carry_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b, const float* __restrict__ aff,
                   const float* __restrict__ offset, const float* __restrict__ asum_in, float* __restrict__ asum_out,
                   float* __restrict__ carry_out, const Geom g) {
