@@ -1295,3 +1295,43 @@ def test_iterate_backward_and_blend_capture_into_a_cuda_graph(jb):
     for name, a, b in zip(("grad_feat", "grad_aff", "grad_offset"), eager, captured):
         assert torch.isfinite(b).all()
         assert float((a - b).abs().max()) <= 3e-5 * float(a.abs().max()), name
+
+
+@pytest.mark.gpu
+def test_iterate_backward_full_size_properties(jb, monkeypatch):
+    """512 tiles of 128 x 128, T = 6 - the default dispatch of a large batch (split form, 16-row gradient kernel) without
+    any switch: (i) agreement with the T-application path, (ii) linearity in the incoming gradient (a factor 2 shifts the
+    exponent of every product and of the scatter tile's scale, nothing else), (iii) steps whose output carries no
+    gradient and sends none back contribute exact zeros."""
+    F = jb.functional
+    for k in ("JSPSR_ITER_BWD", "JSPSR_ITER_GRAD_TH"):
+        monkeypatch.delenv(k, raising=False)
+    B, H, W, T = 512, 128, 128, 6
+    g = torch.Generator(device="cuda").manual_seed(77)
+    feat = torch.rand(B, 1, H, W, device="cuda", generator=g)
+    aff = 0.1 * torch.sigmoid(1.5 * torch.randn(B, 9, H, W, device="cuda", generator=g))
+    off = (1.5 * torch.randn(B, 18, H, W, device="cuda", generator=g)).clamp_(-8, 8)
+    off[:, 8:10] = 0
+    gl = torch.zeros(T, B, 1, H, W, device="cuda")
+    gl[-1] = torch.randn(B, 1, H, W, device="cuda", generator=g)           # a loss on the last step's output
+    out = F.spn_iterate(feat, aff, off, T)
+    n0 = F.launch_count()
+    gf, ga, go = F.spn_iterate_backward(gl, feat, out, aff, off)
+    assert F.launch_count() - n0 == T + 1
+    gf2, ga2, go2 = F.spn_iterate_backward(2.0 * gl, feat, out, aff, off)
+    for name, a, b in (("grad_feat", gf, gf2), ("grad_aff", ga, ga2), ("grad_offset", go, go2)):
+        assert float((2.0 * a - b).abs().max()) <= 1e-6 * float(b.abs().max()), name   # (RED order of neighbouring CTAs)
+    monkeypatch.setenv("JSPSR_ITER_BWD", "steps")
+    fa, aa, oa = (t.clone().requires_grad_(True) for t in (feat, aff, off))
+    F.iterate(fa, aa, oa, T).backward(gl)
+    for name, a, b in (("grad_feat", fa.grad, gf), ("grad_aff", aa.grad, ga), ("grad_offset", oa.grad, go)):
+        assert float((a - b).abs().max()) <= 3e-5 * float(a.abs().max()), name
+    # (iii) only the first step's output carries a gradient: nothing flows through the later steps
+    gl0 = torch.zeros_like(gl)
+    gl0[0] = gl[-1]
+    monkeypatch.delenv("JSPSR_ITER_BWD")
+    gf0, ga0, go0 = F.spn_iterate_backward(gl0, feat, out, aff, off)
+    one = F.spn_backward(gl0[0], feat, aff, off, None, 0, 0.0, need_grad_init=True, need_grad_w=False)
+    assert float((ga0 - one[1]).abs().max()) <= 1e-6 * float(one[1].abs().max())
+    assert float((go0 - one[2]).abs().max()) <= 1e-6 * float(one[2].abs().max())
+    assert float((gf0 - one[0]).abs().max()) <= 3e-5 * float(one[0].abs().max())
