@@ -10,7 +10,8 @@ What it follows (reference tree = xandercai/JSPSR, paths relative to it):
 
 * ``models/components/spn.py:99-118``  PostProcessor.forward  (normalise ->
   deform_conv2d -> + scale*init)
-* ``models/LRRU.py:267-298``           Post_process_deconv.forward (same, no scale)
+* ``models/LRRU.py:267-298``           Post_process_deconv.forward (same, no scale); ``:447-498`` the four-stage
+  cascade with its input-preservation blend (``lrru_preserve_blend``)
 * ``models/components/nlspn.py:77-235`` NLSPN affinity front-end + T-step loop
 * ``models/components/spn.py:41-52,66-73`` Generator tail (the two 1x1 convolutions that
   produce weight and offset, sigmoid, zero centre pair) - pinned by
@@ -152,6 +153,14 @@ def postprocessor_forward(init, weight, offset, w9, b1, mode=NORM_RESIDUAL,
     if mode == NORM_RESIDUAL:
         out = out + np.asarray(scale, dtype=init.dtype) * init
     return out
+
+
+def lrru_preserve_blend(x, d_clear):
+    """The input-preservation blend between the stages of the LRRU cascade (models/LRRU.py:447-451, repeated at
+    460-464, 474-478, 488-492): valid pixels of `d_clear` (any channel > 0) replace the running estimate.
+    Pinned by tests/golden/cascade_lrru.npz (the reference Model's own forward, make_golden_lrru.py)."""
+    mask = (np.sum(d_clear > 0.0, axis=1, keepdims=True) > 0.0).astype(d_clear.dtype)
+    return (np.asarray(1.0, d_clear.dtype) - mask) * x + mask * d_clear
 
 
 # --------------------------------------------------------------------------

@@ -1335,3 +1335,26 @@ def test_iterate_backward_full_size_properties(jb, monkeypatch):
     assert float((ga0 - one[1]).abs().max()) <= 1e-6 * float(one[1].abs().max())
     assert float((go0 - one[2]).abs().max()) <= 1e-6 * float(one[2].abs().max())
     assert float((gf0 - one[0]).abs().max()) <= 3e-5 * float(one[0].abs().max())
+
+
+@pytest.mark.gpu
+def test_lrru_cascade_replays_the_reference_model(jb):
+    """tests/golden/cascade_lrru.npz (the reference LRRU Model's own forward, models/LRRU.py:447-498): stage by stage from
+    the captured inputs - the blend bit for bit, the propagation to 1e-5 - and as a chain that only takes d_clear and
+    the four (weight, offset) pairs and has to arrive at the model's output."""
+    import types
+    z = np.load(os.path.join(GOLDEN, "cascade_lrru.npz"))
+    F = jb.functional
+    mod = jb.Post_process_deconv(types.SimpleNamespace(kernel_size=3, dkn_residual=True)).cuda()
+    d = dev(z["d_clear"])
+    prev_ref, prev_own = d, d
+    with torch.no_grad():
+        for i in range(4):
+            blend = F.preserve_blend(prev_ref, d)
+            assert torch.equal(blend, dev(z[f"blend{i}"])), i
+            w, o = dev(z[f"weight{i}"]), dev(z[f"offset{i}"])
+            out = mod(blend, w, o)
+            assert_close(out, z[f"out{i}"].astype(np.float64), FP32_TOL, f"cascade stage {i}")
+            prev_ref = dev(z[f"out{i}"])
+            prev_own = mod(F.preserve_blend(prev_own, d), w, o)
+    assert_close(prev_own, z["final"].astype(np.float64), 4 * FP32_TOL, "cascade, chained")

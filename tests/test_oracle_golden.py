@@ -220,3 +220,24 @@ def test_fixture_provenance_is_recorded_and_uniform():
     # when torchvision is importable (build container and GPU box), it is the version the fixtures were made with, so
     # test_ref_port_matches_fixtures really re-runs the fixtures' operator
     assert torchvision.__version__.split("+")[0] == "0.26.0"
+
+
+def test_lrru_cascade_from_the_reference_model():
+    """tests/golden/cascade_lrru.npz: every tensor at the propagation boundary of the reference LRRU Model's four
+    stages (models/LRRU.py:447-498).  The blend is exact (products by 0 / 1); each stage's output follows from its
+    captured inputs through the Post_process_deconv oracle (unit w, zero b as the model initialises them)."""
+    from oracle import spn_oracle as O
+    z = np.load(os.path.join(GOLDEN, "cascade_lrru.npz"))
+    d = z["d_clear"]
+    assert 0.2 < float((d > 0).mean()) < 0.6
+    prev = d                                             # LRRU.py:397-398: lidar = d_clear = depth
+    for i in range(4):
+        assert np.array_equal(O.lrru_preserve_blend(prev, d), z[f"blend{i}"]), i
+        w9, b1 = np.ones(9, np.float64), np.zeros(1, np.float64)
+        out = O.postprocessor_forward(z[f"blend{i}"].astype(np.float64), z[f"weight{i}"].astype(np.float64),
+                                      z[f"offset{i}"].astype(np.float64), w9, b1, O.NORM_RESIDUAL, 1.0)
+        ref = z[f"out{i}"]
+        assert float(np.abs(out - ref).max()) <= 1e-5 * max(1.0, float(np.abs(ref).max())), i
+        prev = ref
+    assert np.array_equal(z["final"], z["out3"])
+    assert str(z["meta"]) == "torch 2.11.0+cu128 torchvision 0.26.0+cu128"
