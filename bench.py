@@ -689,8 +689,8 @@ def side_numbers(torch, F, device, B):
     g = timed(lambda: F.spn_backward(gout, init, weight, offset, w, 1, 1.0, need_grad_init=True))
     out["backward_with_grad_init"] = {"ms": g, "frac_of_hbm_peak": 228 * npix / (g * 1e-3) / 1e9 / peak,
                                       "note": "scatter into a block-floating-point tile of native integer shared-memory "
-                                              "atomics (exact, order-independent inside a CTA); used when the DEM carries a gradient (EDSR call site, "
-                                              "NLSPN loops the split backward does not take)"}
+                                              "atomics (exact, order-independent inside a CTA); used when the propagated DEM carries a gradient (NLSPN "
+                                              "loops the split backward does not take, callers that do not detach it)"}
     # SURVEY.md section 8d's "adversarial" set: offsets ~ N(0, 16^2), so most taps leave the staged tile and take the
     # bounds-checked global path (the price of unbounded offsets, not a configuration the reference produces)
     nf = min(B, 512)

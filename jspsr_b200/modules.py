@@ -75,11 +75,13 @@ def generator_postprocess(generator: nn.Module, postprocessor: nn.Module, dem, c
     The weight/offset tensors never exist in inference; with autograd they are written once by the fused kernel
     and consumed by the fused backward.
 
-    `detach_dem` selects the call site being replaced:
-      True  (default) models/JSPSR.py:372-375 - `dem = dem.detach()` BEFORE the Generator: no gradient reaches `dem`,
-            neither through the Generator's convd1 nor through the propagation;
-      False models/EDSR.py:133-134 - `dem` is not detached at all: it receives the gradient through the Generator body
-            AND the propagation's grad_init.
+    `detach_dem`:
+      True  (default) what both reference call sites do - models/JSPSR.py:372 `dem = dem.detach()` BEFORE the
+            Generator, models/EDSR.py:122-123 `x_copy = x.clone().detach(); dem = x_copy[:, 0:1]`: no gradient reaches
+            `dem`, neither through the Generator's convd1 nor through the propagation;
+      False for a caller whose `dem` carries a gradient (the LRRU-style cascade without its `.detach()`, NLSPN-style
+            refinement of a predicted DEM): it then receives the gradient through the Generator body AND the
+            propagation's grad_init.
     `init_dem` overrides the DEM the propagation starts from (used as given, with its own autograd history)."""
     if detach_dem:
         dem = dem.detach()
