@@ -819,8 +819,9 @@ def test_generator_postprocess_drop_in(jb):
         assert_close(out, ref.detach().double().cpu().numpy(), FP32_TOL, "out")
         for n, p in list(gen.named_parameters()) + list(pp.named_parameters()):
             assert_close(fused[n], p.grad.double().cpu().numpy(), 5 * FP32_TOL, "grad of " + n, gout=gout)
-        # the two call sites: models/JSPSR.py:372 detaches the DEM before the Generator (no gradient reaches it at all),
-        # models/EDSR.py:133-134 does not detach it (gradient through the Generator body AND the propagation)
+        # both reference call sites detach the DEM before the Generator (models/JSPSR.py:372; models/EDSR.py:122-123 through
+        # x.clone().detach()): no gradient reaches it at all.  detach_dem=False is for callers whose DEM carries one:
+        # it then flows through the Generator body AND the propagation
         dem_j = dem.clone().requires_grad_()
         jspsr_b200.generator_postprocess(gen, pp, dem_j, ctx).backward(gout)
         assert dem_j.grad is None
@@ -831,7 +832,7 @@ def test_generator_postprocess_drop_in(jb):
         feature = gen.block(gen.conv(torch.cat((gen.convd2(gen.convd1(dem_r)), gen.convf2(gen.convf1(ctx))), 1)))
         weight, offset = gen.tail(feature)
         pp(dem_r, weight, offset).backward(gout)
-        assert_close(dem_e.grad, dem_r.grad.double().cpu().numpy(), 5 * FP32_TOL, "EDSR variant: grad of dem")
+        assert_close(dem_e.grad, dem_r.grad.double().cpu().numpy(), 5 * FP32_TOL, "detach_dem=False: grad of dem")
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     from jspsr_b200 import functional as F
