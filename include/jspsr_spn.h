@@ -38,7 +38,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define JSPSR_SPN_VERSION 106 /* major*100 + minor */
+#define JSPSR_SPN_VERSION 107 /* major*100 + minor */
 
 typedef enum {
     JSPSR_OK = 0,

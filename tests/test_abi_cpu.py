@@ -76,7 +76,7 @@ def test_peer_argument_validation_needs_no_gpu(lib):
 
 def test_version_and_workspace(lib):
     h = lib.lib()
-    assert h.jspsr_version() == 106
+    assert h.jspsr_version() == 107
     assert 64 <= h.jspsr_spn_workspace_bytes() <= 4096
     assert h.jspsr_spn_host_scratch_bytes(2, 128, 128, 0) >= 2 * 2 * 128 * 128 * 4 * 29
 
