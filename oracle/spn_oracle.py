@@ -328,6 +328,26 @@ def nlspn_propagate(feat_init, offset, aff, prop_time, feat_fix=None, preserve_i
     return feat, feats
 
 
+def nlspn_propagate_backward(grad_list, feat_init, feats, offset, aff):
+    """Gradient of the loop above (no preserve_input) w.r.t. feat_init, aff and offset, given the gradient of every
+    step's output: what autograd makes of nlspn.py:222-235 - step t receives grad_list[t] plus what step t + 1 sent
+    back through its own input, and the gradients of the shared (aff, offset) add up over the steps.
+    Checked against central differences in tests/test_oracle_golden.py."""
+    ones = np.ones(K, dtype=feat_init.dtype)
+    T = len(feats)
+    carry = None
+    grad_aff = np.zeros_like(aff)
+    grad_offset = np.zeros_like(offset)
+    for t in range(T - 1, -1, -1):
+        g = grad_list[t] if carry is None else grad_list[t] + carry
+        src = feat_init if t == 0 else feats[t - 1]
+        r = postprocessor_backward(g, src, aff, offset, ones, NORM_NONE, 0.0, need_grad_init=True)
+        carry = r["grad_init"]
+        grad_aff = grad_aff + r["grad_weight"]
+        grad_offset = grad_offset + r["grad_offset"]
+    return carry, grad_aff, grad_offset
+
+
 # --------------------------------------------------------------------------
 # consumer arithmetic used for the end-to-end gate (evaluation/metrics.py:147-199,
 # 361-396; data/data_utils.py:441-457)

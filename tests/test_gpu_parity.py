@@ -1359,3 +1359,31 @@ def test_lrru_cascade_replays_the_reference_model(jb):
             prev_ref = dev(z[f"out{i}"])
             prev_own = mod(F.preserve_blend(prev_own, d), w, o)
     assert_close(prev_own, z["final"].astype(np.float64), 4 * FP32_TOL, "cascade, chained")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,T,sigma", [(2, 20, 36, 4, 1.5), (1, 33, 130, 3, 5.0), (1, 128, 128, 6, 1.5)])
+def test_iterate_backward_split_vs_oracle(jb, monkeypatch, B, H, W, T, sigma):
+    """The split loop backward against the fp64 oracle of the loop's gradient (oracle.nlspn_propagate_backward, itself
+    held to central differences on the CPU): every step's output carries a gradient.  Inputs are chosen as in the other
+    gradient tests: sampling positions at least 1e-3 away from integer coordinates, where the derivative jumps."""
+    from oracle import spn_oracle as O
+    F = jb.functional
+    monkeypatch.setenv("JSPSR_ITER_BWD", "split")
+    rng = np.random.default_rng(40 + T)
+    feat = rng.random((B, 1, H, W)).astype(np.float32)
+    aff = (0.2 * rng.normal(size=(B, 9, H, W))).astype(np.float32)
+    off = np.clip(sigma * rng.normal(size=(B, 18, H, W)), -20, 20).astype(np.float32)
+    frac = off - np.floor(off)
+    off = np.where((frac < 1e-3) | (frac > 1 - 1e-3), np.floor(off) + 0.5, off).astype(np.float32)
+    off[:, 8:10] = 0.0
+    gl = rng.normal(size=(T, B, 1, H, W)).astype(np.float32)
+    f64 = lambda a: a.astype(np.float64)
+    _, feats = O.nlspn_propagate(f64(feat), f64(off), f64(aff), T)
+    gf, ga, go = O.nlspn_propagate_backward(f64(gl), f64(feat), feats, f64(off), f64(aff))
+    out = F.spn_iterate(dev(feat), dev(aff), dev(off), T)
+    assert_close(out[-1], feats[-1], FP32_TOL, "loop forward")
+    d_gf, d_ga, d_go = F.spn_iterate_backward(dev(gl), dev(feat), out, dev(aff), dev(off))
+    assert_close(d_gf, gf, 2 * FP32_TOL, "grad_feat", gout=gl)
+    assert_close(d_ga, ga, 2 * FP32_TOL, "grad_aff", gout=gl)
+    assert_close(d_go, go, 2 * FP32_TOL, "grad_offset", gout=gl)

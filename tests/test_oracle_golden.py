@@ -241,3 +241,30 @@ def test_lrru_cascade_from_the_reference_model():
         prev = ref
     assert np.array_equal(z["final"], z["out3"])
     assert str(z["meta"]) == "torch 2.11.0+cu128 torchvision 0.26.0+cu128"
+
+
+def test_loop_backward_is_gradient_of_the_loop():
+    """nlspn_propagate_backward against central differences of nlspn_propagate in fp64: a loss that touches every
+    step's output, offsets small enough that no tap sits on an integer position within the step."""
+    rng = np.random.default_rng(7)
+    B, H, W, T = 1, 6, 7, 3
+    feat = rng.random((B, 1, H, W))
+    aff = 0.2 * rng.normal(size=(B, 9, H, W))
+    offset = rng.normal(0, 1.2, (B, 18, H, W))
+    gl = rng.normal(size=(T, B, 1, H, W))
+
+    def loss(f_, a_, o_):
+        _, fs = O.nlspn_propagate(f_, o_, a_, T)
+        return sum(float((fs[t] * gl[t]).sum()) for t in range(T))
+    _, feats = O.nlspn_propagate(feat, offset, aff, T)
+    gf, ga, go = O.nlspn_propagate_backward(gl, feat, feats, offset, aff)
+    eps = 1e-6
+    for name, arr, grad in (("feat", feat, gf), ("aff", aff, ga), ("offset", offset, go)):
+        for _ in range(10):
+            ix = tuple(rng.integers(0, s_) for s_ in arr.shape)
+            ap, am = arr.copy(), arr.copy()
+            ap[ix] += eps; am[ix] -= eps
+            args_p = dict(feat=feat, aff=aff, offset=offset); args_m = dict(args_p)
+            args_p[name], args_m[name] = ap, am
+            num = (loss(args_p["feat"], args_p["aff"], args_p["offset"]) - loss(args_m["feat"], args_m["aff"], args_m["offset"])) / (2 * eps)
+            assert abs(num - grad[ix]) < 2e-6 * max(1, abs(num)), (name, ix, num, grad[ix])
