@@ -110,3 +110,38 @@ def test_generator_tail_inside_the_reference_model(jb):
     assert_close(conv_b.grad, ref_cb, 2 * FP32_TOL, "grad_conv_b", gout=gout)
     assert_close(w.grad, z["ref_grad_w"], 2 * FP32_TOL, "grad_w", gout=gout)
     assert_close(b.grad, z["ref_grad_b"], 2 * FP32_TOL, "grad_b", gout=gout)
+
+
+def test_edsr_call_site_inside_the_reference_model(jb):
+    """tests/golden/edsr_spn.npz (make_golden_edsr.py): models/EDSR.py:121-134 captured inside the reference's own
+    EDSR(spn=True) run - `post_layer` = PostProcessor(3, True) behind a Generator with bc = 16, i.e. the fused tail at
+    C = 64 feature channels (two CTAs per SM, the other tcgen05 instantiation than the JSPSR configs' C = 128)."""
+    from jspsr_b200 import functional as F
+    z = np.load(os.path.join(GOLDEN, "edsr_spn.npz"))
+    gout = z["ref_grad_out"]
+    pp = _postprocessor(jb, z)
+    weight, offset = dev(z["in_weight"]).requires_grad_(), dev(z["in_offset"]).requires_grad_()
+    out = pp(dev(z["in_dem"]), weight, offset)
+    assert_close(out, z["ref_out"], FP32_TOL, "post_layer: out vs the reference EDSR's output")
+    out.backward(dev(gout))
+    assert_close(weight.grad, z["ref_grad_weight"], FP32_TOL, "grad_weight", gout=gout)
+    assert_close(offset.grad, z["ref_grad_offset"], FP32_TOL, "grad_offset", gout=gout)
+    assert_close(pp.w.grad, z["ref_grad_w"], FP32_TOL, "grad_w", gout=gout)
+    assert_close(pp.b.grad, z["ref_grad_b"], FP32_TOL, "grad_b", gout=gout)
+
+    C = z["in_feature"].shape[1]
+    assert C == 64
+    feature = dev(z["in_feature"]).requires_grad_()
+    conv_w = dev(np.concatenate([z["in_conv_weight_w"].reshape(9, C), z["in_conv_offset_w"].reshape(16, C)])).requires_grad_()
+    conv_b = dev(np.concatenate([z["in_conv_weight_b"], z["in_conv_offset_b"]])).requires_grad_()
+    w, b = dev(z["in_w"]).requires_grad_(), dev(z["in_b"]).requires_grad_()
+    fused = F.gen_propagate(dev(z["in_dem"]), feature, conv_w, conv_b, w, b, 1, 1.0)
+    assert_close(fused, z["ref_out"], FP32_TOL, "fused tail (C = 64): out vs the reference EDSR's output")
+    fused.backward(dev(gout))
+    ref_cw = np.concatenate([z["ref_grad_conv_weight_w"].reshape(9, C), z["ref_grad_conv_offset_w"].reshape(16, C)])
+    ref_cb = np.concatenate([z["ref_grad_conv_weight_b"], z["ref_grad_conv_offset_b"]])
+    assert_close(feature.grad, z["ref_grad_feature"], 2 * FP32_TOL, "grad_feature", gout=gout)
+    assert_close(conv_w.grad, ref_cw, 2 * FP32_TOL, "grad_conv_w", gout=gout)
+    assert_close(conv_b.grad, ref_cb, 2 * FP32_TOL, "grad_conv_b", gout=gout)
+    assert_close(w.grad, z["ref_grad_w"], 2 * FP32_TOL, "grad_w", gout=gout)
+    assert_close(b.grad, z["ref_grad_b"], 2 * FP32_TOL, "grad_b", gout=gout)

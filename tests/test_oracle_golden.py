@@ -268,3 +268,28 @@ def test_loop_backward_is_gradient_of_the_loop():
             args_p[name], args_m[name] = ap, am
             num = (loss(args_p["feat"], args_p["aff"], args_p["offset"]) - loss(args_m["feat"], args_m["aff"], args_m["offset"])) / (2 * eps)
             assert abs(num - grad[ix]) < 2e-6 * max(1, abs(num)), (name, ix, num, grad[ix])
+
+
+def test_oracle_matches_the_reference_edsr_run():
+    """tests/golden/edsr_spn.npz (make_golden_edsr.py): the third call site, models/EDSR.py:121-134 - `post_layer`
+    behind a Generator with 64 feature channels - captured inside the reference's own EDSR(spn=True) run with its
+    loss gradient; the Generator tail (spn.py:41-52,66-73) from the captured feature as well."""
+    from oracle import c_oracle as C
+    C.build()
+    z = np.load(os.path.join(GOLDEN, "edsr_spn.npz"))
+    assert str(z["meta"]) == "torch 2.11.0+cu128 torchvision 0.26.0+cu128"
+    assert bool(z["residual"]) and float(z["scale"]) == 1.0 and z["in_feature"].shape[1] == 64
+    w9, b1 = z["in_w"].reshape(9), z["in_b"]
+    out = C.forward(z["in_dem"], z["in_weight"], z["in_offset"], w9, b1, 1, 1.0)
+    assert np.abs(out - z["ref_out"]).max() <= 1e-5 * np.abs(z["ref_out"]).max()
+    g = C.backward(z["ref_grad_out"], z["in_dem"], z["in_weight"], z["in_offset"], w9, 1, 1.0, need_grad_init=False)
+    gmax = np.abs(z["ref_grad_out"]).max()
+    for k in ("grad_weight", "grad_offset", "grad_w", "grad_b"):
+        ref = z["ref_" + k].reshape(np.asarray(g[k]).shape)
+        floor = 1.2e-7 * gmax * (np.sqrt(z["ref_grad_out"].size) if k in ("grad_w", "grad_b") else 1.0)
+        assert np.abs(g[k] - ref).max() <= 1e-5 * np.abs(ref).max() + floor, k
+    f64 = lambda a: a.astype(np.float64)
+    weight, offset = O.generator_tail(f64(z["in_feature"]), f64(z["in_conv_weight_w"]), f64(z["in_conv_weight_b"]),
+                                      f64(z["in_conv_offset_w"]), f64(z["in_conv_offset_b"]))
+    assert np.abs(weight - z["in_weight"]).max() <= 2e-6 and np.abs(offset - z["in_offset"]).max() <= 2e-5
+    assert np.all(offset[:, 8:10] == 0)
