@@ -77,6 +77,39 @@ def test_installs_into_the_reference_model():
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree only exists in the build container")
+def test_installs_into_the_reference_edsr_and_lrru_models():
+    """The other two construction sites: models/EDSR.py:107 `self.post_layer = PostProcessor(3, True)` and
+    models/LRRU.py:399 `self.Post_process = Post_process_deconv(args)` - the replacement modules leave the models'
+    state_dict (keys, shapes) as the reference wrote it, so its checkpoints load."""
+    import types
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from models.EDSR import EDSR
+    from models.LRRU import Model as LRRU
+    import jspsr_b200 as jb
+    edsr = EDSR(in_channels=4, out_channels=1, n_resblocks=2, n_features=32, scale=1, spn=True)   # common_config.py:20-38
+    ref_keys = {k: tuple(v.shape) for k, v in edsr.state_dict().items()}
+    ref_pp = edsr.post_layer
+    edsr.post_layer = jb.PostProcessor(3, True)
+    assert {k: tuple(v.shape) for k, v in edsr.state_dict().items()} == ref_keys
+    assert (edsr.post_layer.residual, edsr.post_layer.scale) == (ref_pp.residual, ref_pp.scale)
+    edsr.post_layer.load_state_dict(ref_pp.state_dict())
+    assert [n for n, _ in edsr.named_parameters() if n.startswith("post_layer")] == ["post_layer.w", "post_layer.b"]
+
+    args = types.SimpleNamespace(input_channels={"lr_dem": 1, "image": 3}, output_channels=1, kernel_size=3, bc=4,
+                                 prob=1.0, dkn_residual=True)                                       # common_config.py:57-68
+    lrru = LRRU(args)
+    ref_keys = {k: tuple(v.shape) for k, v in lrru.state_dict().items()}
+    ref_post = lrru.Post_process
+    lrru.Post_process = jb.Post_process_deconv(args)
+    assert {k: tuple(v.shape) for k, v in lrru.state_dict().items()} == ref_keys
+    assert lrru.Post_process.dkn_residual == ref_post.dkn_residual
+    lrru.Post_process.load_state_dict(ref_post.state_dict())
+    assert [n for n, _ in lrru.named_parameters() if n.startswith("Post_process")] == ["Post_process.w", "Post_process.b"]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree only exists in the build container")
 def test_generator_postprocess_matches_the_reference_generators_structure(monkeypatch):
     """jspsr_b200.generator_postprocess drives the reference's OWN Generator (models/components/spn.py:8-75): every
     sub-module it touches must exist there with the shapes the fused kernel expects, its body up to `block` must be
